@@ -1,0 +1,199 @@
+"""Deterministic synthetic broadcast-FM captures (stereo + 19 kHz pilot + 57 kHz RDS) as rtl-sdr u8 IQ.
+
+This is the workload generator of SURVEY.md section 8(d): the reference ships no sample capture, so
+every parity test and the benchmark use this recipe.  Two back ends share the same formulas:
+
+* ``synth_u8_numpy``  - float64 numpy, bit-reproducible from the seed; used by tests and the oracle.
+* ``synth_u8_torch``  - the same maths on a torch device, used by ``bench.py`` to fill HBM with many
+  distinct streams quickly (different RNG, so not byte-identical to the numpy version).
+
+Signal (Fs = 1.024 MS/s, the rate hard-wired in the reference, broadcast_fm_demod.cpp:62-72):
+
+    mpx(t) = 0.40*(L+R)/1.4 + 0.10*sin(wp t + p0) + 0.40*(L-R)/1.4*sin(2(wp t + p0))
+           + 0.06*rds(t)*sin(3(wp t + p0))                                   wp = 2 pi 19 kHz
+    iq(t)  = A*exp(j*(2 pi 75e3 * cumsum(mpx)/Fs + 2 pi f_off t)) + complex AWGN at `snr_db`
+    u8     = clip(round(127 + iq), 0, 255), I then Q interleaved (what App::Run expects,
+             src/app.cpp:56-65)
+
+RDS (EN 50067): groups alternate 0A (PI, PTY, one PS segment, AF pair) and 2A (one RadioText
+segment); each 26-bit block is 16 data bits + (CRC-10 xor offset word), MSB first; bits are
+differentially encoded and sent as biphase chips at 2375 chip/s, each chip shaped by a Hann pulse
+of one chip length.
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+FS_BASEBAND = 1_024_000
+F_PILOT = 19_000.0
+F_DEVIATION = 75_000.0
+RDS_CHIP_RATE = 2375.0  # = 57000/24, two chips per 1187.5 bit/s data bit
+
+# rds_constants.h:15-28 (EN 50067 clause 2.3 / annex A)
+RDS_CRC10_POLY_FULL = 0b10110111001  # x^10 + x^8 + x^7 + x^5 + x^4 + x^3 + 1
+RDS_OFFSET = {"A": 0b0011111100, "B": 0b0110011000, "C": 0b0101101000, "C1": 0b1101010000, "D": 0b0110110100}
+
+
+@dataclasses.dataclass
+class StreamParams:
+    seed: int = 0
+    pi_code: int = 0x1234
+    pty: int = 10
+    ps: str = "B200-FM!"
+    radiotext: str = "Blackwell B200 native FM stereo + RDS demodulator test signal....."
+    af_pair: tuple = (0x10, 0x20)
+    snr_db: float = 40.0
+    amplitude: float = 100.0
+    pilot_phase: float = 0.0      # radians
+    f_offset_hz: float = 0.0      # carrier (tuning) offset
+    tones_left: tuple = ((1000.0, 0.5), (3500.0, 0.2))
+    tones_right: tuple = ((1700.0, 0.5), (5200.0, 0.2))
+
+    @staticmethod
+    def for_stream(s: int) -> "StreamParams":
+        """Per-stream variation of config 3: seed s, PI 0x1000+s, pilot phase,
+        carrier offset within +-2 kHz and SNR within 30..50 dB all derived from s."""
+        rng = np.random.default_rng(1_000_003 * (s + 1))
+        ps = f"S{s:05d}FM"[:8]
+        return StreamParams(
+            seed=s, pi_code=(0x1000 + s) & 0xFFFF, pty=(s % 31) + 1, ps=ps,
+            radiotext=(f"stream {s:05d} on B200 " * 4)[:64],
+            snr_db=float(rng.uniform(30.0, 50.0)),
+            pilot_phase=float(rng.uniform(0.0, 2 * np.pi)),
+            f_offset_hz=float(rng.uniform(-2000.0, 2000.0)),
+        )
+
+
+def crc10(data16: int) -> int:
+    """Remainder of data16 * x^10 modulo g(x) (EN 50067 clause 2.3)."""
+    reg = data16 << 10
+    for bit in range(25, 9, -1):
+        if reg & (1 << bit):
+            reg ^= RDS_CRC10_POLY_FULL << (bit - 10)
+    return reg & 0x3FF
+
+
+def rds_block(data16: int, offset_name: str) -> int:
+    return ((data16 & 0xFFFF) << 10) | (crc10(data16 & 0xFFFF) ^ RDS_OFFSET[offset_name])
+
+
+def rds_group_words(p: StreamParams, index: int) -> list[int]:
+    """The four 16-bit data words of the index-th transmitted group (0A and 2A alternate)."""
+    k = index // 2
+    if index % 2 == 0:
+        seg = k % 4
+        b = (0 << 12) | (0 << 11) | (0 << 10) | ((p.pty & 31) << 5) | (0 << 4) | (1 << 3) | (0 << 2) | seg
+        c = ((p.af_pair[0] & 0xFF) << 8) | (p.af_pair[1] & 0xFF)
+        ps = p.ps.ljust(8)[:8].encode("latin-1")
+        d = (ps[2 * seg] << 8) | ps[2 * seg + 1]
+    else:
+        seg = k % 16
+        b = (2 << 12) | (0 << 11) | (0 << 10) | ((p.pty & 31) << 5) | (0 << 4) | seg
+        rt = p.radiotext.ljust(64)[:64].encode("latin-1")
+        c = (rt[4 * seg] << 8) | rt[4 * seg + 1]
+        d = (rt[4 * seg + 2] << 8) | rt[4 * seg + 3]
+    return [p.pi_code & 0xFFFF, b, c, d]
+
+
+def rds_bits(p: StreamParams, n_bits: int) -> np.ndarray:
+    """First n_bits of the (un-encoded) RDS bit stream, MSB first per 26-bit block."""
+    n_groups = (n_bits + 103) // 104
+    out = np.zeros(n_groups * 104, dtype=np.uint8)
+    pos = 0
+    for g in range(n_groups):
+        for word, name in zip(rds_group_words(p, g), ("A", "B", "C", "D")):
+            blk = rds_block(word, name)
+            for bit in range(25, -1, -1):
+                out[pos] = (blk >> bit) & 1
+                pos += 1
+    return out[:n_bits]
+
+
+def rds_chips(p: StreamParams, n_chips: int) -> np.ndarray:
+    """Differentially encoded biphase chips (+-1), two per data bit."""
+    n_bits = (n_chips + 1) // 2
+    b = rds_bits(p, n_bits)
+    d = np.bitwise_xor.accumulate(b)            # d[n] = b[n] ^ d[n-1], d[-1] = 0
+    sym = d.astype(np.float64) * 2.0 - 1.0      # 1 -> +1, 0 -> -1
+    chips = np.empty(n_bits * 2, dtype=np.float64)
+    chips[0::2] = sym
+    chips[1::2] = -sym
+    return chips[:n_chips]
+
+
+def _audio(t, tones, xp):
+    y = 0.0
+    for f, a in tones:
+        y = y + a * xp.sin(2 * np.pi * f * t)
+    return y
+
+
+def synth_u8_numpy(n_samples: int, p: StreamParams | None = None) -> np.ndarray:
+    """uint8 array of length 2*n_samples (I,Q interleaved)."""
+    p = p or StreamParams()
+    fs = float(FS_BASEBAND)
+    n = np.arange(n_samples, dtype=np.float64)
+    t = n / fs
+    left = _audio(t, p.tones_left, np)
+    right = _audio(t, p.tones_right, np)
+    wp = 2 * np.pi * F_PILOT * t + p.pilot_phase
+    n_chips = int(np.ceil(n_samples * RDS_CHIP_RATE / fs)) + 2
+    chips = rds_chips(p, n_chips)
+    u = t * RDS_CHIP_RATE
+    ci = np.floor(u).astype(np.int64)
+    rds = chips[ci] * np.sin(np.pi * (u - ci)) ** 2
+    mpx = (0.40 * (left + right) / 1.4 + 0.10 * np.sin(wp)
+           + 0.40 * (left - right) / 1.4 * np.sin(2 * wp) + 0.06 * rds * np.sin(3 * wp))
+    phi = 2 * np.pi * F_DEVIATION * np.cumsum(mpx) / fs + 2 * np.pi * p.f_offset_hz * t
+    rng = np.random.default_rng(p.seed)
+    sigma = p.amplitude * 10.0 ** (-p.snr_db / 20.0) * np.sqrt(0.5)
+    noise = rng.standard_normal((n_samples, 2)) * sigma
+    iq = np.empty((n_samples, 2), dtype=np.float64)
+    iq[:, 0] = p.amplitude * np.cos(phi) + noise[:, 0]
+    iq[:, 1] = p.amplitude * np.sin(phi) + noise[:, 1]
+    return np.clip(np.rint(127.0 + iq), 0, 255).astype(np.uint8).reshape(-1)
+
+
+def synth_u8_torch(n_samples: int, params: list[StreamParams], device, out=None, sample_offset: int = 0):
+    """torch.uint8 tensor [len(params), 2*n_samples] on `device`; one row per stream.
+
+    `sample_offset` lets the caller generate a long capture in consecutive pieces: piece k covers
+    samples [sample_offset, sample_offset + n_samples) with continuous phase (the FM phase
+    integral is restarted per piece from its exact closed form for the tones and pilot, and the
+    RDS term is small enough (6 %) that a per-piece restart of its integral is not used: instead
+    the cumulative sum is carried by the caller through `synth_u8_torch.carry`)."""
+    import torch
+    fs = float(FS_BASEBAND)
+    S = len(params)
+    dev = torch.device(device)
+    n = torch.arange(sample_offset, sample_offset + n_samples, dtype=torch.float64, device=dev)
+    t = n / fs
+    if out is None:
+        out = torch.empty((S, 2 * n_samples), dtype=torch.uint8, device=dev)
+    n_chips_total = int(np.ceil((sample_offset + n_samples) * RDS_CHIP_RATE / fs)) + 2
+    u = t * RDS_CHIP_RATE
+    ci = torch.floor(u).to(torch.int64)
+    shape = torch.sin(np.pi * (u - ci)) ** 2
+    carry = getattr(synth_u8_torch, "_carry", None)
+    if carry is None or sample_offset == 0 or carry.shape[0] != S or carry.device != dev:
+        carry = torch.zeros(S, dtype=torch.float64, device=dev)
+    for s, p in enumerate(params):
+        left = _audio(t, p.tones_left, torch)
+        right = _audio(t, p.tones_right, torch)
+        wp = 2 * np.pi * F_PILOT * t + p.pilot_phase
+        chips = torch.from_numpy(rds_chips(p, n_chips_total)).to(dev)
+        rds = chips[ci] * shape
+        mpx = (0.40 * (left + right) / 1.4 + 0.10 * torch.sin(wp)
+               + 0.40 * (left - right) / 1.4 * torch.sin(2 * wp) + 0.06 * rds * torch.sin(3 * wp))
+        csum = torch.cumsum(mpx, 0) + carry[s]
+        carry[s] = csum[-1]
+        phi = 2 * np.pi * F_DEVIATION * csum / fs + 2 * np.pi * p.f_offset_hz * t
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(p.seed * 7919 + sample_offset)
+        sigma = p.amplitude * 10.0 ** (-p.snr_db / 20.0) * np.sqrt(0.5)
+        noise = torch.randn((n_samples, 2), generator=gen, device=dev, dtype=torch.float32) * sigma
+        iq = torch.stack((p.amplitude * torch.cos(phi), p.amplitude * torch.sin(phi)), dim=1).to(torch.float32) + noise
+        out[s] = torch.clamp(torch.round(127.0 + iq), 0, 255).to(torch.uint8).reshape(-1)
+    synth_u8_torch._carry = carry
+    return out
