@@ -1,0 +1,417 @@
+"""ctypes binding of the C-ABI (include/fmgpu.h) plus thin host-side classes.
+
+``FMDemod`` mirrors the reference's ``Broadcast_FM_Demod`` block interface
+(src/fm_demod/broadcast_fm_demod.h:228-299) for a batch of independent streams;
+``RDSDecoder`` is the host RDS bit path; ``PolyphaseDownsampler`` and the ``create_*`` designers
+mirror src/dsp.  There is no CPU fallback: loading fails loudly if libfmgpu.so is missing and every
+compute call fails if no sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfmgpu.so")
+
+
+class FMGPUError(RuntimeError):
+    pass
+
+
+class Buf(enum.IntEnum):
+    AUDIO_OUT = 0
+    RDS_PRED_SYM = 1
+    RDS_SYM_COUNT = 2
+    FM_DEMOD = 3
+    FM_OUT_IQ = 4
+    PILOT = 5
+    PLL_DT = 6
+    PLL = 7
+    PLL_RAW_PHASE_ERROR = 8
+    PLL_LPF_PHASE_ERROR = 9
+    AUDIO_LPR = 10
+    AUDIO_LMR = 11
+    RDS = 12
+    RDS_RAW_SYM = 13
+    BPSK_PLL_SYM = 14
+    BPSK_ZCD = 15
+    BPSK_INT_DUMP_TRIGGER = 16
+    BPSK_TED_RAW_PHASE_ERROR = 17
+    BPSK_TED_PI_PHASE_ERROR = 18
+    BPSK_PLL_RAW_PHASE_ERROR = 19
+    BPSK_PLL_PI_PHASE_ERROR = 20
+    BPSK_INT_DUMP_FILTER = 21
+
+
+_BUF_DTYPE = {
+    Buf.AUDIO_OUT: (np.float32, 2), Buf.RDS_PRED_SYM: (np.float32, 1), Buf.RDS_SYM_COUNT: (np.int32, 1),
+    Buf.FM_DEMOD: (np.float32, 1), Buf.FM_OUT_IQ: (np.complex64, 1), Buf.PILOT: (np.complex64, 1),
+    Buf.PLL_DT: (np.float32, 1), Buf.PLL: (np.complex64, 1), Buf.PLL_RAW_PHASE_ERROR: (np.float32, 1),
+    Buf.PLL_LPF_PHASE_ERROR: (np.float32, 1), Buf.AUDIO_LPR: (np.float32, 1), Buf.AUDIO_LMR: (np.float32, 1),
+    Buf.RDS: (np.complex64, 1), Buf.RDS_RAW_SYM: (np.complex64, 1), Buf.BPSK_PLL_SYM: (np.complex64, 1),
+    Buf.BPSK_ZCD: (np.uint8, 1), Buf.BPSK_INT_DUMP_TRIGGER: (np.uint8, 1),
+    Buf.BPSK_TED_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_TED_PI_PHASE_ERROR: (np.float32, 1),
+    Buf.BPSK_PLL_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_PLL_PI_PHASE_ERROR: (np.float32, 1),
+    Buf.BPSK_INT_DUMP_FILTER: (np.complex64, 1),
+}
+
+
+class Scalar(enum.IntEnum):
+    AUDIO_LMR_PHASE_ERROR = 0
+    AGC_PILOT_GAIN = 1
+    AGC_RDS_GAIN = 2
+
+
+class Control(enum.IntEnum):
+    AUDIO_OUT = 0
+    AUDIO_STEREO_MIX_FACTOR = 1
+    USE_DEEMPHASIS = 2
+    DEEMPHASIS_TUS = 3
+    AUDIO_LPR_CUTOFF_HZ = 4
+    AUDIO_LMR_CUTOFF_HZ = 5
+
+
+class Filter(enum.IntEnum):
+    FM_IN = 0
+    FM_OUT = 1
+    HILBERT = 2
+    AUDIO_LPR = 3
+    AUDIO_LMR = 4
+    RDS = 5
+    DEEMPHASIS = 6
+    PEAK_PILOT = 7
+    PLL_LPF = 8
+    BPSK_TED_LPF = 9
+    BPSK_PLL_LPF = 10
+
+
+FILTER_LEN = {Filter.FM_IN: 64, Filter.FM_OUT: 64, Filter.HILBERT: 65, Filter.AUDIO_LPR: 128,
+              Filter.AUDIO_LMR: 128, Filter.RDS: 128, Filter.DEEMPHASIS: 2, Filter.PEAK_PILOT: 3,
+              Filter.PLL_LPF: 2, Filter.BPSK_TED_LPF: 2, Filter.BPSK_PLL_LPF: 2}
+FILTER_IS_IIR = {Filter.DEEMPHASIS, Filter.PEAK_PILOT, Filter.PLL_LPF, Filter.BPSK_TED_LPF, Filter.BPSK_PLL_LPF}
+
+
+class _Config(C.Structure):
+    _fields_ = [("block_size", C.c_int), ("n_streams", C.c_int), ("device", C.c_int),
+                ("keep_intermediates", C.c_int), ("pipeline_depth", C.c_int)]
+
+
+class RDSGroup(C.Structure):
+    _fields_ = [("data", C.c_uint16 * 4), ("valid", C.c_uint8 * 4), ("type", C.c_uint8 * 4)]
+
+
+# every symbol include/fmgpu.h declares; tests check the library exports all of them
+EXPORTED_SYMBOLS = [
+    "fmgpu_create", "fmgpu_destroy", "fmgpu_process_u8", "fmgpu_process_cf32", "fmgpu_enqueue_u8_device",
+    "fmgpu_enqueue_u8_host", "fmgpu_sync", "fmgpu_fetch_outputs", "fmgpu_wait_external_stream",
+    "fmgpu_signal_external_stream", "fmgpu_get_buffer", "fmgpu_get_device_buffer", "fmgpu_get_scalar",
+    "fmgpu_set_control", "fmgpu_upload_taps", "fmgpu_download_taps", "fmgpu_get_rates", "fmgpu_get_config",
+    "fmgpu_launch_count", "fmgpu_create_fir_lpf", "fmgpu_create_fir_hpf", "fmgpu_create_fir_bpf",
+    "fmgpu_create_fir_hilbert", "fmgpu_create_iir_single_pole_lpf", "fmgpu_create_iir_notch_filter",
+    "fmgpu_create_iir_peak_1_filter", "fmgpu_polyphase_ds_create", "fmgpu_polyphase_destroy",
+    "fmgpu_polyphase_get_b", "fmgpu_polyphase_ds_process", "fmgpu_rds_create", "fmgpu_rds_destroy",
+    "fmgpu_rds_push_symbols", "fmgpu_rds_n_groups", "fmgpu_rds_get_groups", "fmgpu_rds_n_bytes",
+    "fmgpu_rds_get_bytes", "fmgpu_rds_get_db", "fmgpu_last_error", "fmgpu_version",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libfmgpu.so (no fallback: raises if the CUDA extension has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FMGPUError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cs = C.c_void_p, C.c_int, C.c_size_t
+    L.fmgpu_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    L.fmgpu_destroy.argtypes = [vp]
+    L.fmgpu_destroy.restype = None
+    L.fmgpu_process_u8.argtypes = [vp, vp, cs]
+    L.fmgpu_process_cf32.argtypes = [vp, vp, cs]
+    L.fmgpu_enqueue_u8_device.argtypes = [vp, vp]
+    L.fmgpu_enqueue_u8_host.argtypes = [vp, vp]
+    L.fmgpu_sync.argtypes = [vp]
+    L.fmgpu_fetch_outputs.argtypes = [vp, ci]
+    L.fmgpu_wait_external_stream.argtypes = [vp, vp]
+    L.fmgpu_signal_external_stream.argtypes = [vp, vp]
+    L.fmgpu_get_buffer.argtypes = [vp, ci, ci, C.POINTER(vp), C.POINTER(cs)]
+    L.fmgpu_get_device_buffer.argtypes = [vp, ci, ci, C.POINTER(vp), C.POINTER(cs)]
+    L.fmgpu_get_scalar.argtypes = [vp, ci, ci, C.POINTER(C.c_float)]
+    L.fmgpu_set_control.argtypes = [vp, ci, C.c_double]
+    L.fmgpu_upload_taps.argtypes = [vp, ci, vp, vp, ci]
+    L.fmgpu_download_taps.argtypes = [vp, ci, vp, vp, ci]
+    L.fmgpu_get_rates.argtypes = [vp, C.POINTER(ci * 5)]
+    L.fmgpu_get_config.argtypes = [vp, C.POINTER(_Config)]
+    L.fmgpu_launch_count.argtypes = [vp]
+    L.fmgpu_launch_count.restype = C.c_longlong
+    for name in ("lpf", "hpf"):
+        getattr(L, f"fmgpu_create_fir_{name}").argtypes = [vp, ci, C.c_float]
+        getattr(L, f"fmgpu_create_fir_{name}").restype = None
+    L.fmgpu_create_fir_bpf.argtypes = [vp, ci, C.c_float, C.c_float]
+    L.fmgpu_create_fir_bpf.restype = None
+    L.fmgpu_create_fir_hilbert.argtypes = [vp, ci]
+    L.fmgpu_create_fir_hilbert.restype = None
+    L.fmgpu_create_iir_single_pole_lpf.argtypes = [vp, vp, C.c_float]
+    L.fmgpu_create_iir_single_pole_lpf.restype = None
+    L.fmgpu_create_iir_notch_filter.argtypes = [vp, vp, C.c_float, C.c_float]
+    L.fmgpu_create_iir_notch_filter.restype = None
+    L.fmgpu_create_iir_peak_1_filter.argtypes = [vp, vp, C.c_float, C.c_float]
+    L.fmgpu_create_iir_peak_1_filter.restype = None
+    L.fmgpu_polyphase_ds_create.argtypes = [ci, ci, ci, C.POINTER(vp)]
+    L.fmgpu_polyphase_destroy.argtypes = [vp]
+    L.fmgpu_polyphase_destroy.restype = None
+    L.fmgpu_polyphase_get_b.argtypes = [vp]
+    L.fmgpu_polyphase_get_b.restype = C.POINTER(C.c_float)
+    L.fmgpu_polyphase_ds_process.argtypes = [vp, vp, vp, ci]
+    L.fmgpu_rds_create.restype = vp
+    L.fmgpu_rds_destroy.argtypes = [vp]
+    L.fmgpu_rds_destroy.restype = None
+    L.fmgpu_rds_push_symbols.argtypes = [vp, vp, cs]
+    L.fmgpu_rds_push_symbols.restype = None
+    L.fmgpu_rds_n_groups.argtypes = [vp]
+    L.fmgpu_rds_get_groups.argtypes = [vp, C.POINTER(RDSGroup), ci]
+    L.fmgpu_rds_n_bytes.argtypes = [vp]
+    L.fmgpu_rds_get_bytes.argtypes = [vp, vp, ci]
+    L.fmgpu_rds_get_db.argtypes = [vp, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
+    L.fmgpu_rds_get_db.restype = None
+    L.fmgpu_last_error.restype = C.c_char_p
+    L.fmgpu_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise FMGPUError(f"{what} failed ({rc}): {lib().fmgpu_last_error().decode()}")
+
+
+def _ptr(x) -> int:
+    """Address of a numpy array, torch tensor (host or device) or raw int."""
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class FMDemod:
+    """A batch of `n_streams` independent broadcast-FM demodulators on one GPU.
+
+    Mirrors Broadcast_FM_Demod(block_size) / Process / the Get* getters of the reference
+    (broadcast_fm_demod.h:228-299); stream index selects the demodulator."""
+
+    def __init__(self, block_size: int = 65536, n_streams: int = 1, device: int = -1,
+                 keep_intermediates: bool = False, pipeline_depth: int = 0):
+        self.L = lib()
+        cfg = _Config(block_size, n_streams, device, int(keep_intermediates), pipeline_depth)
+        h = C.c_void_p()
+        _check(self.L.fmgpu_create(C.byref(cfg), C.byref(h)), "fmgpu_create")
+        self.h = h
+        out = _Config()
+        self.L.fmgpu_get_config(self.h, C.byref(out))
+        self.block_size, self.n_streams = out.block_size, out.n_streams
+        self.depth, self.device = out.pipeline_depth, out.device
+        self.keep_intermediates = bool(out.keep_intermediates)
+        self.blocks_enqueued = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fmgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- synchronous (host buffers) ----
+    def process_u8(self, iq) -> None:
+        """iq: uint8 [n_streams, 2*block_size] (I,Q interleaved), numpy or pinned torch CPU tensor."""
+        n = iq.size if isinstance(iq, np.ndarray) else iq.numel()
+        if n != 2 * self.block_size * self.n_streams:
+            return  # the reference silently ignores wrong-sized blocks (broadcast_fm_demod.cpp:311-313)
+        _check(self.L.fmgpu_process_u8(self.h, _ptr(iq), self.block_size), "fmgpu_process_u8")
+        self.blocks_enqueued += 1
+
+    def process_cf32(self, iq) -> None:
+        """iq: complex64 [n_streams, block_size]."""
+        n = iq.size if isinstance(iq, np.ndarray) else iq.numel()
+        if n != self.block_size * self.n_streams:
+            return
+        _check(self.L.fmgpu_process_cf32(self.h, _ptr(iq), self.block_size), "fmgpu_process_cf32")
+        self.blocks_enqueued += 1
+
+    # ---- asynchronous ----
+    def enqueue_u8_device(self, iq_dev) -> int:
+        """Queues one block whose input lives in device memory; returns the ring slot it uses."""
+        slot = self.blocks_enqueued % self.depth
+        _check(self.L.fmgpu_enqueue_u8_device(self.h, _ptr(iq_dev)), "fmgpu_enqueue_u8_device")
+        self.blocks_enqueued += 1
+        return slot
+
+    def enqueue_u8_host(self, iq_host) -> int:
+        slot = self.blocks_enqueued % self.depth
+        _check(self.L.fmgpu_enqueue_u8_host(self.h, _ptr(iq_host)), "fmgpu_enqueue_u8_host")
+        self.blocks_enqueued += 1
+        return slot
+
+    def fetch_outputs(self, slot: int) -> None:
+        _check(self.L.fmgpu_fetch_outputs(self.h, slot), "fmgpu_fetch_outputs")
+
+    def sync(self) -> None:
+        _check(self.L.fmgpu_sync(self.h), "fmgpu_sync")
+
+    def wait_external_stream(self, cuda_stream: int) -> None:
+        _check(self.L.fmgpu_wait_external_stream(self.h, cuda_stream), "fmgpu_wait_external_stream")
+
+    def signal_external_stream(self, cuda_stream: int) -> None:
+        _check(self.L.fmgpu_signal_external_stream(self.h, cuda_stream), "fmgpu_signal_external_stream")
+
+    # ---- getters ----
+    def get(self, buf: Buf, stream: int = 0) -> np.ndarray:
+        p = C.c_void_p()
+        n = C.c_size_t()
+        _check(self.L.fmgpu_get_buffer(self.h, stream, int(buf), C.byref(p), C.byref(n)), f"fmgpu_get_buffer({buf.name})")
+        dt, mult = _BUF_DTYPE[Buf(buf)]
+        dt = np.dtype(dt)
+        count = n.value * mult
+        if count == 0:
+            return np.zeros(0, dt)
+        raw = (C.c_char * (count * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(raw, dtype=dt, count=count).copy()
+
+    def device_buffer(self, buf: Buf, slot: int):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        _check(self.L.fmgpu_get_device_buffer(self.h, slot, int(buf), C.byref(p), C.byref(n)), "fmgpu_get_device_buffer")
+        return p.value, n.value
+
+    def scalar(self, which: Scalar, stream: int = 0) -> float:
+        v = C.c_float()
+        _check(self.L.fmgpu_get_scalar(self.h, stream, int(which), C.byref(v)), "fmgpu_get_scalar")
+        return float(v.value)
+
+    def set_control(self, which: Control, value: float) -> None:
+        _check(self.L.fmgpu_set_control(self.h, int(which), float(value)), "fmgpu_set_control")
+
+    def upload_taps(self, which: Filter, b, a=None) -> None:
+        b = np.ascontiguousarray(b, np.float32)
+        a = None if a is None else np.ascontiguousarray(a, np.float32)
+        _check(self.L.fmgpu_upload_taps(self.h, int(which), b.ctypes.data, None if a is None else a.ctypes.data, b.size),
+               "fmgpu_upload_taps")
+
+    def download_taps(self, which: Filter):
+        n = FILTER_LEN[Filter(which)]
+        b = np.zeros(n, np.float32)
+        a = np.zeros(n, np.float32)
+        _check(self.L.fmgpu_download_taps(self.h, int(which), b.ctypes.data, a.ctypes.data, n), "fmgpu_download_taps")
+        return (b, a) if Filter(which) in FILTER_IS_IIR else (b, None)
+
+    def rates(self) -> dict:
+        r = (C.c_int * 5)()
+        _check(self.L.fmgpu_get_rates(self.h, C.byref(r)), "fmgpu_get_rates")
+        return dict(zip(("baseband", "fm_in", "fm_out", "rds", "audio"), list(r)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.fmgpu_launch_count(self.h))
+
+
+class RDSDecoder:
+    """Host RDS bit path: soft symbols -> groups -> PI / PS / RadioText."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.fmgpu_rds_create())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fmgpu_rds_destroy(self.h)
+            self.h = None
+
+    def push_symbols(self, sym) -> None:
+        sym = np.ascontiguousarray(sym, np.float32)
+        self.L.fmgpu_rds_push_symbols(self.h, sym.ctypes.data, sym.size)
+
+    def groups(self):
+        n = self.L.fmgpu_rds_n_groups(self.h)
+        arr = (RDSGroup * max(n, 1))()
+        n = self.L.fmgpu_rds_get_groups(self.h, arr, n)
+        data = np.array([[g.data[i] for i in range(4)] for g in arr[:n]], np.uint16).reshape(n, 4)
+        valid = np.array([[g.valid[i] for i in range(4)] for g in arr[:n]], np.uint8).reshape(n, 4)
+        typ = np.array([[g.type[i] for i in range(4)] for g in arr[:n]], np.uint8).reshape(n, 4)
+        return data, valid, typ
+
+    def rds_bytes(self) -> bytes:
+        n = self.L.fmgpu_rds_n_bytes(self.h)
+        out = np.zeros(max(n, 1), np.uint8)
+        n = self.L.fmgpu_rds_get_bytes(self.h, out.ctypes.data, n)
+        return out[:n].tobytes()
+
+    def db(self) -> dict:
+        pi, pty = C.c_uint16(0), C.c_uint8(0)
+        ps, rt = C.create_string_buffer(8), C.create_string_buffer(64)
+        self.L.fmgpu_rds_get_db(self.h, C.byref(pi), ps, rt, C.byref(pty))
+        return {"pi": pi.value, "pty": pty.value, "ps": ps.raw, "rt": rt.raw}
+
+
+class PolyphaseDownsampler:
+    """dsp/polyphase_filter.h:9-87 on the GPU: PolyphaseDownsampler<T>(M, K), get_b(), process()."""
+
+    def __init__(self, M: int, K: int, is_complex: bool):
+        self.L = lib()
+        self.M, self.K, self.NN, self.is_complex = M, K, M * K, bool(is_complex)
+        h = C.c_void_p()
+        _check(self.L.fmgpu_polyphase_ds_create(M, K, int(is_complex), C.byref(h)), "fmgpu_polyphase_ds_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fmgpu_polyphase_destroy(self.h)
+            self.h = None
+
+    def get_b(self) -> np.ndarray:
+        p = self.L.fmgpu_polyphase_get_b(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.NN,))
+
+    def get_K(self) -> int:
+        return self.NN
+
+    def process(self, x: np.ndarray, n_out: int) -> np.ndarray:
+        dt = np.complex64 if self.is_complex else np.float32
+        x = np.ascontiguousarray(x, dt)
+        assert x.size == n_out * self.M
+        y = np.zeros(n_out, dt)
+        _check(self.L.fmgpu_polyphase_ds_process(self.h, x.ctypes.data, y.ctypes.data, n_out), "fmgpu_polyphase_ds_process")
+        return y
+
+
+def _designer(name, n_b, n_a, *args):
+    b = np.zeros(n_b, np.float32)
+    if n_a:
+        a = np.zeros(n_a, np.float32)
+        getattr(lib(), name)(b.ctypes.data, a.ctypes.data, *args)
+        return b, a
+    getattr(lib(), name)(b.ctypes.data, *args)
+    return b
+
+
+def create_fir_lpf(N: int, k: float): return _designer("fmgpu_create_fir_lpf", N, 0, N, k)
+def create_fir_hpf(N: int, k: float): return _designer("fmgpu_create_fir_hpf", N, 0, N, k)
+def create_fir_bpf(N: int, k1: float, k2: float): return _designer("fmgpu_create_fir_bpf", N, 0, N, k1, k2)
+def create_fir_hilbert(N: int): return _designer("fmgpu_create_fir_hilbert", N, 0, N)
+def create_iir_single_pole_lpf(k: float): return _designer("fmgpu_create_iir_single_pole_lpf", 2, 2, k)
+def create_iir_notch_filter(k: float, r: float): return _designer("fmgpu_create_iir_notch_filter", 3, 3, k, r)
+def create_iir_peak_1_filter(k: float, r: float): return _designer("fmgpu_create_iir_peak_1_filter", 3, 3, k, r)

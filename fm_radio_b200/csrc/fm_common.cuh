@@ -1,0 +1,159 @@
+// Shared definitions of the sm_100a demodulation kernels.
+//
+// Stage map (one CUDA stream per stage, see fmgpu.cu):
+//   K1  k1_fir4_discrim  u8/cf32 IQ -> 64-tap /4 polyphase FIR -> atan2 discriminator -> fm_demod
+//   K2  k2_mpx           fm_demod -> 64-tap /2 FIR -> [deemphasis] -> 65-tap Hilbert -> fm_out_iq
+//                        -> 19 kHz peak IIR -> pilot angle (turns) + block power
+//   K3  k3_pll           per-stream pilot PLL recurrence -> pll_dt
+//   K4  k4_mix_fir       harmonic mixdown x2/x3 fused with the three 128-tap decimators, stereo mix
+//   K4b k4b_lmr_phase    per-stream L-R phase-offset update (applied to the next block)
+//   K5  k5_bpsk          per-stream RDS AGC + BPSK symbol synchroniser -> soft symbols
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fm {
+
+constexpr int K1_NN = 64;       // taps of filt_poly_ds_lpf_fm_in (broadcast_fm_demod.cpp:133-144)
+constexpr int K1_M = 4;
+constexpr int K1_R = 16;        // consecutive outputs per thread
+constexpr int K1_THREADS = 128;
+constexpr int K1_TILE = K1_R * K1_THREADS;          // 2048 outputs = 8192 IQ samples per CTA
+constexpr int K1_SEG = 16 * 8 + 4;                  // floats per 16-frame segment (+4 pad: bank skew)
+constexpr int K1_HIST = 64;                         // IQ samples of history
+
+constexpr int K2_THREADS = 256;
+constexpr int K2_R = 8;
+constexpr int K2_CH = K2_THREADS * K2_R;            // 2048 fm_out samples per chunk
+constexpr int K2_NN = 64;                           // filt_poly_ds_lpf_fm_out (:146-157)
+constexpr int K2_HILB = 65;                         // filt_hilbert_transform (:192-195)
+
+constexpr int K4_THREADS = 128;
+constexpr int K4_TS = 1024;                         // fm_out-rate samples per CTA
+constexpr int K4_NN = 128;                          // audio / rds decimator taps (:240-274)
+
+constexpr float TWO_PI_F = 6.283185307179586f;
+constexpr float INV_TWO_PI_F = 0.15915494309189535f;
+constexpr float PI_F = 3.14159265358979323846f;
+
+// dsp/simd/chebyshev_sine.h:13-41 -- sin(2 pi x) on [-0.5, 0.5]; coefficients verbatim, Horner in
+// the reference's order (the compiler contracts each step to one FFMA, as the AVX2+FMA build does).
+__device__ __forceinline__ float chebyshev_sine(float x) {
+    const float z = x * x;
+    float b = 3.20396066f;
+    b = fmaf(b, z, -14.07150173f);
+    b = fmaf(b, z, 38.50016403f);
+    b = fmaf(b, z, -67.07687378f);
+    b = fmaf(b, z, 64.83583069f);
+    b = fmaf(b, z, -25.13274193f);
+    return b * (z - 0.25f) * x;
+}
+
+// dsp/clamp.h:4-8
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+    float y = (x > lo) ? x : lo;
+    y = (y > hi) ? hi : y;
+    return y;
+}
+
+// round-half-away like std::round for |x| < 2^22 (apply_harmonic_pll.cpp:19, pll_mixer.cpp:18)
+__device__ __forceinline__ float round_half_away(float x) { return roundf(x); }
+
+struct K1Params {
+    float taps[K1_NN];          // reference memory order: b[NN-1] multiplies the newest sample
+    float discrim_gain;         // A = 0.5*Fs/(2 pi Fd) (fm_demod.cpp:36-39)
+    int n_out;                  // B/4 outputs per stream
+    int parity;                 // history ping-pong: read [parity], write [parity^1]
+    int n_streams;
+};
+
+struct K2Params {
+    float taps_fm_out[K2_NN];
+    float taps_hilbert[K2_HILB];
+    float deemph_b[2], deemph_a[2];
+    float peak_b[3], peak_a[3];
+    int use_deemph;
+    int n_out;                  // B/8 fm_out samples per stream
+    int keep;                   // write pilot (unscaled) for the debug getters
+};
+
+struct K3Params {
+    float lpf_b[2], lpf_a[2];   // filt_iir_lpf_pll_phase_error (:215-224)
+    float int_KTs;              // integrator_gain * Ts (:234)
+    float Kp;                   // proportional_gain (:429)
+    float f_center, f_gain, mixer_KTs;   // (:229-231)
+    float agc_target, agc_beta; // dsp/agc.h:9-11
+    int n;                      // B/8
+    int n_streams;
+    int keep;
+};
+
+struct K4Params {
+    float taps_lpr[K4_NN];
+    float taps_lmr[K4_NN];
+    float taps_rds[K4_NN];
+    float harmonic_lmr, harmonic_rds;
+    float stereo_mix;
+    int audio_out_mode;         // 0 LPR, 1 LMR, 2 STEREO
+    int n;                      // B/8 fm_out-rate samples per stream
+    int n_tiles;
+    int parity;
+    int n_streams;
+    int keep;
+};
+
+struct K5Params {
+    float ted_b[2], ted_a[2];
+    float pll_b[2], pll_a[2];
+    float ted_Kp, pll_Kp;
+    float int_ted_KTs, int_pll_KTs;
+    float dump_KTs;
+    float ted_KTs, ted_fcenter, ted_fgain;
+    float mixer_KTs, mixer_fgain;
+    float agc_target, agc_beta;
+    int cooldown_N;
+    int n;                      // B/64 samples per stream
+    int n_tiles_k4;             // number of power partials per stream
+    int n_streams;
+    int keep;
+};
+
+// indices into the [field][stream] SoA state arrays of the per-stream recurrences
+enum PllState { PLL_LPF_X1 = 0, PLL_LPF_Y1, PLL_INT, PLL_T, PLL_E_PREV, PLL_AGC_GAIN, PLL_STATE_N };
+enum BpskState {
+    BP_LPF_PLL_X1 = 0, BP_LPF_PLL_Y1, BP_INT_PLL, BP_MIX_T, BP_PLL_PREV_ERR,
+    BP_ZCD_XN, BP_COOLDOWN, BP_TED_YN, BP_TED_PHASE_ERR, BP_TED_PREV_ERR,
+    BP_LPF_TED_X1, BP_LPF_TED_Y1, BP_INT_TED, BP_DUMP_RE, BP_DUMP_IM, BP_AGC_GAIN, BP_STATE_N
+};
+// per-stream scalars of K2 (AoS, one CTA per stream)
+enum K2Scal { K2_DEEMPH_X1 = 0, K2_DEEMPH_Y1, K2_PK_X1R, K2_PK_X1I, K2_PK_X2R, K2_PK_X2I,
+              K2_PK_Y1R, K2_PK_Y1I, K2_PK_Y2R, K2_PK_Y2I, K2_SCAL_N = 16 };
+
+struct K5Debug {
+    float2* rds; float2* raw_sym; float2* pll_sym; uint8_t* zcd; uint8_t* dump_trig;
+    float* ted_raw; float* ted_pi; float* pll_raw; float* pll_pi; float2* dump_filter;
+};
+
+// launchers (one per .cu file)
+cudaError_t launch_k1(bool u8, const void* iq, const float2* hist_in, float2* hist_out, float* fm_demod,
+                      const K1Params& p, cudaStream_t st);
+cudaError_t launch_k2(const float* fm_demod, float* hist_demod, float* hist_out, float* scal,
+                      float2* fm_out_iq, float* theta, float* power, float2* pilot_dbg,
+                      const K2Params& p, int n_streams, cudaStream_t st);
+cudaError_t launch_k3(const float* theta, const float* power, float* state, float* pll_dt,
+                      float* dbg_raw, float* dbg_pi, const K3Params& p, cudaStream_t st);
+cudaError_t launch_k4(const float2* fm_out_iq, const float* pll_dt,
+                      const float* hist_x_in, const float2* hist_m2_in, const float2* hist_m3_in,
+                      float* hist_x_out, float2* hist_m2_out, float2* hist_m3_out,
+                      float* lmr_phase, float2* audio_out, float2* rds_out, float* est_partial,
+                      float* rds_power_partial, float* dbg_lpr, float* dbg_lmr, const K4Params& p, cudaStream_t st);
+cudaError_t launch_k5(const float2* rds_in, const float* rds_power_partial, float* state, float* pred_sym,
+                      int* sym_count, const K5Debug& d, const K5Params& p, cudaStream_t st);
+// debug-only finalisation of the GUI buffers: pilot *= gain, pll = (S(t+1/4), S(t))
+cudaError_t launch_kdbg(float2* pilot, const float* pll_state, const float* pll_dt, float2* pll_out,
+                        int n, int n_streams, cudaStream_t st);
+// stand-alone polyphase decimator (dsp/polyphase_filter.h:41-64) for the dsp API surface
+cudaError_t launch_polyphase_ds(const float* ext, const float* taps, float* y, int M, int NN, int n_out,
+                                int is_complex, cudaStream_t st);
+
+} // namespace fm

@@ -1,0 +1,702 @@
+// C-ABI implementation (include/fmgpu.h): handle, per-stream device state, the stage pipeline.
+//
+// Execution model: five stage streams per handle.  Block k of the batch flows
+//     H (host->device copy) -> A (K1, K2) -> B (K3 pilot PLL) -> C (K4, K4b) -> D (K5 BPSK) -> O (device->host)
+// through ring slot k % depth; stage X of block k+1 follows stage X of block k on the same stream
+// (all cross-block filter/loop state is owned by exactly one stage), and CUDA events order stage
+// X(k) after X-1(k) and after the last reader of the slot's buffers.  The two latency-bound
+// recurrences (K3, K5: one thread per stream) therefore overlap with the FMA-bound kernels of the
+// neighbouring blocks instead of serialising the chain.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/fmgpu.h"
+#include "fm_common.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    return fail(FMGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+struct HostTaps {
+    float fm_in[64], fm_out[64], hilbert[65], lpr[128], lmr[128], rds[128];
+    float deemph_b[2], deemph_a[2], peak_b[3], peak_a[3], pll_b[2], pll_a[2];
+    float ted_b[2], ted_a[2], bpll_b[2], bpll_a[2];
+};
+
+struct Slot {
+    uint8_t* in_u8 = nullptr;      // staged input (host-buffer path)
+    float* fm_demod = nullptr;     // [S][B/4]
+    float2* fm_out_iq = nullptr;   // [S][B/8]
+    float* theta = nullptr;        // [S][B/8]
+    float* power = nullptr;        // [S]
+    float* pll_dt = nullptr;       // [S][B/8]
+    float2* audio = nullptr;       // [S][B/32]
+    float2* rds = nullptr;         // [S][B/64] (before AGC)
+    float* est_partial = nullptr;  // [S][tiles]
+    float* rds_pw_partial = nullptr;
+    float* pred_sym = nullptr;     // [S][B/64]
+    int* sym_count = nullptr;      // [S]
+    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_O;
+};
+
+struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
+    float2* pilot = nullptr; float2* pll = nullptr; float* pll_raw = nullptr; float* pll_pi = nullptr;
+    float* lpr = nullptr; float* lmr = nullptr;
+    fm::K5Debug k5{};
+};
+
+struct HostMirror {                // pinned
+    float2* audio = nullptr; float* pred_sym = nullptr; int* sym_count = nullptr;
+};
+
+} // namespace
+
+struct fmgpu_demod {
+    fmgpu_config cfg{};
+    int B = 0, S = 0, n4 = 0, n8 = 0, n32 = 0, n64 = 0, depth = 0, k4_tiles = 0;
+    int device = 0;
+    cudaStream_t stH = nullptr, stA = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stO = nullptr;
+    std::vector<Slot> slots;
+    std::vector<HostMirror> mirrors;
+    DebugBufs dbg;
+    // per-stream state
+    float2* k1_hist[2] = { nullptr, nullptr };
+    float* k2_hist_demod = nullptr; float* k2_hist_out = nullptr; float* k2_scal = nullptr;
+    float* pll_state = nullptr;
+    float* k4_hist_x[2] = { nullptr, nullptr };
+    float2* k4_hist_m2[2] = { nullptr, nullptr };
+    float2* k4_hist_m3[2] = { nullptr, nullptr };
+    float* lmr_phase = nullptr;
+    float* bpsk_state = nullptr;
+    float2* in_f32 = nullptr;      // cf32 path staging (lazy)
+    // host-side configuration
+    HostTaps taps{};
+    int ctl_audio_out = 2; float ctl_stereo_mix = 1.0f; int ctl_use_deemph = 0;
+    int ctl_deemph_tus = 1, ctl_lpr_hz = 15000, ctl_lmr_hz = 15000;
+    bool dirty_deemph = true, dirty_lpr = true, dirty_lmr = true;
+    // bookkeeping
+    unsigned long long step = 0;   // blocks enqueued so far
+    long long launches = 0;
+    int last_fetched_slot = -1;
+    bool dbg_valid = false;
+    std::vector<uint8_t> dbg_host; // host copies for the debug getters
+    std::vector<float> scalar_host;
+};
+
+namespace {
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemset(*p, 0, n * sizeof(T));
+}
+
+void design_default_taps(fmgpu_demod* h) {
+    // broadcast_fm_demod.cpp:129-274 and bpsk_synchroniser.cpp:27-48
+    const float ROLLOFF = 0.95f;
+    HostTaps& t = h->taps;
+    fmgpu_create_fir_lpf(t.fm_in, 64, (256000.0f / 2.0f) / (1024000.0f / 2.0f) * ROLLOFF);
+    fmgpu_create_fir_lpf(t.fm_out, 64, (128000.0f / 2.0f) / (256000.0f / 2.0f) * ROLLOFF);
+    fmgpu_create_fir_hilbert(t.hilbert, 65);
+    fmgpu_create_iir_peak_1_filter(t.peak_b, t.peak_a, 19000.0f / (128000.0f / 2.0f), 0.9999f);
+    fmgpu_create_iir_single_pole_lpf(t.pll_b, t.pll_a, 100.0f / (128000.0f / 2.0f));
+    fmgpu_create_fir_lpf(t.rds, 128, 2000.0f / (128000.0f / 2.0f));
+    fmgpu_create_iir_single_pole_lpf(t.ted_b, t.ted_a, 1.5e3f / (16e3f / 2.0f));
+    fmgpu_create_iir_single_pole_lpf(t.bpll_b, t.bpll_a, 10.0f / (16e3f / 2.0f));
+}
+
+float clampk(float k) { const float lo = 0.01f, hi = 0.99f; return k > lo ? (k > hi ? hi : k) : lo; }
+
+// Broadcast_FM_Demod::UpdateFilters (broadcast_fm_demod.cpp:330-389)
+void update_filters(fmgpu_demod* h) {
+    const float PI = 3.14159265358979323846f;
+    if (h->dirty_deemph) {
+        h->dirty_deemph = false;
+        const float Tc = (float)h->ctl_deemph_tus * 1e-6f;
+        const float Fc = 1.0f / (2.0f * PI * Tc);
+        fmgpu_create_iir_single_pole_lpf(h->taps.deemph_b, h->taps.deemph_a, clampk(Fc / (128000.0f / 2.0f)));
+    }
+    if (h->dirty_lpr) {
+        h->dirty_lpr = false;
+        fmgpu_create_fir_lpf(h->taps.lpr, 128, clampk((float)h->ctl_lpr_hz / (128000.0f / 2.0f)));
+    }
+    if (h->dirty_lmr) {
+        h->dirty_lmr = false;
+        fmgpu_create_fir_lpf(h->taps.lmr, 128, clampk((float)h->ctl_lmr_hz / (128000.0f / 2.0f)));
+    }
+}
+
+int init_state(fmgpu_demod* h) {
+    // initial values that are not zero: AGC gains 0.1 (dsp/agc.h:10)
+    std::vector<float> pll(fm::PLL_STATE_N * (size_t)h->S, 0.0f), bp(fm::BP_STATE_N * (size_t)h->S, 0.0f);
+    for (int s = 0; s < h->S; s++) {
+        pll[(size_t)fm::PLL_AGC_GAIN * h->S + s] = 0.1f;
+        bp[(size_t)fm::BP_AGC_GAIN * h->S + s] = 0.1f;
+    }
+    CU(cudaMemcpy(h->pll_state, pll.data(), pll.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->bpsk_state, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return FMGPU_OK;
+}
+
+int alloc_all(fmgpu_demod* h) {
+    const size_t S = h->S;
+    CU(cudaStreamCreateWithFlags(&h->stH, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->stA, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->stB, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->stD, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->stO, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(dalloc(&h->k1_hist[i], S * fm::K1_HIST));
+        CU(dalloc(&h->k4_hist_x[i], S * fm::K4_NN));
+        CU(dalloc(&h->k4_hist_m2[i], S * fm::K4_NN));
+        CU(dalloc(&h->k4_hist_m3[i], S * fm::K4_NN));
+    }
+    CU(dalloc(&h->k2_hist_demod, S * fm::K2_NN));
+    CU(dalloc(&h->k2_hist_out, S * 64));
+    CU(dalloc(&h->k2_scal, S * fm::K2_SCAL_N));
+    CU(dalloc(&h->pll_state, S * fm::PLL_STATE_N));
+    CU(dalloc(&h->bpsk_state, S * fm::BP_STATE_N));
+    CU(dalloc(&h->lmr_phase, S));
+    h->slots.resize(h->depth);
+    h->mirrors.resize(h->depth);
+    for (int i = 0; i < h->depth; i++) {
+        Slot& sl = h->slots[i];
+        CU(dalloc(&sl.fm_demod, S * h->n4));
+        CU(dalloc(&sl.fm_out_iq, S * h->n8));
+        CU(dalloc(&sl.theta, S * h->n8));
+        CU(dalloc(&sl.power, S));
+        CU(dalloc(&sl.pll_dt, S * h->n8));
+        CU(dalloc(&sl.audio, S * h->n32));
+        CU(dalloc(&sl.rds, S * h->n64));
+        CU(dalloc(&sl.est_partial, S * h->k4_tiles));
+        CU(dalloc(&sl.rds_pw_partial, S * h->k4_tiles));
+        CU(dalloc(&sl.pred_sym, S * h->n64));
+        CU(dalloc(&sl.sym_count, S));
+        cudaEvent_t* evs[6] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_O };
+        for (auto* ev : evs) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        HostMirror& m = h->mirrors[i];
+        CU(cudaMallocHost((void**)&m.audio, S * h->n32 * sizeof(float2)));
+        CU(cudaMallocHost((void**)&m.pred_sym, S * h->n64 * sizeof(float)));
+        CU(cudaMallocHost((void**)&m.sym_count, S * sizeof(int)));
+        std::memset(m.sym_count, 0, S * sizeof(int));
+    }
+    if (h->cfg.keep_intermediates) {
+        DebugBufs& d = h->dbg;
+        CU(dalloc(&d.pilot, S * h->n8)); CU(dalloc(&d.pll, S * h->n8));
+        CU(dalloc(&d.pll_raw, S * h->n8)); CU(dalloc(&d.pll_pi, S * h->n8));
+        CU(dalloc(&d.lpr, S * h->n32)); CU(dalloc(&d.lmr, S * h->n32));
+        CU(dalloc(&d.k5.rds, S * h->n64)); CU(dalloc(&d.k5.raw_sym, S * h->n64)); CU(dalloc(&d.k5.pll_sym, S * h->n64));
+        CU(dalloc(&d.k5.zcd, S * h->n64)); CU(dalloc(&d.k5.dump_trig, S * h->n64));
+        CU(dalloc(&d.k5.ted_raw, S * h->n64)); CU(dalloc(&d.k5.ted_pi, S * h->n64));
+        CU(dalloc(&d.k5.pll_raw, S * h->n64)); CU(dalloc(&d.k5.pll_pi, S * h->n64));
+        CU(dalloc(&d.k5.dump_filter, S * h->n64));
+    }
+    return init_state(h);
+}
+
+void free_all(fmgpu_demod* h) {
+    cudaDeviceSynchronize();
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    for (int i = 0; i < 2; i++) { F(h->k1_hist[i]); F(h->k4_hist_x[i]); F(h->k4_hist_m2[i]); F(h->k4_hist_m3[i]); }
+    F(h->k2_hist_demod); F(h->k2_hist_out); F(h->k2_scal); F(h->pll_state); F(h->bpsk_state); F(h->lmr_phase); F(h->in_f32);
+    for (auto& sl : h->slots) {
+        F(sl.in_u8); F(sl.fm_demod); F(sl.fm_out_iq); F(sl.theta); F(sl.power); F(sl.pll_dt); F(sl.audio); F(sl.rds);
+        F(sl.est_partial); F(sl.rds_pw_partial); F(sl.pred_sym); F(sl.sym_count);
+        cudaEvent_t evs[6] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_O };
+        for (auto ev : evs) if (ev) cudaEventDestroy(ev);
+    }
+    for (auto& m : h->mirrors) {
+        if (m.audio) cudaFreeHost(m.audio);
+        if (m.pred_sym) cudaFreeHost(m.pred_sym);
+        if (m.sym_count) cudaFreeHost(m.sym_count);
+    }
+    DebugBufs& d = h->dbg;
+    F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr);
+    F(d.k5.rds); F(d.k5.raw_sym); F(d.k5.pll_sym); F(d.k5.zcd); F(d.k5.dump_trig);
+    F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
+    cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
+    for (auto st : sts) if (st) cudaStreamDestroy(st);
+}
+
+// Enqueue the chain for one block whose input is already ordered on stA (or signalled by ev_H).
+int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
+    update_filters(h);
+    const int slot = (int)(h->step % (unsigned long long)h->depth);
+    const int parity = (int)(h->step & 1ull);
+    Slot& sl = h->slots[slot];
+    const bool keep = h->cfg.keep_intermediates != 0;
+
+    // ---- stage A: K1 + K2 ----
+    CU(cudaStreamWaitEvent(h->stA, sl.ev_C, 0));        // previous user of this slot's A/B buffers
+    if (wait_H) CU(cudaStreamWaitEvent(h->stA, sl.ev_H, 0));
+    {
+        fm::K1Params p{};
+        std::memcpy(p.taps, h->taps.fm_in, sizeof(p.taps));
+        // fm_demod.cpp:36-39 with Fd = 75 kHz, Fs = 256 kHz (broadcast_fm_demod.cpp:396-398)
+        const float Wd = 75e3f * 2.0f * 3.14159265358979323846f;
+        const float Ts = 1.0f / 256000.0f;
+        p.discrim_gain = 1.0f / (Wd * Ts) * 0.5f;
+        p.n_out = h->n4; p.parity = parity; p.n_streams = h->S;
+        CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
+    }
+    {
+        fm::K2Params p{};
+        std::memcpy(p.taps_fm_out, h->taps.fm_out, sizeof(p.taps_fm_out));
+        std::memcpy(p.taps_hilbert, h->taps.hilbert, sizeof(p.taps_hilbert));
+        std::memcpy(p.deemph_b, h->taps.deemph_b, 8); std::memcpy(p.deemph_a, h->taps.deemph_a, 8);
+        std::memcpy(p.peak_b, h->taps.peak_b, 12); std::memcpy(p.peak_a, h->taps.peak_a, 12);
+        p.use_deemph = h->ctl_use_deemph; p.n_out = h->n8; p.keep = keep;
+        CU(fm::launch_k2(sl.fm_demod, h->k2_hist_demod, h->k2_hist_out, h->k2_scal, sl.fm_out_iq, sl.theta, sl.power,
+                         keep ? h->dbg.pilot : nullptr, p, h->S, h->stA));
+    }
+    CU(cudaEventRecord(sl.ev_A, h->stA));
+
+    // ---- stage B: K3 ----
+    CU(cudaStreamWaitEvent(h->stB, sl.ev_A, 0));
+    {
+        fm::K3Params p{};
+        std::memcpy(p.lpf_b, h->taps.pll_b, 8); std::memcpy(p.lpf_a, h->taps.pll_a, 8);
+        const float Ts = 1.0f / 128000.0f;
+        p.int_KTs = 0.1f * Ts; p.Kp = 0.01f;
+        p.f_center = -19000.0f; p.f_gain = -100.0f; p.mixer_KTs = Ts;
+        p.agc_target = 1.0f; p.agc_beta = 0.2f;
+        p.n = h->n8; p.n_streams = h->S; p.keep = keep;
+        CU(fm::launch_k3(sl.theta, sl.power, h->pll_state, sl.pll_dt, h->dbg.pll_raw, h->dbg.pll_pi, p, h->stB));
+        if (keep) { CU(fm::launch_kdbg(h->dbg.pilot, h->pll_state, sl.pll_dt, h->dbg.pll, h->n8, h->S, h->stB)); h->launches++; }
+    }
+    CU(cudaEventRecord(sl.ev_B, h->stB));
+
+    // ---- stage C: K4 + K4b ----
+    CU(cudaStreamWaitEvent(h->stC, sl.ev_B, 0));
+    CU(cudaStreamWaitEvent(h->stC, sl.ev_D, 0));        // K5 of the slot's previous block read sl.rds
+    CU(cudaStreamWaitEvent(h->stC, sl.ev_O, 0));        // ... and the fetch read sl.audio
+    {
+        fm::K4Params p{};
+        std::memcpy(p.taps_lpr, h->taps.lpr, sizeof(p.taps_lpr));
+        std::memcpy(p.taps_lmr, h->taps.lmr, sizeof(p.taps_lmr));
+        std::memcpy(p.taps_rds, h->taps.rds, sizeof(p.taps_rds));
+        p.harmonic_lmr = 38000.0f / 19000.0f; p.harmonic_rds = 57000.0f / 19000.0f;
+        p.stereo_mix = h->ctl_stereo_mix; p.audio_out_mode = h->ctl_audio_out;
+        p.n = h->n8; p.n_tiles = h->k4_tiles; p.parity = parity; p.n_streams = h->S; p.keep = keep;
+        CU(fm::launch_k4(sl.fm_out_iq, sl.pll_dt, h->k4_hist_x[parity], h->k4_hist_m2[parity], h->k4_hist_m3[parity],
+                         h->k4_hist_x[parity ^ 1], h->k4_hist_m2[parity ^ 1], h->k4_hist_m3[parity ^ 1],
+                         h->lmr_phase, sl.audio, sl.rds, sl.est_partial, sl.rds_pw_partial,
+                         h->dbg.lpr, h->dbg.lmr, p, h->stC));
+    }
+    CU(cudaEventRecord(sl.ev_C, h->stC));
+
+    // ---- stage D: K5 ----
+    CU(cudaStreamWaitEvent(h->stD, sl.ev_C, 0));
+    CU(cudaStreamWaitEvent(h->stD, sl.ev_O, 0));        // the fetch read sl.pred_sym / sl.sym_count
+    {
+        fm::K5Params p{};
+        std::memcpy(p.ted_b, h->taps.ted_b, 8); std::memcpy(p.ted_a, h->taps.ted_a, 8);
+        std::memcpy(p.pll_b, h->taps.bpll_b, 8); std::memcpy(p.pll_a, h->taps.bpll_a, 8);
+        // bpsk_synchroniser.cpp:51-91 with the defaults of bpsk_synchroniser.h:18-32
+        const float Fs = 16e3f, Fsym = 2e3f, Ts = 1.0f / Fs;
+        const int sps = (int)std::round(Fs / Fsym);
+        p.cooldown_N = sps / 2;
+        p.dump_KTs = 1.0f / (0.5f * (float)sps * 1.0f);
+        p.ted_KTs = Ts; p.ted_fcenter = Fsym; p.ted_fgain = 1.5e3f;
+        p.mixer_KTs = Ts; p.mixer_fgain = 10.0f;
+        const float k = Fsym / Fs;
+        p.int_ted_KTs = 10.0f * Ts * k; p.int_pll_KTs = 10.0f * Ts * k;
+        p.ted_Kp = 0.3f; p.pll_Kp = 0.3f;
+        p.agc_target = 0.5f; p.agc_beta = 0.2f;
+        p.n = h->n64; p.n_tiles_k4 = h->k4_tiles; p.n_streams = h->S; p.keep = keep;
+        CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, h->stD));
+    }
+    CU(cudaEventRecord(sl.ev_D, h->stD));
+    h->launches += 6;
+    h->step++;
+    h->dbg_valid = false;
+    return slot;
+}
+
+int fetch_slot(fmgpu_demod* h, int slot) {
+    Slot& sl = h->slots[slot];
+    HostMirror& m = h->mirrors[slot];
+    const size_t S = h->S;
+    CU(cudaStreamWaitEvent(h->stO, sl.ev_D, 0));
+    CU(cudaMemcpyAsync(m.audio, sl.audio, S * h->n32 * sizeof(float2), cudaMemcpyDeviceToHost, h->stO));
+    CU(cudaMemcpyAsync(m.pred_sym, sl.pred_sym, S * h->n64 * sizeof(float), cudaMemcpyDeviceToHost, h->stO));
+    CU(cudaMemcpyAsync(m.sym_count, sl.sym_count, S * sizeof(int), cudaMemcpyDeviceToHost, h->stO));
+    CU(cudaEventRecord(sl.ev_O, h->stO));
+    h->last_fetched_slot = slot;
+    return FMGPU_OK;
+}
+
+int sync_all(fmgpu_demod* h) {
+    CU(cudaStreamSynchronize(h->stH));
+    CU(cudaStreamSynchronize(h->stA));
+    CU(cudaStreamSynchronize(h->stB));
+    CU(cudaStreamSynchronize(h->stC));
+    CU(cudaStreamSynchronize(h->stD));
+    CU(cudaStreamSynchronize(h->stO));
+    return FMGPU_OK;
+}
+
+struct BufInfo { size_t elem; int per_stream; };   // element bytes, elements per stream
+
+} // namespace
+
+extern "C" {
+
+const char* fmgpu_last_error(void) { return g_last_error.c_str(); }
+const char* fmgpu_version(void) { return "fm-radio-b200 0.1 (sm_100a)"; }
+
+int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
+    if (!cfg || !out) return fail(FMGPU_ERR_ARG, "fmgpu_create: null argument");
+    *out = nullptr;
+    const int B = cfg->block_size;
+    if (B < 1024 || (B & (B - 1)) != 0) return fail(FMGPU_ERR_ARG, "fmgpu_create: block_size must be a power of two >= 1024");
+    if (cfg->n_streams < 1) return fail(FMGPU_ERR_ARG, "fmgpu_create: n_streams must be >= 1");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(FMGPU_ERR_CUDA, std::string("fmgpu_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    int dev = cfg->device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= n_dev) return fail(FMGPU_ERR_ARG, "fmgpu_create: bad device ordinal");
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(FMGPU_ERR_CUDA, "fmgpu_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    auto* h = new fmgpu_demod();
+    h->cfg = *cfg; h->cfg.device = dev;
+    h->device = dev;
+    h->B = B; h->S = cfg->n_streams;
+    h->n4 = B / 4; h->n8 = B / 8; h->n32 = B / 32; h->n64 = B / 64;
+    h->depth = cfg->pipeline_depth > 0 ? cfg->pipeline_depth : 4;
+    // the GUI buffers exist once (not per ring slot): with them on, blocks are not overlapped
+    if (cfg->keep_intermediates) h->depth = 1;
+    h->cfg.pipeline_depth = h->depth;
+    h->k4_tiles = (h->n8 + fm::K4_TS - 1) / fm::K4_TS;
+    design_default_taps(h);
+    update_filters(h);
+    const int rc = alloc_all(h);
+    if (rc != FMGPU_OK) { const std::string msg = g_last_error; free_all(h); delete h; g_last_error = msg; return rc; }
+    *out = h;
+    return FMGPU_OK;
+}
+
+void fmgpu_destroy(fmgpu_demod* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_all(h);
+    delete h;
+}
+
+static int process_host(fmgpu_demod* h, const void* iq_host, size_t n_samples, bool u8) {
+    if (!h || !iq_host) return fail(FMGPU_ERR_ARG, "process: null argument");
+    if (n_samples != (size_t)h->B) return fail(FMGPU_ERR_SIZE, "process: n_samples != block_size");
+    CU(cudaSetDevice(h->device));
+    const int slot = (int)(h->step % (unsigned long long)h->depth);
+    Slot& sl = h->slots[slot];
+    const void* dev_in;
+    if (u8) {
+        const size_t bytes = (size_t)h->S * h->B * 2;
+        if (!sl.in_u8) CU(cudaMalloc((void**)&sl.in_u8, bytes));
+        CU(cudaStreamWaitEvent(h->stH, sl.ev_A, 0));     // K1 of the slot's previous block read in_u8
+        CU(cudaMemcpyAsync(sl.in_u8, iq_host, bytes, cudaMemcpyHostToDevice, h->stH));
+        dev_in = sl.in_u8;
+    } else {
+        const size_t bytes = (size_t)h->S * h->B * sizeof(float2);
+        if (!h->in_f32) CU(cudaMalloc((void**)&h->in_f32, bytes));
+        CU(cudaStreamSynchronize(h->stA));
+        CU(cudaMemcpyAsync(h->in_f32, iq_host, bytes, cudaMemcpyHostToDevice, h->stH));
+        dev_in = h->in_f32;
+    }
+    CU(cudaEventRecord(sl.ev_H, h->stH));
+    const int rc = enqueue_chain(h, dev_in, u8, true);
+    if (rc < 0) return rc;
+    return FMGPU_OK;
+}
+
+int fmgpu_process_u8(fmgpu_demod* h, const uint8_t* iq_host, size_t n_samples) {
+    int rc = process_host(h, iq_host, n_samples, true);
+    if (rc != FMGPU_OK) return rc;
+    rc = fetch_slot(h, (int)((h->step - 1) % (unsigned long long)h->depth));
+    if (rc != FMGPU_OK) return rc;
+    return sync_all(h);
+}
+
+int fmgpu_process_cf32(fmgpu_demod* h, const float* iq_host, size_t n_samples) {
+    int rc = process_host(h, iq_host, n_samples, false);
+    if (rc != FMGPU_OK) return rc;
+    rc = fetch_slot(h, (int)((h->step - 1) % (unsigned long long)h->depth));
+    if (rc != FMGPU_OK) return rc;
+    return sync_all(h);
+}
+
+int fmgpu_enqueue_u8_host(fmgpu_demod* h, const uint8_t* iq_pinned_host) {
+    if (!h) return fail(FMGPU_ERR_ARG, "enqueue: null handle");
+    return process_host(h, iq_pinned_host, (size_t)h->B, true);
+}
+
+int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev) {
+    if (!h || !iq_dev) return fail(FMGPU_ERR_ARG, "enqueue: null argument");
+    CU(cudaSetDevice(h->device));
+    const int rc = enqueue_chain(h, iq_dev, true, false);
+    return rc < 0 ? rc : FMGPU_OK;
+}
+
+int fmgpu_sync(fmgpu_demod* h) {
+    if (!h) return fail(FMGPU_ERR_ARG, "sync: null handle");
+    CU(cudaSetDevice(h->device));
+    return sync_all(h);
+}
+
+int fmgpu_fetch_outputs(fmgpu_demod* h, int slot) {
+    if (!h || slot < 0 || slot >= h->depth) return fail(FMGPU_ERR_ARG, "fetch: bad slot");
+    CU(cudaSetDevice(h->device));
+    return fetch_slot(h, slot);
+}
+
+int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
+    if (!h) return fail(FMGPU_ERR_ARG, "null handle");
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
+    cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
+    for (auto st : sts) CU(cudaStreamWaitEvent(st, ev, 0));
+    CU(cudaEventDestroy(ev));
+    return FMGPU_OK;
+}
+
+int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream) {
+    if (!h) return fail(FMGPU_ERR_ARG, "null handle");
+    cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
+    for (auto st : sts) {
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, st));
+        CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ev, 0));
+        CU(cudaEventDestroy(ev));
+    }
+    return FMGPU_OK;
+}
+
+static bool buf_info(const fmgpu_demod* h, fmgpu_buffer b, BufInfo* bi, const void** dev, int slot) {
+    const Slot& sl = h->slots[slot];
+    const DebugBufs& d = h->dbg;
+    const bool keep = h->cfg.keep_intermediates != 0;
+    switch (b) {
+    case FMGPU_BUF_AUDIO_OUT: *bi = { 8, h->n32 }; *dev = sl.audio; return true;
+    case FMGPU_BUF_RDS_PRED_SYM: *bi = { 4, h->n64 }; *dev = sl.pred_sym; return true;
+    case FMGPU_BUF_RDS_SYM_COUNT: *bi = { 4, 1 }; *dev = sl.sym_count; return true;
+    case FMGPU_BUF_FM_DEMOD: *bi = { 4, h->n4 }; *dev = sl.fm_demod; return true;
+    case FMGPU_BUF_FM_OUT_IQ: *bi = { 8, h->n8 }; *dev = sl.fm_out_iq; return true;
+    case FMGPU_BUF_PLL_DT: *bi = { 4, h->n8 }; *dev = sl.pll_dt; return true;
+    default: break;
+    }
+    if (!keep) return false;
+    switch (b) {
+    case FMGPU_BUF_PILOT: *bi = { 8, h->n8 }; *dev = d.pilot; return true;
+    case FMGPU_BUF_PLL: *bi = { 8, h->n8 }; *dev = d.pll; return true;
+    case FMGPU_BUF_PLL_RAW_PHASE_ERROR: *bi = { 4, h->n8 }; *dev = d.pll_raw; return true;
+    case FMGPU_BUF_PLL_LPF_PHASE_ERROR: *bi = { 4, h->n8 }; *dev = d.pll_pi; return true;
+    case FMGPU_BUF_AUDIO_LPR: *bi = { 4, h->n32 }; *dev = d.lpr; return true;
+    case FMGPU_BUF_AUDIO_LMR: *bi = { 4, h->n32 }; *dev = d.lmr; return true;
+    case FMGPU_BUF_RDS: *bi = { 8, h->n64 }; *dev = d.k5.rds; return true;
+    case FMGPU_BUF_RDS_RAW_SYM: *bi = { 8, h->n64 }; *dev = d.k5.raw_sym; return true;
+    case FMGPU_BUF_BPSK_PLL_SYM: *bi = { 8, h->n64 }; *dev = d.k5.pll_sym; return true;
+    case FMGPU_BUF_BPSK_ZCD: *bi = { 1, h->n64 }; *dev = d.k5.zcd; return true;
+    case FMGPU_BUF_BPSK_INT_DUMP_TRIGGER: *bi = { 1, h->n64 }; *dev = d.k5.dump_trig; return true;
+    case FMGPU_BUF_BPSK_TED_RAW_PHASE_ERROR: *bi = { 4, h->n64 }; *dev = d.k5.ted_raw; return true;
+    case FMGPU_BUF_BPSK_TED_PI_PHASE_ERROR: *bi = { 4, h->n64 }; *dev = d.k5.ted_pi; return true;
+    case FMGPU_BUF_BPSK_PLL_RAW_PHASE_ERROR: *bi = { 4, h->n64 }; *dev = d.k5.pll_raw; return true;
+    case FMGPU_BUF_BPSK_PLL_PI_PHASE_ERROR: *bi = { 4, h->n64 }; *dev = d.k5.pll_pi; return true;
+    case FMGPU_BUF_BPSK_INT_DUMP_FILTER: *bi = { 8, h->n64 }; *dev = d.k5.dump_filter; return true;
+    default: return false;
+    }
+}
+
+int fmgpu_get_buffer(fmgpu_demod* h, int stream, fmgpu_buffer buf, const void** host_ptr, size_t* n_elems) {
+    if (!h || !host_ptr || !n_elems) return fail(FMGPU_ERR_ARG, "get_buffer: null argument");
+    if (stream < 0 || stream >= h->S) return fail(FMGPU_ERR_ARG, "get_buffer: bad stream");
+    if (h->last_fetched_slot < 0) return fail(FMGPU_ERR_STATE, "get_buffer: nothing processed yet");
+    const int slot = h->last_fetched_slot;
+    HostMirror& m = h->mirrors[slot];
+    const int count = m.sym_count[stream];
+    switch (buf) {
+    case FMGPU_BUF_AUDIO_OUT: *host_ptr = m.audio + (size_t)stream * h->n32; *n_elems = h->n32; return FMGPU_OK;
+    case FMGPU_BUF_RDS_PRED_SYM: *host_ptr = m.pred_sym + (size_t)stream * h->n64; *n_elems = (size_t)count; return FMGPU_OK;
+    case FMGPU_BUF_RDS_SYM_COUNT: *host_ptr = m.sym_count + stream; *n_elems = 1; return FMGPU_OK;
+    default: break;
+    }
+    // Everything else is copied on demand from the device (GUI / test path, not the hot path).
+    BufInfo bi{}; const void* dev = nullptr;
+    if (!buf_info(h, buf, &bi, &dev, slot))
+        return fail(FMGPU_ERR_STATE, "get_buffer: buffer needs keep_intermediates = 1");
+    CU(cudaSetDevice(h->device));
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    const size_t bytes = bi.elem * (size_t)bi.per_stream;
+    // host scratch: one region per buffer id, sized lazily
+    const size_t max_bytes = 8ull * (size_t)h->n4;
+    if (h->dbg_host.size() < (size_t)FMGPU_BUF__COUNT * max_bytes) h->dbg_host.resize((size_t)FMGPU_BUF__COUNT * max_bytes);
+    uint8_t* dst = h->dbg_host.data() + (size_t)buf * max_bytes;
+    CU(cudaMemcpy(dst, (const uint8_t*)dev + (size_t)stream * bytes, bytes, cudaMemcpyDeviceToHost));
+    *host_ptr = dst;
+    *n_elems = (buf == FMGPU_BUF_RDS_RAW_SYM) ? (size_t)count : (size_t)bi.per_stream;
+    return FMGPU_OK;
+}
+
+int fmgpu_get_device_buffer(fmgpu_demod* h, int slot, fmgpu_buffer buf, void** dev_ptr, size_t* n_elems_per_stream) {
+    if (!h || !dev_ptr || slot < 0 || slot >= h->depth) return fail(FMGPU_ERR_ARG, "get_device_buffer: bad argument");
+    BufInfo bi{}; const void* dev = nullptr;
+    if (!buf_info(h, buf, &bi, &dev, slot)) return fail(FMGPU_ERR_STATE, "get_device_buffer: buffer needs keep_intermediates = 1");
+    *dev_ptr = (void*)dev;
+    if (n_elems_per_stream) *n_elems_per_stream = (size_t)bi.per_stream;
+    return FMGPU_OK;
+}
+
+int fmgpu_get_scalar(fmgpu_demod* h, int stream, fmgpu_scalar which, float* out) {
+    if (!h || !out || stream < 0 || stream >= h->S) return fail(FMGPU_ERR_ARG, "get_scalar: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    const float* src = nullptr;
+    switch (which) {
+    case FMGPU_SCALAR_AUDIO_LMR_PHASE_ERROR: src = h->lmr_phase + stream; break;
+    case FMGPU_SCALAR_AGC_PILOT_GAIN: src = h->pll_state + (size_t)fm::PLL_AGC_GAIN * h->S + stream; break;
+    case FMGPU_SCALAR_AGC_RDS_GAIN: src = h->bpsk_state + (size_t)fm::BP_AGC_GAIN * h->S + stream; break;
+    default: return fail(FMGPU_ERR_ARG, "get_scalar: unknown id");
+    }
+    CU(cudaMemcpy(out, src, sizeof(float), cudaMemcpyDeviceToHost));
+    return FMGPU_OK;
+}
+
+int fmgpu_set_control(fmgpu_demod* h, fmgpu_control which, double value) {
+    if (!h) return fail(FMGPU_ERR_ARG, "set_control: null handle");
+    switch (which) {
+    case FMGPU_CTL_AUDIO_OUT:
+        if ((int)value < 0 || (int)value > 2) return fail(FMGPU_ERR_ARG, "set_control: audio_out must be 0..2");
+        h->ctl_audio_out = (int)value; break;
+    case FMGPU_CTL_AUDIO_STEREO_MIX_FACTOR: h->ctl_stereo_mix = (float)value; break;
+    case FMGPU_CTL_USE_DEEMPHASIS: h->ctl_use_deemph = value != 0.0; break;
+    case FMGPU_CTL_DEEMPHASIS_TUS: h->ctl_deemph_tus = (int)value; h->dirty_deemph = true; break;
+    case FMGPU_CTL_AUDIO_LPR_CUTOFF_HZ: h->ctl_lpr_hz = (int)value; h->dirty_lpr = true; break;
+    case FMGPU_CTL_AUDIO_LMR_CUTOFF_HZ: h->ctl_lmr_hz = (int)value; h->dirty_lmr = true; break;
+    default: return fail(FMGPU_ERR_ARG, "set_control: unknown id");
+    }
+    return FMGPU_OK;
+}
+
+static bool taps_ptr(fmgpu_demod* h, fmgpu_filter which, float** b, float** a, int* n) {
+    HostTaps& t = h->taps;
+    *a = nullptr;
+    switch (which) {
+    case FMGPU_FILT_FM_IN: *b = t.fm_in; *n = 64; return true;
+    case FMGPU_FILT_FM_OUT: *b = t.fm_out; *n = 64; return true;
+    case FMGPU_FILT_HILBERT: *b = t.hilbert; *n = 65; return true;
+    case FMGPU_FILT_AUDIO_LPR: *b = t.lpr; *n = 128; return true;
+    case FMGPU_FILT_AUDIO_LMR: *b = t.lmr; *n = 128; return true;
+    case FMGPU_FILT_RDS: *b = t.rds; *n = 128; return true;
+    case FMGPU_FILT_DEEMPHASIS: *b = t.deemph_b; *a = t.deemph_a; *n = 2; return true;
+    case FMGPU_FILT_PEAK_PILOT: *b = t.peak_b; *a = t.peak_a; *n = 3; return true;
+    case FMGPU_FILT_PLL_LPF: *b = t.pll_b; *a = t.pll_a; *n = 2; return true;
+    case FMGPU_FILT_BPSK_TED_LPF: *b = t.ted_b; *a = t.ted_a; *n = 2; return true;
+    case FMGPU_FILT_BPSK_PLL_LPF: *b = t.bpll_b; *a = t.bpll_a; *n = 2; return true;
+    default: return false;
+    }
+}
+
+int fmgpu_upload_taps(fmgpu_demod* h, fmgpu_filter which, const float* b, const float* a, int n) {
+    if (!h || !b) return fail(FMGPU_ERR_ARG, "upload_taps: null argument");
+    float *hb, *ha; int hn;
+    if (!taps_ptr(h, which, &hb, &ha, &hn)) return fail(FMGPU_ERR_ARG, "upload_taps: unknown filter");
+    if (n != hn) return fail(FMGPU_ERR_ARG, "upload_taps: wrong length");
+    if (ha && !a) return fail(FMGPU_ERR_ARG, "upload_taps: IIR filter needs a[]");
+    update_filters(h);          // settle pending redesigns first so the upload is not overwritten
+    std::memcpy(hb, b, sizeof(float) * n);
+    if (ha) std::memcpy(ha, a, sizeof(float) * n);
+    return FMGPU_OK;
+}
+
+int fmgpu_download_taps(fmgpu_demod* h, fmgpu_filter which, float* b, float* a, int n) {
+    if (!h || !b) return fail(FMGPU_ERR_ARG, "download_taps: null argument");
+    float *hb, *ha; int hn;
+    if (!taps_ptr(h, which, &hb, &ha, &hn)) return fail(FMGPU_ERR_ARG, "download_taps: unknown filter");
+    if (n != hn) return fail(FMGPU_ERR_ARG, "download_taps: wrong length");
+    update_filters(h);
+    std::memcpy(b, hb, sizeof(float) * n);
+    if (ha && a) std::memcpy(a, ha, sizeof(float) * n);
+    return FMGPU_OK;
+}
+
+int fmgpu_get_rates(fmgpu_demod* h, int rates_hz[5]) {
+    if (!h || !rates_hz) return fail(FMGPU_ERR_ARG, "get_rates: null argument");
+    rates_hz[0] = 1024000; rates_hz[1] = 256000; rates_hz[2] = 128000; rates_hz[3] = 16000; rates_hz[4] = 32000;
+    return FMGPU_OK;
+}
+
+int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out) {
+    if (!h || !out) return fail(FMGPU_ERR_ARG, "get_config: null argument");
+    *out = h->cfg;
+    return FMGPU_OK;
+}
+
+long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
+
+// ---- stand-alone polyphase decimator (dsp/polyphase_filter.h:9-87) ----
+struct fmgpu_polyphase {
+    int M, K, NN, is_complex;
+    std::vector<float> b;          // host taps (get_b)
+    std::vector<float> hist;       // last NN inputs
+    float* d_ext = nullptr; float* d_taps = nullptr; float* d_y = nullptr;
+    size_t cap_ext = 0, cap_y = 0;
+};
+
+int fmgpu_polyphase_ds_create(int M, int K, int is_complex, fmgpu_polyphase** out) {
+    if (!out || M < 1 || K < 1) return fail(FMGPU_ERR_ARG, "polyphase_ds_create: bad argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(FMGPU_ERR_CUDA, "polyphase_ds_create: no CUDA device (there is no CPU fallback)");
+    auto* f = new fmgpu_polyphase();
+    f->M = M; f->K = K; f->NN = M * K; f->is_complex = is_complex ? 1 : 0;
+    f->b.assign(f->NN, 0.0f);
+    f->hist.assign((size_t)f->NN * (is_complex ? 2 : 1), 0.0f);
+    cudaError_t e = cudaMalloc((void**)&f->d_taps, f->NN * sizeof(float));
+    if (e != cudaSuccess) { delete f; return fail(FMGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = f;
+    return FMGPU_OK;
+}
+
+void fmgpu_polyphase_destroy(fmgpu_polyphase* f) {
+    if (!f) return;
+    if (f->d_ext) cudaFree(f->d_ext);
+    if (f->d_taps) cudaFree(f->d_taps);
+    if (f->d_y) cudaFree(f->d_y);
+    delete f;
+}
+
+float* fmgpu_polyphase_get_b(fmgpu_polyphase* f) { return f ? f->b.data() : nullptr; }
+
+int fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* y_host, int n_out) {
+    if (!f || !x_host || !y_host || n_out < 0) return fail(FMGPU_ERR_ARG, "polyphase_ds_process: bad argument");
+    if (n_out == 0) return FMGPU_OK;
+    const int C = f->is_complex ? 2 : 1;
+    const size_t n_in = (size_t)n_out * f->M;
+    const size_t ext_floats = ((size_t)f->NN + n_in) * C, y_floats = (size_t)n_out * C;
+    if (f->cap_ext < ext_floats) { if (f->d_ext) cudaFree(f->d_ext); CU(cudaMalloc((void**)&f->d_ext, ext_floats * 4)); f->cap_ext = ext_floats; }
+    if (f->cap_y < y_floats) { if (f->d_y) cudaFree(f->d_y); CU(cudaMalloc((void**)&f->d_y, y_floats * 4)); f->cap_y = y_floats; }
+    CU(cudaMemcpy(f->d_taps, f->b.data(), f->NN * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(f->d_ext, f->hist.data(), (size_t)f->NN * C * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(f->d_ext + (size_t)f->NN * C, x_host, n_in * C * 4, cudaMemcpyHostToDevice));
+    CU(fm::launch_polyphase_ds(f->d_ext, f->d_taps, f->d_y, f->M, f->NN, n_out, f->is_complex, 0));
+    CU(cudaMemcpy(y_host, f->d_y, y_floats * 4, cudaMemcpyDeviceToHost));
+    // new history = last NN samples of (hist ++ x)
+    CU(cudaMemcpy(f->hist.data(), f->d_ext + n_in * C, (size_t)f->NN * C * 4, cudaMemcpyDeviceToHost));
+    return FMGPU_OK;
+}
+
+} // extern "C"

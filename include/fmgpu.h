@@ -1,0 +1,208 @@
+/* fmgpu.h -- C-ABI of the B200-native broadcast-FM demodulation chain.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: the
+ * seam is the C++ class Broadcast_FM_Demod (src/fm_demod/broadcast_fm_demod.h:91-299) built by
+ * App (src/app.cpp:19) and fed by App::Run (src/app.cpp:56-65).  Every entry point below names
+ * the reference interface it replaces; fm_radio_b200/csrc/shim/ holds a header-compatible
+ * Broadcast_FM_Demod whose methods forward to these functions.
+ *
+ * Plain pointers and sizes only.  There is NO CPU fallback: every call fails with
+ * FMGPU_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Threading: one thread at a time per handle (as the reference: Process is called from exactly
+ * one runner thread, fm_demod_no_tuner.cpp:179-189).  Different handles are independent.
+ */
+#ifndef FMGPU_H
+#define FMGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fmgpu_demod fmgpu_demod;
+typedef struct fmgpu_rds fmgpu_rds;
+
+enum {
+    FMGPU_OK = 0,
+    FMGPU_ERR_ARG = -1,      /* bad argument (null, wrong size, unknown id)            */
+    FMGPU_ERR_CUDA = -2,     /* CUDA runtime error or no device; see fmgpu_last_error  */
+    FMGPU_ERR_STATE = -3,    /* call not valid in the handle's current state           */
+    FMGPU_ERR_SIZE = -4      /* input length != block_size: the reference silently returns
+                                (broadcast_fm_demod.cpp:311-313); the shim swallows this  */
+};
+
+/* Broadcast_FM_Demod(const int block_size) (broadcast_fm_demod.cpp:59) generalised to a batch of
+ * n_streams independent demodulators that share one launch (all state is per stream, exactly as
+ * all state is per object in the reference, broadcast_fm_demod.h:143-166). */
+typedef struct fmgpu_config {
+    int block_size;          /* IQ samples per stream per Process; power of two, >= 1024          */
+    int n_streams;           /* >= 1                                                              */
+    int device;              /* CUDA ordinal, -1 = current device                                 */
+    int keep_intermediates;  /* 1: also produce every GUI-visible buffer (pilot, pll, errors,
+                                lpr/lmr, BPSK display arrays) -- what the reference always does.
+                                0: lean mode, only audio + RDS symbols leave the kernels          */
+    int pipeline_depth;      /* slots of inter-stage buffers for the asynchronous path (>= 1);
+                                0 = default (4); forced to 1 when keep_intermediates is set       */
+} fmgpu_config;
+
+int  fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out);
+void fmgpu_destroy(fmgpu_demod* h);
+
+/* ---- synchronous block interface (host buffers) ------------------------------------------
+ * fmgpu_process_u8 replaces App::Run + Broadcast_FM_Demod::Process (src/app.cpp:56-65,
+ * broadcast_fm_demod.cpp:309-328): iq holds n_streams consecutive blocks of block_size (I,Q) u8
+ * pairs as rtl-sdr emits them; the (float)u8 - 127.0f unpack is fused into the first kernel.
+ * fmgpu_process_cf32 replaces Broadcast_FM_Demod::Process(span<const complex<float>>) itself.
+ * Both copy host->device, run the chain, copy audio + RDS symbols (+ intermediates) back into
+ * the handle's pinned host mirrors and return when those are valid (the reference notifies its
+ * observers synchronously inside Process, broadcast_fm_demod.cpp:326-327).
+ * n_samples is the number of complex samples per stream and must equal block_size. */
+int fmgpu_process_u8(fmgpu_demod* h, const uint8_t* iq_host, size_t n_samples);
+int fmgpu_process_cf32(fmgpu_demod* h, const float* iq_host, size_t n_samples);
+
+/* ---- asynchronous batch interface (device buffers) ---------------------------------------
+ * New with the batch driver (no reference counterpart).  iq_dev is a DEVICE pointer to
+ * [n_streams][block_size][2] u8.  The block is enqueued on the handle's stage streams and the
+ * call returns immediately; up to pipeline_depth blocks may be in flight.  The input buffer must
+ * stay valid and unmodified until fmgpu_sync (or until pipeline_depth further enqueues).
+ * Outputs of enqueue number k land in ring slot k % pipeline_depth (device), see
+ * fmgpu_get_device_buffer. */
+int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev);
+/* Same, but iq_host is a (preferably pinned) HOST pointer: the host->device copy is queued on the
+ * handle's copy stream and overlaps with the kernels of the blocks already in flight. */
+int fmgpu_enqueue_u8_host(fmgpu_demod* h, const uint8_t* iq_host);
+int fmgpu_sync(fmgpu_demod* h);
+/* Copies slot's audio + symbols to the pinned host mirrors (asynchronously on the output stream;
+ * valid after fmgpu_sync). */
+int fmgpu_fetch_outputs(fmgpu_demod* h, int slot);
+/* Makes the handle's first kernel wait for work already queued on an external CUDA stream
+ * (cudaStream_t passed as void*, e.g. torch's current stream that produced iq_dev). */
+int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream);
+/* Records completion of everything enqueued so far into the external stream (so that stream's
+ * events time the whole chain). */
+int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream);
+
+/* ---- buffers: the getters of broadcast_fm_demod.h:242-256 and bpsk_synchroniser.h:76-85 ---- */
+typedef enum fmgpu_buffer {
+    FMGPU_BUF_AUDIO_OUT = 0,        /* GetAudioOut: Frame<float>[B/32] = L,R interleaved f32   */
+    FMGPU_BUF_RDS_PRED_SYM,         /* GetRDSPredSymbols: f32[count]                            */
+    FMGPU_BUF_RDS_SYM_COUNT,        /* rds_total_symbols: i32[1]                                */
+    /* the rest need keep_intermediates = 1 */
+    FMGPU_BUF_FM_DEMOD,             /* fm_demod_buf f32[B/4] (private in the reference)         */
+    FMGPU_BUF_FM_OUT_IQ,            /* GetFMOutIQ cf32[B/8]                                     */
+    FMGPU_BUF_PILOT,                /* GetPilotOutput cf32[B/8] (after AGC)                     */
+    FMGPU_BUF_PLL_DT,               /* pll_dt_buf f32[B/8] (private in the reference)           */
+    FMGPU_BUF_PLL,                  /* GetPLLOutput cf32[B/8]                                   */
+    FMGPU_BUF_PLL_RAW_PHASE_ERROR,  /* Get_PLL_Raw_Phase_Error_Output f32[B/8]                  */
+    FMGPU_BUF_PLL_LPF_PHASE_ERROR,  /* Get_PLL_LPF_Phase_Error_Output f32[B/8]                  */
+    FMGPU_BUF_AUDIO_LPR,            /* GetLPRAudioOutput f32[B/32]                              */
+    FMGPU_BUF_AUDIO_LMR,            /* GetLMRAudioOutput f32[B/32]                              */
+    FMGPU_BUF_RDS,                  /* GetRDSOutput cf32[B/64] (after AGC)                      */
+    FMGPU_BUF_RDS_RAW_SYM,          /* GetRDSRawSymbols cf32[count]                             */
+    FMGPU_BUF_BPSK_PLL_SYM,         /* BPSK_Synchroniser::GetPLLSymbols cf32[B/64]              */
+    FMGPU_BUF_BPSK_ZCD,             /* GetZeroCrossings u8[B/64]                                */
+    FMGPU_BUF_BPSK_INT_DUMP_TRIGGER,/* GetIntDumpTriggers u8[B/64]                              */
+    FMGPU_BUF_BPSK_TED_RAW_PHASE_ERROR, /* f32[B/64]                                            */
+    FMGPU_BUF_BPSK_TED_PI_PHASE_ERROR,  /* f32[B/64]                                            */
+    FMGPU_BUF_BPSK_PLL_RAW_PHASE_ERROR, /* f32[B/64]                                            */
+    FMGPU_BUF_BPSK_PLL_PI_PHASE_ERROR,  /* f32[B/64]                                            */
+    FMGPU_BUF_BPSK_INT_DUMP_FILTER, /* cf32[B/64]                                               */
+    FMGPU_BUF__COUNT
+} fmgpu_buffer;
+
+/* Host-readable view of `buf` for `stream`, valid until the next process/fetch call on the handle
+ * (same lifetime rule as the reference's spans).  *n_elems is in elements of the buffer's type
+ * (complex and Frame count as one element). */
+int fmgpu_get_buffer(fmgpu_demod* h, int stream, fmgpu_buffer buf, const void** host_ptr, size_t* n_elems);
+/* Device pointer of ring slot `slot` for the whole batch ([n_streams][...] stream-major). */
+int fmgpu_get_device_buffer(fmgpu_demod* h, int slot, fmgpu_buffer buf, void** dev_ptr, size_t* n_elems_per_stream);
+
+/* Scalars: GetAudioLMRPhaseError (broadcast_fm_demod.h:291) and the two AGC gains. */
+typedef enum fmgpu_scalar {
+    FMGPU_SCALAR_AUDIO_LMR_PHASE_ERROR = 0,
+    FMGPU_SCALAR_AGC_PILOT_GAIN,
+    FMGPU_SCALAR_AGC_RDS_GAIN
+} fmgpu_scalar;
+int fmgpu_get_scalar(fmgpu_demod* h, int stream, fmgpu_scalar which, float* out);
+
+/* ---- controls: Broadcast_FM_Demod_Controls (broadcast_fm_demod.h:64-89) ------------------- */
+typedef enum fmgpu_control {
+    FMGPU_CTL_AUDIO_OUT = 0,            /* 0 LPR, 1 LMR, 2 STEREO (enum AudioOut, :80)          */
+    FMGPU_CTL_AUDIO_STEREO_MIX_FACTOR,  /* float, default 1                                     */
+    FMGPU_CTL_USE_DEEMPHASIS,           /* bool, default 0                                      */
+    FMGPU_CTL_DEEMPHASIS_TUS,           /* int microseconds; redesigns the 1-pole IIR (:337-352)*/
+    FMGPU_CTL_AUDIO_LPR_CUTOFF_HZ,      /* int Hz; redesigns the L+R FIR (:355-370)             */
+    FMGPU_CTL_AUDIO_LMR_CUTOFF_HZ       /* int Hz; redesigns the L-R FIR (:373-388)             */
+} fmgpu_control;
+/* Latched at the next process/enqueue call (the reference reads controls at Process entry,
+ * UpdateFilters, broadcast_fm_demod.cpp:316).  Applies to every stream of the handle. */
+int fmgpu_set_control(fmgpu_demod* h, fmgpu_control which, double value);
+
+/* ---- filter taps: the get_b()/get_a() arrays the reference designers fill ------------------ */
+typedef enum fmgpu_filter {
+    FMGPU_FILT_FM_IN = 0,     /* filt_poly_ds_lpf_fm_in   64 taps (broadcast_fm_demod.cpp:133-144) */
+    FMGPU_FILT_FM_OUT,        /* filt_poly_ds_lpf_fm_out  64 taps (:146-157)                       */
+    FMGPU_FILT_HILBERT,       /* filt_hilbert_transform   65 taps (:192-195)                       */
+    FMGPU_FILT_AUDIO_LPR,     /* filt_poly_ds_lpf_audio_lpr 128 taps (:240-249)                    */
+    FMGPU_FILT_AUDIO_LMR,     /* filt_poly_ds_lpf_audio_lmr 128 taps (:251-261)                    */
+    FMGPU_FILT_RDS,           /* filt_poly_ds_lpf_rds     128 taps (:263-274)                      */
+    FMGPU_FILT_DEEMPHASIS,    /* b[2], a[2] (:184-190, 337-352)                                    */
+    FMGPU_FILT_PEAK_PILOT,    /* b[3], a[3] (:200-213)                                             */
+    FMGPU_FILT_PLL_LPF,       /* b[2], a[2] (:215-224)                                             */
+    FMGPU_FILT_BPSK_TED_LPF,  /* b[2], a[2] (bpsk_synchroniser.cpp:27-36)                          */
+    FMGPU_FILT_BPSK_PLL_LPF,  /* b[2], a[2] (bpsk_synchroniser.cpp:39-48)                          */
+    FMGPU_FILT__COUNT
+} fmgpu_filter;
+/* Arrays are in the reference's memory order (ReverseArray layout, filter_designer.cpp:27-39).
+ * `a` may be NULL for FIR filters.  n must equal the filter's length. */
+int fmgpu_upload_taps(fmgpu_demod* h, fmgpu_filter which, const float* b, const float* a, int n);
+int fmgpu_download_taps(fmgpu_demod* h, fmgpu_filter which, float* b, float* a, int n);
+
+/* Sample rates (broadcast_fm_demod.h:284-288): baseband, fm_in, fm_out, rds, audio. */
+int fmgpu_get_rates(fmgpu_demod* h, int rates_hz[5]);
+int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out);
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+long long fmgpu_launch_count(fmgpu_demod* h);
+
+/* ---- host-side filter designers: src/dsp/filter_designer.h:8-35, same signatures ----------- */
+void fmgpu_create_fir_lpf(float* b, int N, float k);
+void fmgpu_create_fir_hpf(float* b, int N, float k);
+void fmgpu_create_fir_bpf(float* b, int N, float k1, float k2);
+void fmgpu_create_fir_hilbert(float* b, int N);
+void fmgpu_create_iir_single_pole_lpf(float* b, float* a, float k);
+void fmgpu_create_iir_notch_filter(float* b, float* a, float k, float r);
+void fmgpu_create_iir_peak_1_filter(float* b, float* a, float k, float r);
+
+/* ---- stand-alone resamplers: src/dsp/polyphase_filter.h (PolyphaseDownsampler<T>::process,
+ * :41-64) on the GPU.  Host pointers; state (the last M*K inputs) lives in the object. ---------- */
+typedef struct fmgpu_polyphase fmgpu_polyphase;
+int  fmgpu_polyphase_ds_create(int M, int K, int is_complex, fmgpu_polyphase** out);
+void fmgpu_polyphase_destroy(fmgpu_polyphase* f);
+float* fmgpu_polyphase_get_b(fmgpu_polyphase* f);       /* host array of M*K taps, like get_b() */
+int  fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* y_host, int n_out);
+
+/* ---- RDS bit path on the host (differential_manchester_decoder.h:25-59, rds_group_sync.cpp,
+ * crc10.cpp, and the PI/PTY/PS/RT subset of rds_decoder.cpp) ---------------------------------- */
+typedef struct fmgpu_rds_group {
+    uint16_t data[4];
+    uint8_t  valid[4];
+    uint8_t  type[4];        /* BlockOffsetID: A=0 B=1 C=2 C1=3 D=4 (rds_constants.h:29)       */
+} fmgpu_rds_group;
+fmgpu_rds* fmgpu_rds_create(void);
+void fmgpu_rds_destroy(fmgpu_rds* r);
+void fmgpu_rds_push_symbols(fmgpu_rds* r, const float* sym, size_t n);
+int  fmgpu_rds_n_groups(const fmgpu_rds* r);
+int  fmgpu_rds_get_groups(const fmgpu_rds* r, fmgpu_rds_group* out, int max_groups);
+int  fmgpu_rds_n_bytes(const fmgpu_rds* r);
+int  fmgpu_rds_get_bytes(const fmgpu_rds* r, uint8_t* out, int max_bytes);
+void fmgpu_rds_get_db(const fmgpu_rds* r, uint16_t* pi, char ps8[8], char rt64[64], uint8_t* pty);
+
+const char* fmgpu_last_error(void);
+const char* fmgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMGPU_H */
