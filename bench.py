@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the FM stereo + RDS demodulation hot path (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU chain
+
+Workload = BASELINE.json configs[2] ("config 3"): 1024 independent stereo+RDS streams per GPU,
+one STEP = one 65536-sample IQ block of every stream (67.1 M IQ samples per GPU per step; 128 MiB
+of u8 input per step, larger than the 126 MB L2, cycling over distinct blocks).  Weak scaling:
+N GPUs demodulate N x 1024 streams (config 5's 8192 at N = 8) with no data-path collective.
+
+metric  IQ MS/s demodulated (stereo audio + RDS symbols out), whole job.
+value   inputs resident in HBM, blocks pipelined through the handle's stage streams.
+e2e     the same through the host-facing C-ABI: pinned host u8 in (H2D inside the timed region),
+        audio + RDS symbols out to pinned host memory (D2H inside the timed region) every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 65536
+STREAMS_PER_GPU = 1024
+FS = 1_024_000
+FLOP_PER_SAMPLE_K1 = 64.0          # 64 real taps x (re, im) x FMA=2 x 1/4 output rate
+FLOP_PER_SAMPLE_CHAIN = 160.0      # SURVEY.md 8(d) headline figure
+BYTES_PER_SAMPLE_FUSED = 2.26      # 2 B u8 in + 0.25 B audio + 0.01 B symbols
+BYTES_PER_SAMPLE_K1 = 3.0          # K1 as built: 2 B u8 in + 4 B fm_demod out per 4 samples
+N_SM, FP32_LANES = 148, 128
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference: the unmodified reference's fm_demod_benchmark (oracle/_ref, compiled in place)
+# --------------------------------------------------------------------------------------------
+def _write_capture(args):
+    seed, n_blocks, path = args
+    from fm_radio_b200 import synth
+    synth.synth_u8_numpy(BLOCK * n_blocks, synth.StreamParams.for_stream(seed)).tofile(path)
+    return path
+
+
+def cpu_reference_run(n_procs: int, n_blocks: int, repeats: int, warmup: int, tmpdir: str):
+    """n_procs concurrent `fm_demod_benchmark -b 65536 -i capture` processes (the reference DSP is
+    single threaded), one capture of n_blocks blocks each; returns per-repeat wall s."""
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import bind
+    exe = bind.REF_BENCH
+    kind = "reference"
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/fm_demod_benchmark missing: run __graft_entry__.build() where /root/reference exists")
+    n_unique = min(n_procs, 8)
+    with ProcessPoolExecutor(max_workers=min(n_unique, os.cpu_count() or 1)) as ex:
+        files = list(ex.map(_write_capture, [(s, n_blocks, os.path.join(tmpdir, f"cap{s}.u8")) for s in range(n_unique)]))
+    times = []
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([exe, "-b", str(BLOCK), "-i", files[i % n_unique]], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL) for i in range(n_procs)]
+        for p in procs:
+            p.wait()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_blocks = 156                      # 10 s of signal per process (config 1's capture length)
+    with tempfile.TemporaryDirectory() as td:
+        times, kind = cpu_reference_run(cores, n_blocks, max(args.steps, 1), max(args.warmup, 1), td)
+    samples = cores * n_blocks * BLOCK
+    t = sum(times) / len(times)
+    value = samples / t / 1e6
+    line = {
+        "impl": "reference", "metric": "IQ MS/s demodulated stereo+RDS", "value": value, "unit": "MS/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": max(args.warmup, 1), "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1024 streams x 65536-sample blocks per GPU (BASELINE config 3); reference arm = "
+                               f"{cores} concurrent single-threaded fm_demod_benchmark processes, 10 s capture each",
+                   "block_size": BLOCK},
+        "cpu_baseline": {"value": value, "unit": "MS/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} processes x {n_blocks} blocks x {BLOCK} IQ samples per step"},
+        "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "x_realtime": value * 1e6 / FS,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fm_radio_b200 as fm
+    from fm_radio_b200 import Buf, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    S, B = args.streams, BLOCK
+    n_in = args.input_blocks
+
+    # ---- synthetic stereo+RDS captures for this rank's streams, resident in HBM ----
+    from fm_radio_b200.batch import shard_streams
+    my_streams = shard_streams(S * world, rank, world)
+    params = [synth.StreamParams.for_stream(s) for s in my_streams]
+    cap = torch.empty((n_in, S, 2 * B), dtype=torch.uint8, device=dev)
+    chunk = 64
+    for s0 in range(0, S, chunk):
+        piece = synth.synth_u8_torch(B * n_in, params[s0:s0 + chunk], dev)
+        cap[:, s0:s0 + chunk] = piece.view(len(params[s0:s0 + chunk]), n_in, 2 * B).transpose(0, 1)
+    torch.cuda.synchronize()
+
+    demod = fm.FMDemod(B, S, device=local_rank, pipeline_depth=args.depth)
+    ext = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        demod.sync()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    demod.wait_external_stream(ext)
+    for k in range(args.warmup):
+        demod.enqueue_u8_device(cap[k % n_in])
+    barrier()
+    launches0 = demod.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    demod.wait_external_stream(ext)
+    for k in range(args.steps):
+        demod.enqueue_u8_device(cap[(args.warmup + k) % n_in])
+    demod.signal_external_stream(ext)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = demod.launch_count - launches0
+    slot = (demod.blocks_enqueued - 1) % demod.depth
+    demod.fetch_outputs(slot)
+    demod.sync()
+    audio = demod.get(Buf.AUDIO_OUT, 0)
+    assert np.isfinite(audio).all() and np.abs(audio).max() > 1e-3, "demodulated audio is empty"
+
+    # ---- end to end through the host-facing C-ABI: pinned host in, pinned host out ----
+    n_host = 2
+    host_in = [torch.empty((S, 2 * B), dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+    for i in range(n_host):
+        host_in[i].copy_(cap[i % n_in])
+    torch.cuda.synchronize()
+    e2e_steps = max(4, args.steps // 2)
+    for k in range(2):
+        sl = demod.enqueue_u8_host(host_in[k % n_host]); demod.fetch_outputs(sl)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        sl = demod.enqueue_u8_host(host_in[k % n_host])
+        demod.fetch_outputs(sl)
+    demod.sync()
+    t_e2e = time.perf_counter() - t0
+    h2d = S * 2 * B
+    d2h = S * (B // 32) * 8 + S * (B // 64) * 4 + S * 4
+
+    # ---- per-kernel device times, one block at a time (events inside the library) ----
+    demod.sync()
+    stage_ms = demod.profile_stages(cap[0], 4)
+
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    samples_step = world * S * B
+    value = samples_step * args.steps / t_dev / 1e6
+    e2e_value = samples_step * e2e_steps / t_e2e / 1e6
+
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        fp32_peak = N_SM * FP32_LANES * 2 * sm_max * 1e6 / 1e12             # TFLOP/s at max SM clock
+        k1_ms = stage_ms["k1_fir4_discrim"]
+        k1_flops = FLOP_PER_SAMPLE_K1 * S * B
+        k1_tflops = k1_flops / (k1_ms * 1e-3) / 1e12
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roof = {
+            "kernel": "k1_fir4_discrim", "bound": "fp32",
+            "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp32_peak,
+            "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no fp32 figure; "
+                           "the chain is FP32-FMA bound, not HBM or tensor bound, SURVEY.md 8d)",
+            "traffic": None,
+            "hbm": {"achieved": BYTES_PER_SAMPLE_K1 * S * B / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": BYTES_PER_SAMPLE_K1 * S * B / (k1_ms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+            "flop_per_launch": k1_flops, "ms_per_launch": k1_ms,
+            "chain": {"flop_per_sample": FLOP_PER_SAMPLE_CHAIN,
+                      "achieved_tflops": FLOP_PER_SAMPLE_CHAIN * value * 1e6 / world / 1e12,
+                      "frac_of_fp32_peak": FLOP_PER_SAMPLE_CHAIN * value * 1e6 / world / 1e12 / fp32_peak,
+                      "hbm_frac_fused_min": BYTES_PER_SAMPLE_FUSED * value * 1e6 / world / 1e9 / hbm_peak},
+        }
+        line = {
+            "metric": "IQ MS/s demodulated stereo+RDS", "value": value, "unit": "MS/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{S} streams x {B}-sample u8 IQ blocks per GPU (BASELINE config 3; N GPUs = config 5 sharded by stream)",
+                       "streams_per_gpu": S, "block_size": B, "pipeline_depth": demod.depth,
+                       "l2": f"input per step {S * 2 * B / 2**20:.0f} MiB > 126 MB L2, cycling over {n_in} distinct blocks per stream",
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+            "x_realtime": value * 1e6 / FS,
+            "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "x_realtime": e2e_value * 1e6 / FS,
+                    "api": "fmgpu_enqueue_u8_host + fmgpu_fetch_outputs per block, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "stage_ms_serial": stage_ms,
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1
+            with tempfile.TemporaryDirectory() as td:
+                times, kind = cpu_reference_run(cores, 78, 2, 1, td)       # 5 s of signal per process
+            v = cores * 78 * BLOCK / (sum(times) / len(times)) / 1e6
+            line["cpu_baseline"] = {"value": v, "unit": "MS/s", "cores": cores, "kind": kind,
+                                    "sample": f"{cores} concurrent fm_demod_benchmark processes x 78 blocks x {BLOCK} samples, mean of 2",
+                                    "per_core": v / cores}
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "MS/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    demod.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--depth", type=int, default=4, help="pipeline depth (blocks in flight)")
+    ap.add_argument("--input-blocks", type=int, default=4, help="distinct input blocks per stream kept in HBM")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "fmgpu_enqueue_u8_host", "fmgpu_sync", "fmgpu_fetch_outputs", "fmgpu_wait_external_stream",
     "fmgpu_signal_external_stream", "fmgpu_get_buffer", "fmgpu_get_device_buffer", "fmgpu_get_scalar",
     "fmgpu_set_control", "fmgpu_upload_taps", "fmgpu_download_taps", "fmgpu_get_rates", "fmgpu_get_config",
-    "fmgpu_launch_count", "fmgpu_create_fir_lpf", "fmgpu_create_fir_hpf", "fmgpu_create_fir_bpf",
+    "fmgpu_launch_count", "fmgpu_profile_stages", "fmgpu_create_fir_lpf", "fmgpu_create_fir_hpf", "fmgpu_create_fir_bpf",
     "fmgpu_create_fir_hilbert", "fmgpu_create_iir_single_pole_lpf", "fmgpu_create_iir_notch_filter",
     "fmgpu_create_iir_peak_1_filter", "fmgpu_polyphase_ds_create", "fmgpu_polyphase_destroy",
     "fmgpu_polyphase_get_b", "fmgpu_polyphase_ds_process", "fmgpu_rds_create", "fmgpu_rds_destroy",
@@ -150,6 +150,7 @@ def lib():
     L.fmgpu_get_rates.argtypes = [vp, C.POINTER(ci * 5)]
     L.fmgpu_get_config.argtypes = [vp, C.POINTER(_Config)]
     L.fmgpu_launch_count.argtypes = [vp]
+    L.fmgpu_profile_stages.argtypes = [vp, vp, ci, C.POINTER(C.c_float * 5)]
     L.fmgpu_launch_count.restype = C.c_longlong
     for name in ("lpf", "hpf"):
         getattr(L, f"fmgpu_create_fir_{name}").argtypes = [vp, ci, C.c_float]
@@ -323,6 +324,13 @@ class FMDemod:
         r = (C.c_int * 5)()
         _check(self.L.fmgpu_get_rates(self.h, C.byref(r)), "fmgpu_get_rates")
         return dict(zip(("baseband", "fm_in", "fm_out", "rds", "audio"), list(r)))
+
+    def profile_stages(self, iq_dev, n_blocks: int = 4) -> dict:
+        """Average device ms per kernel with blocks run one at a time (CUDA events inside the library)."""
+        ms = (C.c_float * 5)()
+        _check(self.L.fmgpu_profile_stages(self.h, _ptr(iq_dev), n_blocks, C.byref(ms)), "fmgpu_profile_stages")
+        self.blocks_enqueued += n_blocks
+        return dict(zip(("k1_fir4_discrim", "k2_mpx", "k3_pll", "k4_mix_fir", "k5_bpsk"), [float(x) for x in ms]))
 
     @property
     def launch_count(self) -> int:

@@ -229,7 +229,7 @@ void free_all(fmgpu_demod* h) {
 }
 
 // Enqueue the chain for one block whose input is already ordered on stA (or signalled by ev_H).
-int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
+int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cudaEvent_t* prof = nullptr) {
     update_filters(h);
     const int slot = (int)(h->step % (unsigned long long)h->depth);
     const int parity = (int)(h->step & 1ull);
@@ -247,6 +247,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
         const float Ts = 1.0f / 256000.0f;
         p.discrim_gain = 1.0f / (Wd * Ts) * 0.5f;
         p.n_out = h->n4; p.parity = parity; p.n_streams = h->S;
+        if (prof) CU(cudaEventRecord(prof[0], h->stA));
         CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
     }
     {
@@ -256,9 +257,11 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
         std::memcpy(p.deemph_b, h->taps.deemph_b, 8); std::memcpy(p.deemph_a, h->taps.deemph_a, 8);
         std::memcpy(p.peak_b, h->taps.peak_b, 12); std::memcpy(p.peak_a, h->taps.peak_a, 12);
         p.use_deemph = h->ctl_use_deemph; p.n_out = h->n8; p.keep = keep;
+        if (prof) CU(cudaEventRecord(prof[1], h->stA));
         CU(fm::launch_k2(sl.fm_demod, h->k2_hist_demod, h->k2_hist_out, h->k2_scal, sl.fm_out_iq, sl.theta, sl.power,
                          keep ? h->dbg.pilot : nullptr, p, h->S, h->stA));
     }
+    if (prof) CU(cudaEventRecord(prof[2], h->stA));
     CU(cudaEventRecord(sl.ev_A, h->stA));
 
     // ---- stage B: K3 ----
@@ -271,7 +274,9 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
         p.f_center = -19000.0f; p.f_gain = -100.0f; p.mixer_KTs = Ts;
         p.agc_target = 1.0f; p.agc_beta = 0.2f;
         p.n = h->n8; p.n_streams = h->S; p.keep = keep;
+        if (prof) CU(cudaEventRecord(prof[3], h->stB));
         CU(fm::launch_k3(sl.theta, sl.power, h->pll_state, sl.pll_dt, h->dbg.pll_raw, h->dbg.pll_pi, p, h->stB));
+        if (prof) CU(cudaEventRecord(prof[4], h->stB));
         if (keep) { CU(fm::launch_kdbg(h->dbg.pilot, h->pll_state, sl.pll_dt, h->dbg.pll, h->n8, h->S, h->stB)); h->launches++; }
     }
     CU(cudaEventRecord(sl.ev_B, h->stB));
@@ -288,11 +293,13 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
         p.harmonic_lmr = 38000.0f / 19000.0f; p.harmonic_rds = 57000.0f / 19000.0f;
         p.stereo_mix = h->ctl_stereo_mix; p.audio_out_mode = h->ctl_audio_out;
         p.n = h->n8; p.n_tiles = h->k4_tiles; p.parity = parity; p.n_streams = h->S; p.keep = keep;
+        if (prof) CU(cudaEventRecord(prof[5], h->stC));
         CU(fm::launch_k4(sl.fm_out_iq, sl.pll_dt, h->k4_hist_x[parity], h->k4_hist_m2[parity], h->k4_hist_m3[parity],
                          h->k4_hist_x[parity ^ 1], h->k4_hist_m2[parity ^ 1], h->k4_hist_m3[parity ^ 1],
                          h->lmr_phase, sl.audio, sl.rds, sl.est_partial, sl.rds_pw_partial,
                          h->dbg.lpr, h->dbg.lmr, p, h->stC));
     }
+    if (prof) CU(cudaEventRecord(prof[6], h->stC));
     CU(cudaEventRecord(sl.ev_C, h->stC));
 
     // ---- stage D: K5 ----
@@ -314,8 +321,10 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H) {
         p.ted_Kp = 0.3f; p.pll_Kp = 0.3f;
         p.agc_target = 0.5f; p.agc_beta = 0.2f;
         p.n = h->n64; p.n_tiles_k4 = h->k4_tiles; p.n_streams = h->S; p.keep = keep;
+        if (prof) CU(cudaEventRecord(prof[7], h->stD));
         CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, h->stD));
     }
+    if (prof) CU(cudaEventRecord(prof[8], h->stD));
     CU(cudaEventRecord(sl.ev_D, h->stD));
     h->launches += 6;
     h->step++;
@@ -449,6 +458,29 @@ int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev) {
     CU(cudaSetDevice(h->device));
     const int rc = enqueue_chain(h, iq_dev, true, false);
     return rc < 0 ? rc : FMGPU_OK;
+}
+
+int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[5]) {
+    if (!h || !iq_dev || !ms || n_blocks < 1) return fail(FMGPU_ERR_ARG, "profile_stages: bad argument");
+    CU(cudaSetDevice(h->device));
+    cudaEvent_t ev[9];
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    double acc[5] = { 0, 0, 0, 0, 0 };
+    const int pairs[5][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 } };
+    for (int b = 0; b < n_blocks; b++) {
+        if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+        const int rc = enqueue_chain(h, iq_dev, true, false, ev);
+        if (rc < 0) return rc;
+        if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+        for (int i = 0; i < 5; i++) {
+            float t = 0.0f;
+            CU(cudaEventElapsedTime(&t, ev[pairs[i][0]], ev[pairs[i][1]]));
+            acc[i] += t;
+        }
+    }
+    for (int i = 0; i < 5; i++) ms[i] = (float)(acc[i] / n_blocks);
+    for (auto& e : ev) cudaEventDestroy(e);
+    return FMGPU_OK;
 }
 
 int fmgpu_sync(fmgpu_demod* h) {

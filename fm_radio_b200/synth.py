@@ -155,45 +155,31 @@ def synth_u8_numpy(n_samples: int, p: StreamParams | None = None) -> np.ndarray:
     return np.clip(np.rint(127.0 + iq), 0, 255).astype(np.uint8).reshape(-1)
 
 
-def synth_u8_torch(n_samples: int, params: list[StreamParams], device, out=None, sample_offset: int = 0):
-    """torch.uint8 tensor [len(params), 2*n_samples] on `device`; one row per stream.
-
-    `sample_offset` lets the caller generate a long capture in consecutive pieces: piece k covers
-    samples [sample_offset, sample_offset + n_samples) with continuous phase (the FM phase
-    integral is restarted per piece from its exact closed form for the tones and pilot, and the
-    RDS term is small enough (6 %) that a per-piece restart of its integral is not used: instead
-    the cumulative sum is carried by the caller through `synth_u8_torch.carry`)."""
+def synth_u8_torch(n_samples: int, params: list[StreamParams], device):
+    """torch.uint8 tensor [len(params), 2*n_samples] on `device`, one row per stream: the same
+    recipe as synth_u8_numpy evaluated with torch ops (float64 phase, torch's own noise generator)."""
     import torch
     fs = float(FS_BASEBAND)
-    S = len(params)
     dev = torch.device(device)
-    n = torch.arange(sample_offset, sample_offset + n_samples, dtype=torch.float64, device=dev)
-    t = n / fs
-    if out is None:
-        out = torch.empty((S, 2 * n_samples), dtype=torch.uint8, device=dev)
-    n_chips_total = int(np.ceil((sample_offset + n_samples) * RDS_CHIP_RATE / fs)) + 2
+    t = torch.arange(n_samples, dtype=torch.float64, device=dev) / fs
+    out = torch.empty((len(params), 2 * n_samples), dtype=torch.uint8, device=dev)
+    n_chips = int(np.ceil(n_samples * RDS_CHIP_RATE / fs)) + 2
     u = t * RDS_CHIP_RATE
     ci = torch.floor(u).to(torch.int64)
     shape = torch.sin(np.pi * (u - ci)) ** 2
-    carry = getattr(synth_u8_torch, "_carry", None)
-    if carry is None or sample_offset == 0 or carry.shape[0] != S or carry.device != dev:
-        carry = torch.zeros(S, dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev)
     for s, p in enumerate(params):
         left = _audio(t, p.tones_left, torch)
         right = _audio(t, p.tones_right, torch)
         wp = 2 * np.pi * F_PILOT * t + p.pilot_phase
-        chips = torch.from_numpy(rds_chips(p, n_chips_total)).to(dev)
+        chips = torch.from_numpy(rds_chips(p, n_chips)).to(dev)
         rds = chips[ci] * shape
         mpx = (0.40 * (left + right) / 1.4 + 0.10 * torch.sin(wp)
                + 0.40 * (left - right) / 1.4 * torch.sin(2 * wp) + 0.06 * rds * torch.sin(3 * wp))
-        csum = torch.cumsum(mpx, 0) + carry[s]
-        carry[s] = csum[-1]
-        phi = 2 * np.pi * F_DEVIATION * csum / fs + 2 * np.pi * p.f_offset_hz * t
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(p.seed * 7919 + sample_offset)
+        phi = 2 * np.pi * F_DEVIATION * torch.cumsum(mpx, 0) / fs + 2 * np.pi * p.f_offset_hz * t
+        gen.manual_seed(p.seed)
         sigma = p.amplitude * 10.0 ** (-p.snr_db / 20.0) * np.sqrt(0.5)
         noise = torch.randn((n_samples, 2), generator=gen, device=dev, dtype=torch.float32) * sigma
         iq = torch.stack((p.amplitude * torch.cos(phi), p.amplitude * torch.sin(phi)), dim=1).to(torch.float32) + noise
         out[s] = torch.clamp(torch.round(127.0 + iq), 0, 255).to(torch.uint8).reshape(-1)
-    synth_u8_torch._carry = carry
     return out

@@ -163,6 +163,10 @@ int fmgpu_download_taps(fmgpu_demod* h, fmgpu_filter which, float* b, float* a, 
 /* Sample rates (broadcast_fm_demod.h:284-288): baseband, fm_in, fm_out, rds, audio. */
 int fmgpu_get_rates(fmgpu_demod* h, int rates_hz[5]);
 int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out);
+/* Measurement aid: runs n_blocks blocks ONE AT A TIME (no overlap between blocks) on the device
+ * input iq_dev with CUDA events recorded on the launching streams around each kernel, and returns
+ * the average device time in ms of K1, K2, K3, K4(+K4b), K5.  Advances the demodulator state. */
+int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[5]);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long fmgpu_launch_count(fmgpu_demod* h);
 

@@ -1,0 +1,332 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI, against the CPU checkers
+(oracle/fm_oracle.c, and the unmodified reference when oracle/_ref travelled to the box) and the
+committed golden fixtures.
+
+Tolerances:
+  * feed-forward buffers (fm_demod, fm_out_iq, audio_lpr): max-abs <= 1e-4 x RMS of the signal;
+  * buffers behind the PLL / BPSK feedback loops, blocks >= 48 (t >= 3.07 s, "after lock"):
+    max-abs <= 1e-4 OR SNR >= 60 dB;  pll_dt: <= 1e-4 turns;
+  * RDS groups, validity flags, block types, packed bytes, PI / PTY / PS / RT: bit-exact.
+"""
+import numpy as np
+import pytest
+
+import fm_radio_b200 as fm
+from fm_radio_b200 import Buf, Control, Filter, Scalar, synth
+from oracle import bind
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TAP_IDS = {"fm_in": Filter.FM_IN, "fm_out": Filter.FM_OUT, "hilbert": Filter.HILBERT, "audio_lpr": Filter.AUDIO_LPR,
+           "audio_lmr": Filter.AUDIO_LMR, "rds": Filter.RDS, "deemphasis": Filter.DEEMPHASIS,
+           "peak_pilot": Filter.PEAK_PILOT, "pll_lpf": Filter.PLL_LPF, "bpsk_ted_lpf": Filter.BPSK_TED_LPF,
+           "bpsk_pll_lpf": Filter.BPSK_PLL_LPF}
+FEED_FORWARD = (("fm_demod", Buf.FM_DEMOD), ("fm_out_iq", Buf.FM_OUT_IQ), ("audio_lpr", Buf.AUDIO_LPR))
+FEEDBACK = (("pilot", Buf.PILOT), ("pll", Buf.PLL), ("audio_lmr", Buf.AUDIO_LMR), ("rds", Buf.RDS),
+            ("audio_out", Buf.AUDIO_OUT))
+
+
+def _assert_ff(got, ref, what):
+    assert np.abs(got - ref).max() <= 1e-4 * max(np.sqrt(np.mean(np.abs(ref) ** 2)), 1e-3), what
+
+
+def _assert_fb(got, ref, what):
+    assert np.abs(got - ref).max() <= 1e-4 or H.snr_db(got, ref) >= 60.0, (what, np.abs(got - ref).max(), H.snr_db(got, ref))
+
+
+@pytest.mark.parametrize("kind", H.cpu_checker_kinds())
+@pytest.mark.parametrize("tag", ["seed0", "stream7"])
+def test_single_stream_every_stage_matches_checker(kind, tag):
+    iq = H.capture(tag)
+    chk = bind.CpuDemod(H.B, kind)
+    g = fm.FMDemod(H.B, 1, keep_intermediates=True)
+    dec = fm.RDSDecoder()
+    n_sym_g = n_sym_c = 0
+    for k in range(70):
+        blk = iq[2 * H.B * k:2 * H.B * (k + 1)]
+        chk.process_u8(blk)
+        if k == 0:      # same coefficients on both sides (the designers are tested separately)
+            H.copy_taps(chk, lambda name, b, a: g.upload_taps(TAP_IDS[name], b, a))
+        g.process_u8(blk)
+        sym = g.get(Buf.RDS_PRED_SYM)
+        dec.push_symbols(sym)
+        n_sym_g += len(sym); n_sym_c += len(chk.get("rds_pred_sym"))
+        for name, buf in FEED_FORWARD:
+            _assert_ff(g.get(buf), chk.get(name), (k, name))
+        if k >= H.LOCK_BLOCK:
+            for name, buf in FEEDBACK:
+                _assert_fb(g.get(buf), chk.get(name), (k, name))
+            assert H.wrap_turn_diff(g.get(Buf.PLL_DT), chk.get("pll_dt")).max() <= 1e-4, k
+            assert np.abs(g.get(Buf.PLL_RAW_PHASE_ERROR) - chk.get("pll_raw_phase_error")).max() <= 1e-3
+            assert abs(g.scalar(Scalar.AUDIO_LMR_PHASE_ERROR) - chk.scalar("audio_lmr_phase_error")) <= 1e-3
+            assert abs(g.scalar(Scalar.AGC_PILOT_GAIN) / chk.scalar("agc_pilot_gain") - 1) <= 1e-4
+            assert abs(g.scalar(Scalar.AGC_RDS_GAIN) / chk.scalar("agc_rds_gain") - 1) <= 1e-3
+    assert abs(n_sym_g - n_sym_c) <= 1
+    for a, b in zip(dec.groups(), chk.groups()):
+        assert np.array_equal(a, b)                      # bit-exact group sequence, validity, block types
+    assert dec.rds_bytes() == chk.rds_bytes()            # byte-exact at equal block size
+    assert dec.db() == chk.db()
+    assert len(dec.groups()[0]) >= 40
+    g.close()
+
+
+@pytest.mark.parametrize("tag", ["seed0", "stream7"])
+def test_matches_golden_fixture_of_the_reference(tag):
+    gold = H.golden(tag)
+    iq = H.capture(tag)
+    g = fm.FMDemod(H.B, 1, keep_intermediates=True)
+    for name, fid in TAP_IDS.items():
+        b, a = gold[f"taps_{name}_b"], gold[f"taps_{name}_a"]
+        g.upload_taps(fid, b, a[:len(b)] if name in H.IIR_NAMES else None)
+    dec = fm.RDSDecoder()
+    syms = []
+    for k in range(int(gold["n_blocks"])):
+        g.process_u8(iq[2 * H.B * k:2 * H.B * (k + 1)])
+        syms.append(g.get(Buf.RDS_PRED_SYM))
+        dec.push_symbols(syms[-1])
+        if f"blk{k}_fm_demod" in gold:
+            for name, buf in FEED_FORWARD:
+                _assert_ff(H.pick(g.get(buf)), gold[f"blk{k}_{name}"], (k, name))
+            if k >= H.LOCK_BLOCK:
+                for name, buf in FEEDBACK:
+                    _assert_fb(H.pick(g.get(buf)), gold[f"blk{k}_{name}"], (k, name))
+                assert H.wrap_turn_diff(H.pick(g.get(Buf.PLL_DT)), gold[f"blk{k}_pll_dt"]).max() <= 1e-4
+    d, v, t = dec.groups()
+    assert np.array_equal(d, gold["groups_data"]) and np.array_equal(v, gold["groups_valid"]) and np.array_equal(t, gold["groups_type"])
+    assert dec.rds_bytes() == gold["rds_bytes"].tobytes()
+    db = dec.db()
+    assert db["pi"] == int(gold["db_pi"][0]) and db["ps"] == gold["db_ps"].tobytes() and db["rt"] == gold["db_rt"].tobytes()
+    sym = np.concatenate(syms)
+    n = min(len(sym), len(gold["symbols"]))
+    assert abs(len(sym) - len(gold["symbols"])) <= 1
+    assert np.mean(np.sign(sym[:n]) == np.sign(gold["symbols"][:n])) > 0.999
+    g.close()
+
+
+def test_small_blocks_match_golden_and_checker():
+    gold = H.golden("seed0_b4096")
+    bs, nb = int(gold["block_size"]), int(gold["n_blocks"])
+    iq = H.capture("seed0")[:2 * bs * nb]
+    g = fm.FMDemod(bs, 1)
+    dec = fm.RDSDecoder()
+    for k in range(nb):
+        g.process_u8(iq[2 * bs * k:2 * bs * (k + 1)])
+        dec.push_symbols(g.get(Buf.RDS_PRED_SYM))
+    d, v, _ = dec.groups()
+    assert np.array_equal(d, gold["groups_data"]) and np.array_equal(v, gold["groups_valid"])
+    assert dec.rds_bytes() == gold["rds_bytes"].tobytes()
+    g.close()
+    # minimum block size 1024: every FIR history spans exactly one previous block
+    bs = 1024
+    nb = 3 * 1024
+    chk = bind.CpuDemod(bs, "port")
+    g = fm.FMDemod(bs, 1, keep_intermediates=True)
+    dec = fm.RDSDecoder()
+    for k in range(nb):
+        blk = iq[2 * bs * k:2 * bs * (k + 1)]
+        chk.process_u8(blk); g.process_u8(blk)
+        dec.push_symbols(g.get(Buf.RDS_PRED_SYM))
+        if k % 97 == 0:
+            for name, buf in FEED_FORWARD:
+                _assert_ff(g.get(buf), chk.get(name), (k, name))
+    for a, b in zip(dec.groups(), chk.groups()):
+        assert np.array_equal(a, b)
+    assert len(dec.groups()[0]) >= 10
+    g.close()
+
+
+def test_batched_streams_async_pipeline_matches_per_stream_checker():
+    """8 different streams in one batch through the asynchronous device-buffer path (depth 3 ring),
+    each compared with its own checker; also bitwise equal to the synchronous host-buffer path."""
+    import torch
+    S, nblk = 8, 64
+    caps = np.stack([synth.synth_u8_numpy(H.B * nblk, synth.StreamParams.for_stream(100 + s)) for s in range(S)])
+    dev_in = torch.from_numpy(caps).cuda()
+    g = fm.FMDemod(H.B, S, pipeline_depth=3)
+    gs = fm.FMDemod(H.B, S)
+    decs = [fm.RDSDecoder() for _ in range(S)]
+    audio_async, audio_sync = [], []
+    g.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    pending = []
+    for k in range(nblk):
+        blk = dev_in[:, 2 * H.B * k:2 * H.B * (k + 1)].contiguous()
+        pending.append(blk)           # keep the input alive while it is in flight
+        slot = g.enqueue_u8_device(blk)
+        g.fetch_outputs(slot)
+        if (k + 1) % 3 == 0 or k == nblk - 1:
+            pass
+        g.sync()                      # outputs of the slot are valid now
+        for s in range(S):
+            decs[s].push_symbols(g.get(Buf.RDS_PRED_SYM, s))
+        if k >= H.LOCK_BLOCK:
+            audio_async.append(np.stack([g.get(Buf.AUDIO_OUT, s) for s in range(S)]))
+        gs.process_u8(caps[:, 2 * H.B * k:2 * H.B * (k + 1)].copy())
+        if k >= H.LOCK_BLOCK:
+            audio_sync.append(np.stack([gs.get(Buf.AUDIO_OUT, s) for s in range(S)]))
+    assert np.array_equal(np.stack(audio_async), np.stack(audio_sync))
+    for s in range(S):
+        chk = bind.CpuDemod(H.B, "port")
+        ref_audio = []
+        for k in range(nblk):
+            chk.process_u8(caps[s, 2 * H.B * k:2 * H.B * (k + 1)])
+            if k >= H.LOCK_BLOCK:
+                ref_audio.append(chk.get("audio_out"))
+        for a, b in zip(decs[s].groups(), chk.groups()):
+            assert np.array_equal(a, b), s
+        assert decs[s].db() == chk.db()
+        assert decs[s].db()["pi"] == 0x1000 + 100 + s
+        got = np.stack(audio_async)[:, s, :].reshape(-1)
+        _assert_fb(got, np.concatenate(ref_audio), ("audio", s))
+    g.close(); gs.close()
+
+
+def test_overlapped_pipeline_equals_serial():
+    """Many blocks in flight (no sync between enqueues) give bit-identical results to one at a time."""
+    import torch
+    S, nblk = 64, 12
+    rng = np.random.default_rng(5)
+    base = synth.synth_u8_numpy(H.B * nblk, synth.StreamParams.for_stream(9)).reshape(nblk, 2 * H.B)
+    caps = np.empty((nblk, S, 2 * H.B), np.uint8)
+    for s in range(S):
+        caps[:, s, :] = np.roll(base, 2 * 997 * s, axis=1) if s else base
+    dev = torch.from_numpy(caps).cuda()
+    a = fm.FMDemod(H.B, S, pipeline_depth=4)
+    b = fm.FMDemod(H.B, S, pipeline_depth=1)
+    a.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    b.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    out_a, out_b = [], []
+    slots = []
+    for k in range(nblk):
+        slot = a.enqueue_u8_device(dev[k])
+        slots.append(slot)
+        if k >= 3:      # fetch with a lag of 3 blocks: 4 blocks are in flight
+            a.fetch_outputs(slots[k - 3]); a.sync()
+            out_a.append(np.stack([a.get(Buf.AUDIO_OUT, s) for s in (0, 1, S - 1)]))
+    for k in range(nblk - 3, nblk):
+        a.fetch_outputs(slots[k]); a.sync()
+        out_a.append(np.stack([a.get(Buf.AUDIO_OUT, s) for s in (0, 1, S - 1)]))
+    for k in range(nblk):
+        b.enqueue_u8_device(dev[k]); b.fetch_outputs(0); b.sync()
+        out_b.append(np.stack([b.get(Buf.AUDIO_OUT, s) for s in (0, 1, S - 1)]))
+    assert np.array_equal(np.stack(out_a), np.stack(out_b))
+    a.close(); b.close()
+
+
+def test_controls_match_checker():
+    iq = H.capture("seed0")
+    chk = bind.CpuDemod(H.B, "port")
+    g = fm.FMDemod(H.B, 1, keep_intermediates=True)
+    for k in range(60):
+        if k == 50:
+            chk.set_control("is_use_deemphasis_filter", 1); g.set_control(Control.USE_DEEMPHASIS, 1)
+            chk.set_control("filt_deemphasis_cutoff", 50); g.set_control(Control.DEEMPHASIS_TUS, 50)
+            chk.set_control("filt_audio_lpr_cutoff", 8000); g.set_control(Control.AUDIO_LPR_CUTOFF_HZ, 8000)
+            chk.set_control("filt_audio_lmr_cutoff", 12000); g.set_control(Control.AUDIO_LMR_CUTOFF_HZ, 12000)
+            chk.set_control("audio_stereo_mix_factor", 0.5); g.set_control(Control.AUDIO_STEREO_MIX_FACTOR, 0.5)
+        if k == 55:
+            chk.set_control("audio_out", 0); g.set_control(Control.AUDIO_OUT, 0)
+        if k == 57:
+            chk.set_control("audio_out", 1); g.set_control(Control.AUDIO_OUT, 1)
+        blk = iq[2 * H.B * k:2 * H.B * (k + 1)]
+        chk.process_u8(blk); g.process_u8(blk)
+        if k >= 48:
+            _assert_ff(g.get(Buf.FM_OUT_IQ), chk.get("fm_out_iq"), (k, "fm_out_iq"))
+            _assert_ff(g.get(Buf.AUDIO_LPR), chk.get("audio_lpr"), (k, "audio_lpr"))
+            _assert_fb(g.get(Buf.AUDIO_OUT), chk.get("audio_out"), (k, "audio_out"))
+    g.close()
+
+
+def test_cf32_entry_point_equals_u8_entry_point():
+    iq = H.capture("seed0")
+    a, b = fm.FMDemod(H.B, 1), fm.FMDemod(H.B, 1)
+    for k in range(6):
+        blk = iq[2 * H.B * k:2 * H.B * (k + 1)]
+        a.process_u8(blk)
+        f = (blk.astype(np.float32) - 127.0).view(np.complex64)     # App::Run, src/app.cpp:56-65
+        b.process_cf32(f)
+        assert np.array_equal(a.get(Buf.AUDIO_OUT), b.get(Buf.AUDIO_OUT))
+        assert np.array_equal(a.get(Buf.RDS_PRED_SYM), b.get(Buf.RDS_PRED_SYM))
+    a.close(); b.close()
+
+
+def test_wrong_size_block_is_ignored_like_the_reference():
+    g = fm.FMDemod(H.B, 1)
+    iq = H.capture("seed0")
+    g.process_u8(iq[:2 * H.B])
+    before = g.get(Buf.AUDIO_OUT)
+    n = g.launch_count
+    g.process_u8(iq[:H.B])                   # wrong size: silently ignored (broadcast_fm_demod.cpp:311-313)
+    assert g.launch_count == n
+    assert np.array_equal(g.get(Buf.AUDIO_OUT), before)
+    rc = g.L.fmgpu_process_u8(g.h, iq.ctypes.data, H.B // 2)
+    assert rc == -4
+    with pytest.raises(fm.FMGPUError):
+        fm.FMDemod(1000, 1)
+    with pytest.raises(fm.FMGPUError):
+        fm.FMDemod(512, 1)
+    g.close()
+
+
+def test_all_zero_block_poisons_the_loop_like_the_reference():
+    """An all-127 block makes the pilot AGC compute sqrt(1/0); the reference turns to NaN for good."""
+    z = np.full(2 * H.B, 127, np.uint8)
+    chk = bind.CpuDemod(H.B, "port")
+    g = fm.FMDemod(H.B, 1, keep_intermediates=True)
+    iq = H.capture("seed0")
+    for blk in (z, iq[:2 * H.B], iq[2 * H.B:4 * H.B]):
+        chk.process_u8(blk); g.process_u8(blk)
+        assert np.array_equal(np.isnan(g.get(Buf.PLL_DT)), np.isnan(chk.get("pll_dt")))
+        assert np.array_equal(np.isnan(g.get(Buf.AUDIO_OUT)), np.isnan(chk.get("audio_out")))
+        _assert_ff(g.get(Buf.AUDIO_LPR), chk.get("audio_lpr"), "lpr")
+    g.close()
+
+
+def test_polyphase_downsampler_api_matches_checker():
+    Lp = bind.lib("port")
+    rng = np.random.default_rng(2)
+    for (M, K, n_out, calls, cplx) in ((4, 16, 4096, 3, True), (2, 32, 100, 4, False), (8, 16, 33, 5, True), (3, 5, 7, 6, False)):
+        C = 2 if cplx else 1
+        b = rng.standard_normal(M * K).astype(np.float32)
+        x = rng.standard_normal(C * M * n_out * calls).astype(np.float32)
+        ref = np.zeros(C * n_out * calls, np.float32)
+        (Lp.polyphase_ds_cf32 if cplx else Lp.polyphase_ds_f32)(M, K, b.ctypes.data, x.ctypes.data, ref.ctypes.data, n_out, calls)
+        f = fm.PolyphaseDownsampler(M, K, cplx)
+        assert f.get_K() == M * K
+        f.get_b()[:] = b
+        xs = x.view(np.complex64) if cplx else x
+        got = np.concatenate([f.process(xs[c * M * n_out:(c + 1) * M * n_out], n_out) for c in range(calls)])
+        ref = ref.view(np.complex64) if cplx else ref
+        assert np.abs(got - ref).max() <= 1e-4 * np.sqrt(np.mean(np.abs(ref) ** 2)) * 10
+
+
+def test_full_batch_1024_streams_properties_and_sampled_checker():
+    """BASELINE config 3 size (1024 streams x 65536-sample blocks): (a) batch invariance -- a stream's
+    result does not depend on where it sits in the batch or on the batch size, bit for bit;
+    (b) a sample of streams against the checker on the bytes actually processed."""
+    import torch
+    S, nblk = 1024, 4
+    params = [synth.StreamParams.for_stream(s % 16) for s in range(S)]     # 16 distinct captures, repeated
+    dev = torch.empty((nblk, S, 2 * H.B), dtype=torch.uint8, device="cuda")
+    uniq = synth.synth_u8_torch(H.B * nblk, params[:16], "cuda")
+    for k in range(nblk):
+        dev[k] = uniq[:, 2 * H.B * k:2 * H.B * (k + 1)].repeat(S // 16, 1)
+    g = fm.FMDemod(H.B, S, pipeline_depth=2)
+    g1 = fm.FMDemod(H.B, 16)
+    g.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    g1.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    chk = {s: bind.CpuDemod(H.B, "port") for s in (0, 5, 15)}
+    for k in range(nblk):
+        slot = g.enqueue_u8_device(dev[k]); g.fetch_outputs(slot); g.sync()
+        small = dev[k, :16].contiguous()
+        s1 = g1.enqueue_u8_device(small); g1.fetch_outputs(s1); g1.sync()
+        for s in (0, 3, 15):
+            for rep in (0, 17, 63):
+                assert np.array_equal(g.get(Buf.AUDIO_OUT, s + 16 * rep), g1.get(Buf.AUDIO_OUT, s))
+                assert np.array_equal(g.get(Buf.RDS_PRED_SYM, s + 16 * rep), g1.get(Buf.RDS_PRED_SYM, s))
+        host = dev[k, :16].cpu().numpy()
+        for s, c in chk.items():
+            c.process_u8(host[s])
+            lpr = 0.25 * (g.get(Buf.AUDIO_OUT, s + 16 * 40)[0::2] + g.get(Buf.AUDIO_OUT, s + 16 * 40)[1::2])
+            _assert_ff(lpr, c.get("audio_lpr"), (k, s))       # (L+R)/2 of the stereo mix is the feed-forward L+R path
+    g.close(); g1.close()

@@ -1,0 +1,145 @@
+"""CPU suite: pins the C restatement (oracle/fm_oracle.c) to the unmodified reference and to the
+golden fixtures generated from it.  No GPU needed.
+
+Tolerances (also in DESIGN.md): feed-forward stages must match to <= 1e-4 of the signal RMS
+(achieved ~1e-6); stages behind the pilot PLL / BPSK feedback loops are compared after lock
+(blocks >= 48) by max-abs <= 1e-4 OR SNR >= 60 dB, because fp32 rounding differences are amplified
+by the loops (reference-vs-reference across ISAs already differs by ~3e-5).
+RDS groups / bytes / PI / PS / RT are bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import bind
+from tests import helpers as H
+
+FEED_FORWARD = ("fm_demod", "fm_out_iq", "audio_lpr")
+FEEDBACK = ("pilot", "pll", "audio_lmr", "rds", "audio_out")
+
+
+def test_generator_is_reproducible():
+    for tag in ("seed0", "stream7"):
+        g = H.golden(tag)
+        iq = H.capture(tag)
+        assert np.array_equal(iq[:256], g["input_head"])
+        assert np.array_equal(H.sha256(iq), g["input_sha256"]), "synthetic capture generator changed"
+
+
+@pytest.mark.parametrize("tag", ["seed0", "stream7"])
+def test_port_matches_golden(tag):
+    g = H.golden(tag)
+    iq = H.capture(tag)
+    p = bind.CpuDemod(H.B, "port")
+    counts = []
+    for k in range(int(g["n_blocks"])):
+        p.process_u8(iq[2 * H.B * k:2 * H.B * (k + 1)])
+        counts.append(len(p.get("rds_pred_sym")))
+        if f"blk{k}_fm_demod" in g:
+            for name in FEED_FORWARD:
+                ref = g[f"blk{k}_{name}"]
+                got = H.pick(p.get(name))
+                assert np.abs(got - ref).max() <= 1e-4 * max(np.sqrt(np.mean(np.abs(ref) ** 2)), 1e-3), (k, name)
+            if k >= H.LOCK_BLOCK:
+                for name in FEEDBACK:
+                    ref = g[f"blk{k}_{name}"]
+                    got = H.pick(p.get(name))
+                    assert np.abs(got - ref).max() <= 1e-4 or H.snr_db(got, ref) >= 60.0, (k, name, H.snr_db(got, ref))
+                d = H.wrap_turn_diff(H.pick(p.get("pll_dt")), g[f"blk{k}_pll_dt"])
+                assert d.max() <= 1e-4, (k, d.max())
+    d, v, t = p.groups()
+    assert np.array_equal(d, g["groups_data"]) and np.array_equal(v, g["groups_valid"]) and np.array_equal(t, g["groups_type"])
+    assert p.rds_bytes() == g["rds_bytes"].tobytes()
+    db = p.db()
+    assert db["pi"] == int(g["db_pi"][0]) and db["pty"] == int(g["db_pty"][0])
+    assert db["ps"] == g["db_ps"].tobytes() and db["rt"] == g["db_rt"].tobytes()
+    assert abs(int(np.sum(counts)) - int(g["sym_counts"].sum())) <= 1
+    assert abs(p.scalar("audio_lmr_phase_error") - float(g["lmr_phase"][-1])) < 2e-3
+
+
+def test_port_matches_golden_small_blocks():
+    g = H.golden("seed0_b4096")
+    bs, nb = int(g["block_size"]), int(g["n_blocks"])
+    iq = H.capture("seed0", 70)[:2 * bs * nb]
+    p = bind.CpuDemod(bs, "port")
+    for k in range(nb):
+        p.process_u8(iq[2 * bs * k:2 * bs * (k + 1)])
+    d, v, t = p.groups()
+    assert np.array_equal(d, g["groups_data"]) and np.array_equal(v, g["groups_valid"])
+    assert p.rds_bytes() == g["rds_bytes"].tobytes()
+
+
+@pytest.mark.skipif(not bind.available("ref"), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_matches_reference_live():
+    iq = H.capture("seed0")
+    r, p = bind.CpuDemod(H.B, "ref"), bind.CpuDemod(H.B, "port")
+    sr, sp = [], []
+    for k in range(70):
+        blk = iq[2 * H.B * k:2 * H.B * (k + 1)]
+        r.process_u8(blk); p.process_u8(blk)
+        sr.append(r.get("rds_pred_sym")); sp.append(p.get("rds_pred_sym"))
+        for name in FEED_FORWARD:
+            a, b = r.get(name), p.get(name)
+            assert np.abs(a - b).max() <= 1e-4 * np.sqrt(np.mean(np.abs(a) ** 2)), (k, name)
+        if k >= H.LOCK_BLOCK:
+            for name in FEEDBACK:
+                a, b = r.get(name), p.get(name)
+                assert np.abs(a - b).max() <= 1e-4 or H.snr_db(b, a) >= 60.0, (k, name)
+            assert H.wrap_turn_diff(r.get("pll_dt"), p.get("pll_dt")).max() <= 1e-4
+    for x, y in zip(r.groups(), p.groups()):
+        assert np.array_equal(x, y)
+    assert r.rds_bytes() == p.rds_bytes()
+    assert r.db() == p.db()
+    sr, sp = np.concatenate(sr), np.concatenate(sp)
+    n = min(len(sr), len(sp))
+    assert abs(len(sr) - len(sp)) <= 1
+    assert np.mean(np.sign(sr[:n]) == np.sign(sp[:n])) > 0.999
+
+
+@pytest.mark.skipif(not bind.available("ref"), reason="oracle/_ref not built")
+def test_port_filter_designers_match_reference():
+    Lr, Lp = bind.lib("ref"), bind.lib("port")
+    rng = np.random.default_rng(0)
+    for N in (16, 64, 65, 128):
+        for k in rng.uniform(0.02, 0.95, 4):
+            a, b = np.zeros(N, np.float32), np.zeros(N, np.float32)
+            Lr.create_fir_lpf(a.ctypes.data, N, float(k)); Lp.create_fir_lpf(b.ctypes.data, N, float(k))
+            assert np.abs(a - b).max() < 2e-7
+            Lr.create_fir_hpf(a.ctypes.data, N, float(k)); Lp.create_fir_hpf(b.ctypes.data, N, float(k))
+            assert np.abs(a - b).max() < 2e-7
+        Lr.create_fir_hilbert(a.ctypes.data, N); Lp.create_fir_hilbert(b.ctypes.data, N)
+        assert np.abs(a - b).max() < 1e-7      # -ffast-math reciprocal: 1 ulp
+    for k in (0.003, 0.1, 0.5, 0.9):
+        ba, aa, bb, ab = (np.zeros(3, np.float32) for _ in range(4))
+        Lr.create_iir_single_pole_lpf(ba.ctypes.data, aa.ctypes.data, k); Lp.create_iir_single_pole_lpf(bb.ctypes.data, ab.ctypes.data, k)
+        assert np.allclose(ba, bb, rtol=2e-6, atol=1e-9) and np.allclose(aa, ab, rtol=2e-6, atol=1e-9)
+    # create_iir_peak_1_filter normalises with a `static` lambda that captures (k, r) of the FIRST
+    # call in the process (filter_designer.cpp:288), so only the demodulator's own parameters
+    # (broadcast_fm_demod.cpp:205-209) can be compared.
+    bind.CpuDemod(1024, "ref")
+    k = 19000.0 / (128000.0 / 2.0)
+    Lr.create_iir_peak_1_filter(ba.ctypes.data, aa.ctypes.data, k, 0.9999); Lp.create_iir_peak_1_filter(bb.ctypes.data, ab.ctypes.data, k, 0.9999)
+    assert np.allclose(ba, bb, rtol=1e-3, atol=1e-12) and np.allclose(aa, ab, rtol=2e-6)   # (1-r) cancellation in fp32
+
+
+@pytest.mark.skipif(not bind.available("ref"), reason="oracle/_ref not built")
+def test_port_polyphase_matches_reference():
+    Lr, Lp = bind.lib("ref"), bind.lib("port")
+    rng = np.random.default_rng(1)
+    for (M, K, n_out, calls) in ((4, 16, 96, 3), (2, 32, 10, 5), (8, 16, 256, 2), (3, 5, 7, 4)):
+        b = rng.standard_normal(M * K).astype(np.float32)
+        x = rng.standard_normal(M * n_out * calls).astype(np.float32)
+        ya, yb = np.zeros(n_out * calls, np.float32), np.zeros(n_out * calls, np.float32)
+        Lr.polyphase_ds_f32(M, K, b.ctypes.data, x.ctypes.data, ya.ctypes.data, n_out, calls)
+        Lp.polyphase_ds_f32(M, K, b.ctypes.data, x.ctypes.data, yb.ctypes.data, n_out, calls)
+        assert np.abs(ya - yb).max() < 1e-4
+        xc = rng.standard_normal(2 * M * n_out * calls).astype(np.float32)
+        ya, yb = np.zeros(2 * n_out * calls, np.float32), np.zeros(2 * n_out * calls, np.float32)
+        Lr.polyphase_ds_cf32(M, K, b.ctypes.data, xc.ctypes.data, ya.ctypes.data, n_out, calls)
+        Lp.polyphase_ds_cf32(M, K, b.ctypes.data, xc.ctypes.data, yb.ctypes.data, n_out, calls)
+        assert np.abs(ya - yb).max() < 1e-4
+    for (L, K, n_in, calls) in ((3, 8, 50, 2), (4, 2, 16, 3)):
+        b = rng.standard_normal(L * K).astype(np.float32)
+        x = rng.standard_normal(n_in * calls).astype(np.float32)
+        ya, yb = np.zeros(L * n_in * calls, np.float32), np.zeros(L * n_in * calls, np.float32)
+        Lr.polyphase_us_f32(L, K, b.ctypes.data, x.ctypes.data, ya.ctypes.data, n_in, calls)
+        Lp.polyphase_us_f32(L, K, b.ctypes.data, x.ctypes.data, yb.ctypes.data, n_in, calls)
+        assert np.abs(ya - yb).max() < 1e-4
