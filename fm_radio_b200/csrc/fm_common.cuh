@@ -72,6 +72,12 @@ struct K2Params {
     float taps_hilbert[K2_HILB];
     float deemph_b[2], deemph_a[2];
     float peak_b[3], peak_a[3];
+    // block-parallel linear-recurrence scan (k2_mpx.cu): powers of the recurrences' state matrices,
+    // computed on the host in double.  A = [[a1, a0], [1, 0]] for the pilot filter, alpha = a[0] for
+    // the de-emphasis pole.  P[l] = A^(8 * 2^l) (l = 0..5: thread strides 1..16, then one warp),
+    // Q[j] = A^(8 j) (j = 0..31: offset of lane j inside its warp).
+    float pk_P[6][4], pk_Q[32][4];
+    float de_P[6], de_Q[32];
     int use_deemph;
     int n_out;                  // B/8 fm_out samples per stream
     int keep;                   // write pilot (unscaled) for the debug getters

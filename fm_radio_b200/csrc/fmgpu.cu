@@ -135,6 +135,24 @@ void update_filters(fmgpu_demod* h) {
     }
 }
 
+// Powers of the state matrices of the two linear recurrences of K2, in double (see K2Params).
+void fill_scan_matrices(fm::K2Params& p) {
+    auto matpow = [](double a1, double a0, int n, float out[4]) {
+        double m[4] = { 1, 0, 0, 1 };                       // row-major 2x2
+        for (int i = 0; i < n; i++) {
+            const double r0 = a1 * m[0] + a0 * m[2], r1 = a1 * m[1] + a0 * m[3];
+            m[2] = m[0]; m[3] = m[1]; m[0] = r0; m[1] = r1;  // m = A * m, A = [[a1, a0], [1, 0]]
+        }
+        for (int i = 0; i < 4; i++) out[i] = (float)m[i];
+    };
+    const double a1 = p.peak_a[1], a0 = p.peak_a[0];
+    for (int l = 0; l < 6; l++) matpow(a1, a0, 8 << l, p.pk_P[l]);
+    for (int j = 0; j < 32; j++) matpow(a1, a0, 8 * j, p.pk_Q[j]);
+    const double al = p.deemph_a[0];
+    for (int l = 0; l < 6; l++) p.de_P[l] = (float)std::pow(al, (double)(8 << l));
+    for (int j = 0; j < 32; j++) p.de_Q[j] = (float)std::pow(al, (double)(8 * j));
+}
+
 int init_state(fmgpu_demod* h) {
     // initial values that are not zero: AGC gains 0.1 (dsp/agc.h:10)
     std::vector<float> pll(fm::PLL_STATE_N * (size_t)h->S, 0.0f), bp(fm::BP_STATE_N * (size_t)h->S, 0.0f);
@@ -257,6 +275,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         std::memcpy(p.deemph_b, h->taps.deemph_b, 8); std::memcpy(p.deemph_a, h->taps.deemph_a, 8);
         std::memcpy(p.peak_b, h->taps.peak_b, 12); std::memcpy(p.peak_a, h->taps.peak_a, 12);
         p.use_deemph = h->ctl_use_deemph; p.n_out = h->n8; p.keep = keep;
+        fill_scan_matrices(p);
         if (prof) CU(cudaEventRecord(prof[1], h->stA));
         CU(fm::launch_k2(sl.fm_demod, h->k2_hist_demod, h->k2_hist_out, h->k2_scal, sl.fm_out_iq, sl.theta, sl.power,
                          keep ? h->dbg.pilot : nullptr, p, h->S, h->stA));

@@ -6,18 +6,11 @@
 //     y[i] = sum_k b[k] * x[(i+1)*4 - 64 + k]                (c32_f32_cum_mul.cpp:70-111 on AVX)
 //   FM_Demod::Process, atan2 + wrapped first difference      fm_demod/fm_demod.cpp:30-45
 //
-// Design (FP32-FMA-pipe bound, 64 FLOP per input IQ sample):
-//   * one CTA = 2048 consecutive outputs of one stream = 8192 IQ samples (+64 samples of halo);
-//     the u8 tile is read once with 128-bit coalesced loads, unpacked with PRMT + FADD (no I2F)
-//     and staged in shared memory as fp32, 16-frame segments skewed by 4 banks so that the
-//     per-thread LDS.128 window reads are conflict free;
-//   * each thread owns 16 consecutive outputs (+ the one before them, recomputed bit-identically
-//     so the discriminator's first difference needs no cross-thread or cross-CTA exchange):
-//     34 register accumulators, the window slides one 4-sample frame (2 x LDS.128) per 128 FFMA;
-//   * the 64 taps ride in the kernel parameter block (__grid_constant__), i.e. constant bank 0,
-//     and the tap loop is fully unrolled so every FFMA takes its tap as a c[0][imm] operand:
-//     no register, no load, no issue slot spent on coefficients;
-//   * epilogue: atan2f, wrapped difference, gain; 4 x STG.128 per thread.
+// Two kernels:
+//   k1_fir4_discrim_u8   the production path (rtl-sdr bytes).  FP32-FMA-pipe bound, 64 FLOP per
+//                        input IQ sample; design notes at the kernel.
+//   k1_fir4_discrim<..>  first version, kept for the cf32 entry point (Process(span<cf32>), one
+//                        stream, GUI use) where the input is 4x larger and speed is irrelevant.
 // The previous block's last 64 samples are the only state (ping-pong buffers, because the CTA
 // that reads the history is not the CTA that writes it); the discriminator's prev_theta is
 // recomputed from that history instead of being stored.
@@ -35,6 +28,28 @@ __device__ __forceinline__ float wrap_phase(float x) {          // fm_demod.cpp:
     if (x >= PI_F) return x - 2.0f * PI_F;
     else if (x <= -PI_F) return x + 2.0f * PI_F;
     return x;
+}
+
+// atan2 of the discriminator, shared by both kernels (so the cf32 and u8 entry points give identical
+// bits): minimax odd polynomial of degree 15 on [0, 1], 1.2e-7 rad max error in fp32, one MUFU.RCP.
+__device__ __forceinline__ float fm_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float q = __fdividef(mn, mx);
+    q = (mx == 0.0f) ? 0.0f : q;                         // atan2(0, 0) = 0 as the reference's libm
+    const float s = q * q;
+    float p = -0.004054562299f;
+    p = fmaf(p, s, 0.021862939178f);
+    p = fmaf(p, s, -0.05591229796f);
+    p = fmaf(p, s, 0.096421950378f);
+    p = fmaf(p, s, -0.139086285623f);
+    p = fmaf(p, s, 0.1994656543f);
+    p = fmaf(p, s, -0.333298607622f);
+    p = fmaf(p, s, 0.999999335572f);
+    float r = p * q;
+    r = (ay > ax) ? (0.5f * PI_F - r) : r;
+    r = (x < 0.0f) ? (PI_F - r) : r;
+    return copysignf(r, y);
 }
 
 template <bool U8>
@@ -121,14 +136,176 @@ k1_fir4_discrim(const void* __restrict__ iq, const float2* __restrict__ hist_in,
     }
 
     // ---- discriminator epilogue (fm_demod.cpp:36-44) ----
-    float prev = atan2f(ai[0], ar[0]);
+    float prev = fm_atan2f(ai[0], ar[0]);
     float out[K1_R];
 #pragma unroll
     for (int r = 0; r < K1_R; r++) {
-        const float th = atan2f(ai[r + 1], ar[r + 1]);
+        const float th = fm_atan2f(ai[r + 1], ar[r + 1]);
         out[r] = wrap_phase(th - prev) * p.discrim_gain;
         prev = th;
     }
+    float4* dst = (float4*)(fm_demod + (size_t)s * p.n_out + o0 + t * K1_R);
+#pragma unroll
+    for (int q = 0; q < K1_R / 4; q++) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Production u8 kernel.
+//   * one CTA = 2048 consecutive outputs of one stream = 8192 IQ samples + 64 samples of halo,
+//     staged in shared memory AS BYTES (16.5 KB) with 16-byte cp.async copies (LDGSTS.128): with
+//     the fp32 staging of the first version the tile took 68 KB, 3 CTAs/SM, and ncu showed only
+//     51 % of the issue slots in use (long-scoreboard stalls of the load phase, 12 warps/SM);
+//     bytes let ~7 CTAs/SM co-reside so one CTA's load phase hides under the others' FFMAs;
+//   * rows of 128 B (= 16 four-sample frames = the inputs of 16 outputs) are XOR-swizzled at
+//     16-byte granularity (chunk c of row r lives at chunk c ^ (r & 7)), so the per-thread
+//     window reads (thread t walks rows t and t+1) are bank-conflict free LDS.128;
+//   * each thread owns 16 consecutive outputs: 32 register accumulators; per LDS.128 (two frames)
+//     it unpacks 16 bytes with PRMT + FADD (exact (float)u8 - 127, no I2F) and issues 256 FFMAs;
+//   * the 64 taps ride in the kernel parameter block (__grid_constant__, constant bank 0) and the
+//     tap loop is fully unrolled, so every FFMA takes its tap as a constant operand;
+//   * discriminator: own minimax atan2 (8-term odd polynomial, 1.2e-7 rad max error in fp32, one
+//     MUFU.RCP) instead of libdevice's atan2f (about half the instructions); the previous
+//     output's angle comes from the neighbouring lane (SHFL) / warp (shared), and only thread 0
+//     recomputes the output before the tile (bit-identically to the CTA that owns it).
+// ---------------------------------------------------------------------------------------------
+constexpr int K1U_ROWS = K1_THREADS + 1;                 // 129 rows of 128 bytes
+constexpr int K1U_SMEM = K1U_ROWS * 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gmem_src));
+}
+
+// two frames (8 IQ samples) from one 16-byte chunk, applied to every output they feed
+template <int J0>   // J0 = index of the chunk's first frame relative to the thread's window (even, -0 .. 30)
+__device__ __forceinline__ void k1u_chunk(const uint4 w, float (&ar)[K1_R], float (&ai)[K1_R], const K1Params& p) {
+    const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int j = J0 + h;                           // frame index: output r uses frames r+1 .. r+16
+        float xr[4], xi[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const uint32_t v = ws[2 * h + (m >> 1)];
+            xr[m] = u8_to_f32_m127(v, (m & 1) * 2);
+            xi[m] = u8_to_f32_m127(v, (m & 1) * 2 + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < K1_R; r++) {
+            const int g = j - r - 1;                    // tap group, static after unrolling
+            if (g >= 0 && g < 16) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    ar[r] = fmaf(xr[m], p.taps[4 * g + m], ar[r]);
+                    ai[r] = fmaf(xi[m], p.taps[4 * g + m], ai[r]);
+                }
+            }
+        }
+    }
+}
+
+
+__global__ void __launch_bounds__(K1_THREADS, 6)
+k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hist_in,
+                   float2* __restrict__ hist_out, float* __restrict__ fm_demod,
+                   const __grid_constant__ K1Params p)
+{
+    __shared__ __align__(128) uint8_t s_tile[K1U_SMEM];
+    __shared__ float s_theta[K1_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tile = blockIdx.x, s = blockIdx.y;
+    const int o0 = tile * K1_TILE;
+    const int n_valid = min(K1_TILE, p.n_out - o0);      // outputs of this tile (multiple of 16)
+    const int n_rows = (n_valid >> 4) + 1;               // 128-byte rows to stage, row 0 = halo
+    const size_t n_in = (size_t)p.n_out * K1_M;
+
+    // ---- stage: row q of the tile <-> input bytes [(o0-16)*8 + 128 q, +128) of this stream ----
+    const uint8_t* src = iq + (size_t)s * n_in * 2 + (ptrdiff_t)(o0 - 16) * 8;
+    const int c_first = (tile == 0) ? 8 : 0;             // tile 0 takes its halo row from the history
+    for (int ci = c_first + t; ci < n_rows * 8; ci += K1_THREADS) {
+        const int row = ci >> 3, c = ci & 7;
+        cp_async16(s_tile + row * 128 + ((c ^ (row & 7)) << 4), src + (size_t)ci * 16);
+    }
+    if (tile == 0 && t < 8) {                            // history: 64 samples kept as exact floats
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 a = hist_in[(size_t)s * K1_HIST + t * 8 + 2 * k];
+            const float2 b = hist_in[(size_t)s * K1_HIST + t * 8 + 2 * k + 1];
+            wv[k] = (uint32_t)(int)(a.x + 127.0f) | ((uint32_t)(int)(a.y + 127.0f) << 8)
+                  | ((uint32_t)(int)(b.x + 127.0f) << 16) | ((uint32_t)(int)(b.y + 127.0f) << 24);
+        }
+        *(uint4*)(s_tile + ((t ^ 0) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);   // row 0: swizzle key 0
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+
+    // ---- history for the next block: the last 64 IQ samples (one row) of this stream's block ----
+    if (o0 + n_valid == p.n_out && t < K1_HIST) {
+        const int row = n_valid >> 4;                    // last staged row
+        const int c = t >> 3;                            // 8 samples per chunk
+        const uint8_t* b = s_tile + row * 128 + ((c ^ (row & 7)) << 4) + (t & 7) * 2;
+        hist_out[(size_t)s * K1_HIST + t] = make_float2((float)b[0] - 127.0f, (float)b[1] - 127.0f);
+    }
+
+    const bool active = (t * K1_R) < n_valid;
+    float theta_last = 0.0f;
+    float out[K1_R];
+    float th_prev_own = 0.0f;                            // thread 0 only: angle of the output before the tile
+    if (active) {
+        float ar[K1_R], ai[K1_R];
+#pragma unroll
+        for (int r = 0; r < K1_R; r++) { ar[r] = 0.0f; ai[r] = 0.0f; }
+        const uint8_t* row0 = s_tile + t * 128;
+        const uint8_t* row1 = row0 + 128;
+        const int k0 = (t & 7) << 4, k1 = ((t + 1) & 7) << 4;
+        // window frames j = 0..15 are row t (chunk c holds frames 2c, 2c+1), j = 16..31 row t+1
+#define K1U_DO(ROWP, KEY, C, J0) k1u_chunk<J0>(*(const uint4*)((ROWP) + (((C) << 4) ^ (KEY))), ar, ai, p)
+        K1U_DO(row0, k0, 0, 0);  K1U_DO(row0, k0, 1, 2);  K1U_DO(row0, k0, 2, 4);  K1U_DO(row0, k0, 3, 6);
+        K1U_DO(row0, k0, 4, 8);  K1U_DO(row0, k0, 5, 10); K1U_DO(row0, k0, 6, 12); K1U_DO(row0, k0, 7, 14);
+        K1U_DO(row1, k1, 0, 16); K1U_DO(row1, k1, 1, 18); K1U_DO(row1, k1, 2, 20); K1U_DO(row1, k1, 3, 22);
+        K1U_DO(row1, k1, 4, 24); K1U_DO(row1, k1, 5, 26); K1U_DO(row1, k1, 6, 28); K1U_DO(row1, k1, 7, 30);
+#undef K1U_DO
+        if (t == 0) {
+            // output o0-1: frames 0..15 of row 0 with tap group = frame index; same summation order
+            // as the thread that owns this output in the previous tile (bit-identical result)
+            float er = 0.0f, ei = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint4 w = *(const uint4*)(s_tile + (c << 4));
+                const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const uint32_t v = ws[2 * h + (m >> 1)];
+                        er = fmaf(u8_to_f32_m127(v, (m & 1) * 2), p.taps[4 * (2 * c + h) + m], er);
+                        ei = fmaf(u8_to_f32_m127(v, (m & 1) * 2 + 1), p.taps[4 * (2 * c + h) + m], ei);
+                    }
+                }
+            }
+            th_prev_own = fm_atan2f(ei, er);
+        }
+        float prev = 0.0f;
+#pragma unroll
+        for (int r = 0; r < K1_R; r++) {
+            const float th = fm_atan2f(ai[r], ar[r]);
+            out[r] = th - prev;                          // r = 0 fixed up below
+            if (r == 0) out[0] = th;
+            prev = th;
+        }
+        theta_last = prev;
+    }
+    // angle of the output before this thread's first one: previous lane / previous warp / own
+    float th_before = __shfl_up_sync(0xffffffffu, theta_last, 1);
+    if (lane == 31) s_theta[warp] = theta_last;
+    __syncthreads();
+    if (lane == 0) th_before = (warp == 0) ? th_prev_own : s_theta[warp - 1];
+    if (!active) return;
+    out[0] = out[0] - th_before;
+#pragma unroll
+    for (int r = 0; r < K1_R; r++) out[r] = wrap_phase(out[r]) * p.discrim_gain;
     float4* dst = (float4*)(fm_demod + (size_t)s * p.n_out + o0 + t * K1_R);
 #pragma unroll
     for (int q = 0; q < K1_R / 4; q++) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
@@ -148,7 +325,7 @@ cudaError_t launch_k1(bool u8, const void* iq, const float2* hist_in, float2* hi
         configured = true;
     }
     const dim3 grid((p.n_out + K1_TILE - 1) / K1_TILE, p.n_streams);
-    if (u8) k1_fir4_discrim<true><<<grid, K1_THREADS, K1_SMEM_BYTES, st>>>(iq, hist_in, hist_out, fm_demod, p);
+    if (u8) k1_fir4_discrim_u8<<<grid, K1_THREADS, 0, st>>>((const uint8_t*)iq, hist_in, hist_out, fm_demod, p);
     else    k1_fir4_discrim<false><<<grid, K1_THREADS, K1_SMEM_BYTES, st>>>(iq, hist_in, hist_out, fm_demod, p);
     return cudaGetLastError();
 }

@@ -16,8 +16,8 @@
 // arg of the reference's oscillator sample is 2 pi t up to its 4e-8 polynomial error).  The AGC
 // gain is a positive scale and does not enter the angle; if it is not finite (all-zero block:
 // sqrt(1/0)) the reference's pilot becomes NaN and poisons the loop for good -- reproduced through
-// `poison`.  Per-thread I/O is 8 consecutive floats = one 32-byte sector per LDG.128/STG.128 pair,
-// loaded one group ahead, so memory latency never sits on the chain.
+// `poison`.  Per-thread I/O is whole 32-byte sectors (LDG.128 / STG.128 on the lane's own row),
+// loaded a full 32-sample group ahead, so memory latency never sits on the chain.
 #include "fm_common.cuh"
 
 namespace fm {
@@ -50,39 +50,55 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
     float4* pi4 = KEEP ? (float4*)(dbg_pi + (size_t)s * p.n) : nullptr;
 
     const float b0 = p.lpf_b[0], b1 = p.lpf_b[1], a0 = p.lpf_a[0];
-    float4 nx0 = th4[0], nx1 = th4[1];
-    for (int i = 0; i < p.n; i += 8) {
-        const float th[8] = { nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w };
-        if (i + 8 < p.n) { nx0 = th4[(i >> 2) + 2]; nx1 = th4[(i >> 2) + 3]; }
-        float dt[8], raw[8], pie[8];
+    const float int_KTs = p.int_KTs, Kp = p.Kp, f_gain = p.f_gain, f_center = p.f_center, mixer_KTs = p.mixer_KTs;
+    // Groups of 32 samples (four 32-byte sectors per lane), loaded one whole group (~2000 cycles of
+    // recurrence) ahead: the ncu source view of the 8-sample version showed 46 % of the stall samples
+    // on the first use of the prefetched registers (DRAM latency > 8 iterations).
+    constexpr int G = 32;
+    float4 nx[G / 4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            // IIR1: y = xn[0]*b[0] + yn[0]*a[0] + xn[1]*b[1]; the part that does not depend on the
-            // newest error is formed first so only one FFMA sits on the e -> lpf path.
-            const float m = fmaf(x1, b0, y1 * a0);
-            const float lpf = fmaf(e, b1, m);
-            x1 = e; y1 = lpf;
-            integ = clampf(fmaf(p.int_KTs, e, integ), -1.0f, 1.0f);
-            const float PI_error = fmaf(lpf, p.Kp, integ);
-            // PLL_Mixer::Update
-            const float control = clampf(PI_error, -1.0f, 1.0f);
-            const float freq = fmaf(control, p.f_gain, p.f_center);
-            const float tu = fmaf(p.mixer_KTs, freq, t);                 // |tu| < 0.66
-            t = tu - ((tu >= 0.5f) ? 1.0f : ((tu <= -0.5f) ? -1.0f : 0.0f));   // t - round(t), half away
-            // phase detector: arg(pilot * pll) = 2 pi * wrap(theta + t), result in (-pi, pi]
-            const float u = th[j] + tu;                                   // |u| < 1.16
-            const float uw = u - ((u > 0.5f) ? 1.0f : ((u <= -0.5f) ? -1.0f : 0.0f));
-            e = fmaf(uw, TWO_PI_F, poison);
-            dt[j] = t;
-            if (KEEP) { raw[j] = e; pie[j] = PI_error; }
+    for (int q = 0; q < G / 4; q++) nx[q] = th4[q];
+    for (int i = 0; i < p.n; i += G) {
+        float4 cur[G / 4];
+#pragma unroll
+        for (int q = 0; q < G / 4; q++) cur[q] = nx[q];
+        if (i + G < p.n) {
+#pragma unroll
+            for (int q = 0; q < G / 4; q++) nx[q] = th4[((i + G) >> 2) + q];
         }
-        dt4[(i >> 2)] = make_float4(dt[0], dt[1], dt[2], dt[3]);
-        dt4[(i >> 2) + 1] = make_float4(dt[4], dt[5], dt[6], dt[7]);
-        if (KEEP) {
-            raw4[(i >> 2)] = make_float4(raw[0], raw[1], raw[2], raw[3]);
-            raw4[(i >> 2) + 1] = make_float4(raw[4], raw[5], raw[6], raw[7]);
-            pi4[(i >> 2)] = make_float4(pie[0], pie[1], pie[2], pie[3]);
-            pi4[(i >> 2) + 1] = make_float4(pie[4], pie[5], pie[6], pie[7]);
+#pragma unroll
+        for (int q = 0; q < G / 4; q++) {
+            const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
+            float dt[4], raw[4], pie[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // IIR1: y = xn[0]*b[0] + yn[0]*a[0] + xn[1]*b[1]; the part that does not depend on the
+                // newest error is formed first so only one FFMA sits on the e -> lpf path.
+                const float m = fmaf(x1, b0, y1 * a0);
+                const float lpf = fmaf(e, b1, m);
+                x1 = e; y1 = lpf;
+                integ = clampf(fmaf(int_KTs, e, integ), -1.0f, 1.0f);
+                const float PI_error = fmaf(lpf, Kp, integ);
+                // PLL_Mixer::Update
+                const float control = clampf(PI_error, -1.0f, 1.0f);
+                const float freq = fmaf(control, f_gain, f_center);
+                const float tu = fmaf(mixer_KTs, freq, t);                 // |tu| < 0.66
+                // t - round(t): the nearest integer comes from two FADDs with 1.5 * 2^23 (all on the
+                // FMA pipe, 4-cycle latency each, no FRND / compare-select chain).  Ties (|tu| == 0.5
+                // exactly) round to even instead of away from zero; both results are the same phase.
+                t = tu - ((tu + 12582912.0f) - 12582912.0f);
+                // phase detector: arg(pilot * pll) = 2 pi * wrap(theta + t)
+                const float u = th[j] + tu;                                 // |u| < 1.16
+                const float uw = u - ((u + 12582912.0f) - 12582912.0f);
+                e = fmaf(uw, TWO_PI_F, poison);
+                dt[j] = t;
+                if (KEEP) { raw[j] = e; pie[j] = PI_error; }
+            }
+            dt4[(i >> 2) + q] = make_float4(dt[0], dt[1], dt[2], dt[3]);
+            if (KEEP) {
+                raw4[(i >> 2) + q] = make_float4(raw[0], raw[1], raw[2], raw[3]);
+                pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
+            }
         }
     }
     state[PLL_LPF_X1 * S + s] = x1;

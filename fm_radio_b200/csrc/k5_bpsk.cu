@@ -45,11 +45,22 @@ k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_p
     const float target_gain = sqrtf(p.agc_target / avg_power);
     gain = gain + p.agc_beta * (target_gain - gain);
 
-    const float2* x = rds_in + (size_t)s * p.n;
+    const float4* x4 = (const float4*)(rds_in + (size_t)s * p.n);
     const size_t o = (size_t)s * p.n;
     int total = 0;
-    for (int i = 0; i < p.n; i++) {
-        float2 xi = x[i];
+    // 8 samples (two 32-byte sectors) per lane are loaded one group ahead of their use, so the
+    // global-load latency never sits on the recurrence
+    float4 nx[4] = { x4[0], x4[1], x4[2], x4[3] };
+    for (int i0 = 0; i0 < p.n; i0 += 8) {
+    const float4 cur[4] = { nx[0], nx[1], nx[2], nx[3] };
+    if (i0 + 8 < p.n) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) nx[q] = x4[(i0 >> 1) + 4 + q];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = i0 + j;
+        float2 xi = (j & 1) ? make_float2(cur[j >> 1].z, cur[j >> 1].w) : make_float2(cur[j >> 1].x, cur[j >> 1].y);
         xi.x *= gain; xi.y *= gain;
         // PI controller of the carrier PLL (:106-113)
         const float pll_lpf = fmaf(pll_prev, p.pll_b[1], fmaf(lp_x1, p.pll_b[0], lp_y1 * p.pll_a[0]));
@@ -118,6 +129,7 @@ k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_p
             dbg_pll_pi[o + i] = PI_pll_error;
             dbg_dump_filter[o + i] = make_float2(dump_re, dump_im);
         }
+    }
     }
     sym_count[s] = total;
     ST(BP_LPF_PLL_X1) = lp_x1; ST(BP_LPF_PLL_Y1) = lp_y1; ST(BP_INT_PLL) = int_pll;

@@ -120,6 +120,7 @@ def test_small_blocks_match_golden_and_checker():
     # minimum block size 1024: every FIR history spans exactly one previous block
     bs = 1024
     nb = 3 * 1024
+    iq = H.capture("seed0")
     chk = bind.CpuDemod(bs, "port")
     g = fm.FMDemod(bs, 1, keep_intermediates=True)
     dec = fm.RDSDecoder()
