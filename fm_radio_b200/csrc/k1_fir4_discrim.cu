@@ -24,10 +24,9 @@ __device__ __forceinline__ float u8_to_f32_m127(uint32_t w, int byte) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388735.0f;
 }
 
-__device__ __forceinline__ float wrap_phase(float x) {          // fm_demod.cpp:6-10
-    if (x >= PI_F) return x - 2.0f * PI_F;
-    else if (x <= -PI_F) return x + 2.0f * PI_F;
-    return x;
+__device__ __forceinline__ float wrap_phase(float x) {          // fm_demod.cpp:6-10, as two selects
+    const float lo = x - 2.0f * PI_F, hi = x + 2.0f * PI_F;
+    return (x >= PI_F) ? lo : ((x <= -PI_F) ? hi : x);
 }
 
 // atan2 of the discriminator, shared by both kernels (so the cf32 and u8 entry points give identical
@@ -50,6 +49,31 @@ __device__ __forceinline__ float fm_atan2f(float y, float x) {
     r = (ay > ax) ? (0.5f * PI_F - r) : r;
     r = (x < 0.0f) ? (PI_F - r) : r;
     return copysignf(r, y);
+}
+
+// Two atan2 at once for the packed FP32 pipe (FFMA2 / FMUL2, sm_100): operation for operation the
+// same IEEE sequence as fm_atan2f, so both give identical bits for identical inputs.
+__device__ __forceinline__ float2 fm_atan2f_x2(float y0, float x0, float y1, float x1) {
+    const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    float2 q = make_float2(__fdividef(mn0, mx0), __fdividef(mn1, mx1));
+    q.x = (mx0 == 0.0f) ? 0.0f : q.x;
+    q.y = (mx1 == 0.0f) ? 0.0f : q.y;
+    const float2 s = __fmul2_rn(q, q);
+    float2 p = make_float2(-0.004054562299f, -0.004054562299f);
+    p = __ffma2_rn(p, s, make_float2(0.021862939178f, 0.021862939178f));
+    p = __ffma2_rn(p, s, make_float2(-0.05591229796f, -0.05591229796f));
+    p = __ffma2_rn(p, s, make_float2(0.096421950378f, 0.096421950378f));
+    p = __ffma2_rn(p, s, make_float2(-0.139086285623f, -0.139086285623f));
+    p = __ffma2_rn(p, s, make_float2(0.1994656543f, 0.1994656543f));
+    p = __ffma2_rn(p, s, make_float2(-0.333298607622f, -0.333298607622f));
+    p = __ffma2_rn(p, s, make_float2(0.999999335572f, 0.999999335572f));
+    float2 r = __fmul2_rn(p, q);
+    r.x = (ay0 > ax0) ? (0.5f * PI_F - r.x) : r.x;
+    r.y = (ay1 > ax1) ? (0.5f * PI_F - r.y) : r.y;
+    r.x = (x0 < 0.0f) ? (PI_F - r.x) : r.x;
+    r.y = (x1 < 0.0f) ? (PI_F - r.y) : r.y;
+    return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
 }
 
 template <bool U8>
@@ -177,19 +201,24 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gmem_src));
 }
 
-// two frames (8 IQ samples) from one 16-byte chunk, applied to every output they feed
-template <int J0>   // J0 = index of the chunk's first frame relative to the thread's window (even, -0 .. 30)
-__device__ __forceinline__ void k1u_chunk(const uint4 w, float (&ar)[K1_R], float (&ai)[K1_R], const K1Params& p) {
+// two frames (8 IQ samples) from one 16-byte chunk, applied to every output they feed.
+// One (re, im) pair per 64-bit register pair: the unpack is 2 PRMT + 1 FADD2 per IQ sample and every
+// tap costs ONE FFMA2 (re and im together) whose tap operand is a uniform-register scalar broadcast
+// to both halves (SASS: FFMA2 R, R.F32x2.HI_LO, UR.F32, R.F32x2.HI_LO).
+template <int J0>   // J0 = index of the chunk's first frame relative to the thread's window (even, 0 .. 30)
+__device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], const K1Params& p) {
     const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+    const float2 bias = make_float2(-8388735.0f, -8388735.0f);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int j = J0 + h;                           // frame index: output r uses frames r+1 .. r+16
-        float xr[4], xi[4];
+        float2 x[4];
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             const uint32_t v = ws[2 * h + (m >> 1)];
-            xr[m] = u8_to_f32_m127(v, (m & 1) * 2);
-            xi[m] = u8_to_f32_m127(v, (m & 1) * 2 + 1);
+            const uint32_t sel = 0x7440u | (uint32_t)((m & 1) * 2);
+            x[m] = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, sel)),
+                                          __uint_as_float(__byte_perm(v, 0x4B000000u, sel + 1u))), bias);
         }
 #pragma unroll
         for (int r = 0; r < K1_R; r++) {
@@ -197,8 +226,8 @@ __device__ __forceinline__ void k1u_chunk(const uint4 w, float (&ar)[K1_R], floa
             if (g >= 0 && g < 16) {
 #pragma unroll
                 for (int m = 0; m < 4; m++) {
-                    ar[r] = fmaf(xr[m], p.taps[4 * g + m], ar[r]);
-                    ai[r] = fmaf(xi[m], p.taps[4 * g + m], ai[r]);
+                    const float tap = p.taps[4 * g + m];
+                    acc[r] = __ffma2_rn(x[m], make_float2(tap, tap), acc[r]);
                 }
             }
         }
@@ -254,14 +283,14 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
     float out[K1_R];
     float th_prev_own = 0.0f;                            // thread 0 only: angle of the output before the tile
     if (active) {
-        float ar[K1_R], ai[K1_R];
+        float2 acc[K1_R];
 #pragma unroll
-        for (int r = 0; r < K1_R; r++) { ar[r] = 0.0f; ai[r] = 0.0f; }
+        for (int r = 0; r < K1_R; r++) acc[r] = make_float2(0.0f, 0.0f);
         const uint8_t* row0 = s_tile + t * 128;
         const uint8_t* row1 = row0 + 128;
         const int k0 = (t & 7) << 4, k1 = ((t + 1) & 7) << 4;
         // window frames j = 0..15 are row t (chunk c holds frames 2c, 2c+1), j = 16..31 row t+1
-#define K1U_DO(ROWP, KEY, C, J0) k1u_chunk<J0>(*(const uint4*)((ROWP) + (((C) << 4) ^ (KEY))), ar, ai, p)
+#define K1U_DO(ROWP, KEY, C, J0) k1u_chunk<J0>(*(const uint4*)((ROWP) + (((C) << 4) ^ (KEY))), acc, p)
         K1U_DO(row0, k0, 0, 0);  K1U_DO(row0, k0, 1, 2);  K1U_DO(row0, k0, 2, 4);  K1U_DO(row0, k0, 3, 6);
         K1U_DO(row0, k0, 4, 8);  K1U_DO(row0, k0, 5, 10); K1U_DO(row0, k0, 6, 12); K1U_DO(row0, k0, 7, 14);
         K1U_DO(row1, k1, 0, 16); K1U_DO(row1, k1, 1, 18); K1U_DO(row1, k1, 2, 20); K1U_DO(row1, k1, 3, 22);
@@ -289,11 +318,11 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
         }
         float prev = 0.0f;
 #pragma unroll
-        for (int r = 0; r < K1_R; r++) {
-            const float th = fm_atan2f(ai[r], ar[r]);
-            out[r] = th - prev;                          // r = 0 fixed up below
-            if (r == 0) out[0] = th;
-            prev = th;
+        for (int r = 0; r < K1_R; r += 2) {
+            const float2 th = fm_atan2f_x2(acc[r].y, acc[r].x, acc[r + 1].y, acc[r + 1].x);
+            out[r] = (r == 0) ? th.x : th.x - prev;      // r = 0 fixed up below
+            out[r + 1] = th.y - th.x;
+            prev = th.y;
         }
         theta_last = prev;
     }

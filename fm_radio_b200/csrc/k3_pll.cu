@@ -8,21 +8,51 @@
 // Parallelisation: the loop cannot be scanned (clamps, phase wrap), so parallelism is across
 // streams only: ONE THREAD PER STREAM, one warp (32 streams) per CTA so that the warps spread over
 // the SMs; every other stage of the chain overlaps with it on other CUDA streams.  What is
-// optimised here is the LENGTH OF THE DEPENDENT CHAIN per sample, because aggregate throughput
-// of a 1024-stream batch is bounded by n_samples * chain latency:
-//   reference chain  e -> PI -> NCO -> 2 x polynomial sine -> complex multiply -> atan2f -> e
-//   this kernel      e -> PI -> NCO -> (theta[n] + t) wrapped to one turn        -> e
-// using theta[n] = arg(pilot[n])/2pi precomputed in parallel by K2 (arg(a*b) = arg(a)+arg(b);
-// arg of the reference's oscillator sample is 2 pi t up to its 4e-8 polynomial error).  The AGC
-// gain is a positive scale and does not enter the angle; if it is not finite (all-zero block:
-// sqrt(1/0)) the reference's pilot becomes NaN and poisons the loop for good -- reproduced through
-// `poison`.  Per-thread I/O is whole 32-byte sectors (LDG.128 / STG.128 on the lane's own row),
-// loaded a full 32-sample group ahead, so memory latency never sits on the chain.
+// optimised here is the LENGTH OF THE DEPENDENT CHAIN per sample, because the time of a
+// 1024-stream batch is n_samples x chain latency (one warp per SM sub-partition, nothing to hide
+// latency behind):
+//   reference   e -> IIR, integrator+clamp -> PI -> clamp -> freq -> t+=, wrap -> 2 x polynomial sine
+//                 -> complex multiply -> atan2f -> e                         (~50 dependent ops)
+//   first cut   e -> fma, min, max -> fma, min, max -> fma -> fma -> add -> 3-op wrap -> fma -> e
+//               13 dependent ops of 4-5 cycles; measured 101 cycles per sample on B200
+//   this kernel w -> {fma.sat, fma.sat} -> sub -> {fma.sat, fma.sat} -> sub -> fma -> fma -> 3-op wrap -> w
+//               9 dependent ops, all on the FMA pipe (no FMA<->ALU pipe crossings)
+// using
+//   * theta[n] = arg(pilot[n])/2pi precomputed in parallel by K2 (arg(a*b) = arg(a)+arg(b); arg of
+//     the reference's oscillator sample is 2 pi t up to its 4e-8 polynomial error), so the phase
+//     detector is wrap(theta + t);
+//   * the error kept in TURNS (w = e / 2pi) with 2pi folded into the coefficients that consume it;
+//   * clamp(x, -1, 1) == sat(x) - sat(-x) exactly (one of the two terms is zero), and sat() is a free
+//     modifier of the FFMA that produces x, so a clamp costs one dependent FADD instead of two
+//     ALU-pipe FMNMX;
+//   * the phase detector input formed straight from freq, fma(KTs, freq, theta + t), next to the
+//     NCO update fma(KTs, freq, t) instead of after it.  (Merging freq into the increment,
+//     (t + KTs*fc) + (KTs*fg)*c, saves one more op but was rejected: it moves the NCO's rounding
+//     points and the loop's static phase error with them -- 3.7e-5 turns away from the reference
+//     instead of 9e-7, measured.)
+// The AGC gain is a positive scale and does not enter the angle; if it is not finite (all-zero
+// block: sqrt(1/0)) the reference's pilot becomes NaN and poisons the loop for good -- such a lane
+// takes the slow loop below, which keeps the reference's clamp-of-NaN behaviour.  Per-thread I/O is
+// whole 32-byte sectors (LDG.128 / STG.128 on the lane's own row), loaded a full 32-sample group
+// ahead, so memory latency never sits on the chain.
 #include "fm_common.cuh"
 
 namespace fm {
 
-template <bool KEEP>
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// x - nearest integer.  WRAP 0: two FADDs with 1.5 * 2^23 (FMA pipe, ties to even); WRAP 1: FRND.
+template <int WRAP>
+__device__ __forceinline__ float wrap_turn(float x) {
+    if (WRAP == 0) return x - ((x + 12582912.0f) - 12582912.0f);
+    return x - rintf(x);
+}
+
+template <bool KEEP, int WRAP>
 __global__ void __launch_bounds__(32)
 k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* __restrict__ state,
        float* __restrict__ pll_dt, float* __restrict__ dbg_raw, float* __restrict__ dbg_pi,
@@ -31,81 +61,99 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n_streams) return;
     const int S = p.n_streams;
-    float x1 = state[PLL_LPF_X1 * S + s];
+    float x1 = state[PLL_LPF_X1 * S + s];       // previous phase error, in turns
     float y1 = state[PLL_LPF_Y1 * S + s];
     float integ = state[PLL_INT * S + s];
     float t = state[PLL_T * S + s];
-    float e = state[PLL_E_PREV * S + s];
+    float w = state[PLL_E_PREV * S + s];        // phase error in turns
     float gain = state[PLL_AGC_GAIN * S + s];
 
     // dsp/agc.h:12-19 (block-wise): P = mean |x|^2, g += beta*(sqrt(target/P) - g)
     const float avg_power = power[s] / (float)p.n;
     const float target_gain = sqrtf(p.agc_target / avg_power);
     gain = gain + p.agc_beta * (target_gain - gain);
-    const float poison = 0.0f * gain;          // 0 for a finite gain, NaN for inf/NaN
+    const bool poisoned = !(fabsf(gain) <= 3.0e38f);            // inf or NaN
 
     const float4* th4 = (const float4*)(theta + (size_t)s * p.n);
     float4* dt4 = (float4*)(pll_dt + (size_t)s * p.n);
     float4* raw4 = KEEP ? (float4*)(dbg_raw + (size_t)s * p.n) : nullptr;
     float4* pi4 = KEEP ? (float4*)(dbg_pi + (size_t)s * p.n) : nullptr;
 
-    const float b0 = p.lpf_b[0], b1 = p.lpf_b[1], a0 = p.lpf_a[0];
-    const float int_KTs = p.int_KTs, Kp = p.Kp, f_gain = p.f_gain, f_center = p.f_center, mixer_KTs = p.mixer_KTs;
-    // Groups of 32 samples (four 32-byte sectors per lane), loaded one whole group (~2000 cycles of
-    // recurrence) ahead: the ncu source view of the 8-sample version showed 46 % of the stall samples
-    // on the first use of the prefetched registers (DRAM latency > 8 iterations).
-    constexpr int G = 32;
-    float4 nx[G / 4];
+    const float a0 = p.lpf_a[0], Kp = p.Kp;
+    const float b0t = p.lpf_b[0] * TWO_PI_F, b1t = p.lpf_b[1] * TWO_PI_F, ci = p.int_KTs * TWO_PI_F;
+    const float f_gain = p.f_gain, f_center = p.f_center, mixer_KTs = p.mixer_KTs;
+
+    if (!poisoned) {
+        // Groups of 32 samples (four 32-byte sectors per lane), loaded one whole group ahead.
+        constexpr int G = 32;
+        float4 nx[G / 4];
 #pragma unroll
-    for (int q = 0; q < G / 4; q++) nx[q] = th4[q];
-    for (int i = 0; i < p.n; i += G) {
-        float4 cur[G / 4];
+        for (int q = 0; q < G / 4; q++) nx[q] = th4[q];
+        for (int i = 0; i < p.n; i += G) {
+            float4 cur[G / 4];
 #pragma unroll
-        for (int q = 0; q < G / 4; q++) cur[q] = nx[q];
-        if (i + G < p.n) {
+            for (int q = 0; q < G / 4; q++) cur[q] = nx[q];
+            if (i + G < p.n) {
 #pragma unroll
-            for (int q = 0; q < G / 4; q++) nx[q] = th4[((i + G) >> 2) + q];
-        }
-#pragma unroll
-        for (int q = 0; q < G / 4; q++) {
-            const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
-            float dt[4], raw[4], pie[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // IIR1: y = xn[0]*b[0] + yn[0]*a[0] + xn[1]*b[1]; the part that does not depend on the
-                // newest error is formed first so only one FFMA sits on the e -> lpf path.
-                const float m = fmaf(x1, b0, y1 * a0);
-                const float lpf = fmaf(e, b1, m);
-                x1 = e; y1 = lpf;
-                integ = clampf(fmaf(int_KTs, e, integ), -1.0f, 1.0f);
-                const float PI_error = fmaf(lpf, Kp, integ);
-                // PLL_Mixer::Update
-                const float control = clampf(PI_error, -1.0f, 1.0f);
-                const float freq = fmaf(control, f_gain, f_center);
-                const float tu = fmaf(mixer_KTs, freq, t);                 // |tu| < 0.66
-                // t - round(t): the nearest integer comes from two FADDs with 1.5 * 2^23 (all on the
-                // FMA pipe, 4-cycle latency each, no FRND / compare-select chain).  Ties (|tu| == 0.5
-                // exactly) round to even instead of away from zero; both results are the same phase.
-                t = tu - ((tu + 12582912.0f) - 12582912.0f);
-                // phase detector: arg(pilot * pll) = 2 pi * wrap(theta + t)
-                const float u = th[j] + tu;                                 // |u| < 1.16
-                const float uw = u - ((u + 12582912.0f) - 12582912.0f);
-                e = fmaf(uw, TWO_PI_F, poison);
-                dt[j] = t;
-                if (KEEP) { raw[j] = e; pie[j] = PI_error; }
+                for (int q = 0; q < G / 4; q++) nx[q] = th4[((i + G) >> 2) + q];
             }
-            dt4[(i >> 2) + q] = make_float4(dt[0], dt[1], dt[2], dt[3]);
-            if (KEEP) {
-                raw4[(i >> 2) + q] = make_float4(raw[0], raw[1], raw[2], raw[3]);
-                pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
+#pragma unroll
+            for (int q = 0; q < G / 4; q++) {
+                const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
+                float dt[4], raw[4], pie[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // off the chain: everything that depends only on the previous iteration's t, x1, y1
+                    const float m = fmaf(x1, b0t, y1 * a0);
+                    const float a = th[j] + t;                              // |a| <= 1
+                    // IIR1 y = xn[0]*b[0] + yn[0]*a[0] + xn[1]*b[1] on the newest error
+                    const float lpf = fmaf(w, b1t, m);
+                    // integrator with clamp(-1, 1) = sat(x) - sat(-x)
+                    integ = fma_sat(ci, w, integ) - fma_sat(-ci, w, -integ);
+                    x1 = w; y1 = lpf;
+                    // PI error and PLL_Mixer::Update's clamp, the same way
+                    const float control = fma_sat(lpf, Kp, integ) - fma_sat(-lpf, Kp, -integ);
+                    // NCO (pll_mixer.cpp:12-21), in the reference's rounding structure -- freq is
+                    // quantised to ulp(19000) = 2^-9 Hz and the loop's static phase error (1 rad per
+                    // Hz of NCO bias) follows that quantisation: t += KTs*freq; t -= round(t)
+                    const float freq = fmaf(control, f_gain, f_center);
+                    t = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, t));
+                    // phase detector: arg(pilot * pll) / 2pi = wrap(theta + t), straight from freq
+                    w = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, a));
+                    dt[j] = t;
+                    if (KEEP) { raw[j] = w * TWO_PI_F; pie[j] = fmaf(lpf, Kp, integ); }
+                }
+                dt4[(i >> 2) + q] = make_float4(dt[0], dt[1], dt[2], dt[3]);
+                if (KEEP) {
+                    raw4[(i >> 2) + q] = make_float4(raw[0], raw[1], raw[2], raw[3]);
+                    pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
+                }
             }
         }
+    } else {
+        // Poisoned lane: e is NaN from here on; clamp(NaN) = -1 as dsp/clamp.h:4-8 evaluates it, so
+        // the NCO runs at f_center - f_gain.  Reference operation order, no latency tricks.
+        const float nan = 0.0f * gain;
+        float x1r = x1 * TWO_PI_F;
+        for (int i = 0; i < p.n; i++) {
+            const float e = fmaf(w, TWO_PI_F, nan);
+            const float lpf = fmaf(e, p.lpf_b[1], fmaf(x1r, p.lpf_b[0], y1 * a0));
+            x1r = e; y1 = lpf;
+            integ = clampf(fmaf(p.int_KTs, e, integ), -1.0f, 1.0f);
+            const float PI_error = fmaf(lpf, Kp, integ);
+            const float control = clampf(PI_error, -1.0f, 1.0f);
+            const float tu = fmaf(p.mixer_KTs, fmaf(control, p.f_gain, p.f_center), t);
+            t = tu - roundf(tu);
+            pll_dt[(size_t)s * p.n + i] = t;
+            if (KEEP) { dbg_raw[(size_t)s * p.n + i] = e; dbg_pi[(size_t)s * p.n + i] = PI_error; }
+        }
+        x1 = nan; w = nan;
     }
     state[PLL_LPF_X1 * S + s] = x1;
     state[PLL_LPF_Y1 * S + s] = y1;
     state[PLL_INT * S + s] = integ;
     state[PLL_T * S + s] = t;
-    state[PLL_E_PREV * S + s] = e;
+    state[PLL_E_PREV * S + s] = w;
     state[PLL_AGC_GAIN * S + s] = gain;
 }
 
@@ -113,8 +161,8 @@ cudaError_t launch_k3(const float* theta, const float* power, float* state, floa
                       float* dbg_raw, float* dbg_pi, const K3Params& p, cudaStream_t st)
 {
     const int grid = (p.n_streams + 31) / 32;
-    if (p.keep) k3_pll<true><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
-    else        k3_pll<false><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+    if (p.keep) k3_pll<true, 0><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+    else        k3_pll<false, 0><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
     return cudaGetLastError();
 }
 
