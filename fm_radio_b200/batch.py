@@ -24,10 +24,14 @@ class StreamBatch:
     """One rank's share of a batch of streams: FMDemod + one host RDS decoder per stream."""
 
     def __init__(self, stream_ids, block_size: int = 65536, device: int = -1, pipeline_depth: int = 0,
-                 keep_intermediates: bool = False):
+                 keep_intermediates: bool = False, demod=None):
         self.stream_ids = list(stream_ids)
-        self.demod = FMDemod(block_size, len(self.stream_ids), device=device,
-                             keep_intermediates=keep_intermediates, pipeline_depth=pipeline_depth)
+        # `demod` is injectable so the rank/shard/gather logic can be exercised without a GPU (the CPU
+        # test-suite passes a stand-in with the same process_u8/get interface); the product always
+        # builds the CUDA demodulator.
+        self.demod = demod if demod is not None else FMDemod(
+            block_size, len(self.stream_ids), device=device,
+            keep_intermediates=keep_intermediates, pipeline_depth=pipeline_depth)
         self.rds = [RDSDecoder() for _ in self.stream_ids]
         self.audio = None
 

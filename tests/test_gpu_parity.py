@@ -331,3 +331,28 @@ def test_full_batch_1024_streams_properties_and_sampled_checker():
             lpr = 0.25 * (g.get(Buf.AUDIO_OUT, s + 16 * 40)[0::2] + g.get(Buf.AUDIO_OUT, s + 16 * 40)[1::2])
             _assert_ff(lpr, c.get("audio_lpr"), (k, s))       # (L+R)/2 of the stereo mix is the feed-forward L+R path
     g.close(); g1.close()
+
+
+def test_reference_driver_runs_unchanged_on_the_shim(tmp_path):
+    """The reference's own fm_demod_benchmark.cpp + app.cpp + rds_decoder, compiled UNMODIFIED against the
+    Broadcast_FM_Demod shim (fm_radio_b200/csrc/shim), must log the same RDS groups as the
+    reference's CPU build of the same driver on the same capture (stderr, rds_decoder.cpp:123-124)."""
+    import os
+    import subprocess
+    gpu_drv = os.path.join(H.ROOT, "fm_radio_b200", "build", "fm_demod_benchmark_gpu")
+    cpu_drv = bind.REF_BENCH
+    if not (os.path.exists(gpu_drv) and os.path.exists(cpu_drv)):
+        pytest.skip("drivers are built where /root/reference exists and travel with the snapshot")
+    cap = tmp_path / "seed0.u8"
+    H.capture("seed0").tofile(cap)
+
+    def log_of(exe, env=None):
+        r = subprocess.run([exe, "-b", str(H.B), "-i", str(cap)], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, **(env or {})))
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [ln for ln in r.stderr.splitlines() if ln.startswith(("[rds_decoder]", "[rds_sync]"))]
+
+    want = log_of(cpu_drv)
+    assert sum("[group]" in ln for ln in want) >= 40
+    assert log_of(gpu_drv) == want
+    assert log_of(gpu_drv, {"FMGPU_LEAN": "1"}) == want
