@@ -169,9 +169,14 @@ int alloc_all(fmgpu_demod* h) {
     const size_t S = h->S;
     CU(cudaStreamCreateWithFlags(&h->stH, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->stA, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->stB, cudaStreamNonBlocking));
+    // The two latency-bound recurrences get the highest CTA-scheduling priority: their 32 + 32
+    // one-warp CTAs must never queue behind the thousands of CTAs of the FMA-bound kernels.
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (std::getenv("FMGPU_NO_PRIORITY")) prio_hi = prio_lo;
+    CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_hi));
     CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->stD, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
     CU(cudaStreamCreateWithFlags(&h->stO, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         CU(dalloc(&h->k1_hist[i], S * fm::K1_HIST));

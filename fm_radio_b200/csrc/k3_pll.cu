@@ -89,6 +89,9 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
         float4 nx[G / 4];
 #pragma unroll
         for (int q = 0; q < G / 4; q++) nx[q] = th4[q];
+#pragma unroll
+        for (int g = 1; g < 4; g++)
+            if (g * G < p.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(th4 + ((g * G) >> 2)));
         for (int i = 0; i < p.n; i += G) {
             float4 cur[G / 4];
 #pragma unroll
@@ -97,6 +100,10 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
 #pragma unroll
                 for (int q = 0; q < G / 4; q++) nx[q] = th4[((i + G) >> 2) + q];
             }
+            // theta was written by K2 together with 2x as much fm_out_iq, so part of it has left the
+            // L2 by now: pull the lane's 128-byte line of group i + 4G into L2 (DRAM latency under
+            // load exceeds the ~1500 cycles one group of look-ahead buys; measured, see profiles/)
+            if (i + 4 * G < p.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(th4 + ((i + 4 * G) >> 2)));
 #pragma unroll
             for (int q = 0; q < G / 4; q++) {
                 const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
