@@ -115,6 +115,8 @@ EXPORTED_SYMBOLS = [
     "fmgpu_polyphase_get_b", "fmgpu_polyphase_ds_process", "fmgpu_rds_create", "fmgpu_rds_destroy",
     "fmgpu_rds_push_symbols", "fmgpu_rds_n_groups", "fmgpu_rds_get_groups", "fmgpu_rds_n_bytes",
     "fmgpu_rds_get_bytes", "fmgpu_rds_get_db", "fmgpu_last_error", "fmgpu_version",
+    "fmgpu_rds_device_fetch", "fmgpu_rds_device_counts", "fmgpu_rds_device_get_groups",
+    "fmgpu_rds_device_get_bytes", "fmgpu_rds_device_get_db", "fmgpu_get_partition",
 ]
 
 _lib = None
@@ -150,7 +152,7 @@ def lib():
     L.fmgpu_get_rates.argtypes = [vp, C.POINTER(ci * 5)]
     L.fmgpu_get_config.argtypes = [vp, C.POINTER(_Config)]
     L.fmgpu_launch_count.argtypes = [vp]
-    L.fmgpu_profile_stages.argtypes = [vp, vp, ci, C.POINTER(C.c_float * 5)]
+    L.fmgpu_profile_stages.argtypes = [vp, vp, ci, C.POINTER(C.c_float * 6)]
     L.fmgpu_launch_count.restype = C.c_longlong
     for name in ("lpf", "hpf"):
         getattr(L, f"fmgpu_create_fir_{name}").argtypes = [vp, ci, C.c_float]
@@ -182,6 +184,12 @@ def lib():
     L.fmgpu_rds_get_bytes.argtypes = [vp, vp, ci]
     L.fmgpu_rds_get_db.argtypes = [vp, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
     L.fmgpu_rds_get_db.restype = None
+    L.fmgpu_get_partition.argtypes = [vp, C.POINTER(ci * 2)]
+    L.fmgpu_rds_device_fetch.argtypes = [vp]
+    L.fmgpu_rds_device_counts.argtypes = [vp, ci, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(ci * 2)]
+    L.fmgpu_rds_device_get_groups.argtypes = [vp, ci, C.c_ulonglong, C.POINTER(RDSGroup), ci]
+    L.fmgpu_rds_device_get_bytes.argtypes = [vp, ci, C.c_ulonglong, vp, ci]
+    L.fmgpu_rds_device_get_db.argtypes = [vp, ci, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
     L.fmgpu_last_error.restype = C.c_char_p
     L.fmgpu_version.restype = C.c_char_p
     _lib = L
@@ -327,14 +335,63 @@ class FMDemod:
 
     def profile_stages(self, iq_dev, n_blocks: int = 4) -> dict:
         """Average device ms per kernel with blocks run one at a time (CUDA events inside the library)."""
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 6)()
         _check(self.L.fmgpu_profile_stages(self.h, _ptr(iq_dev), n_blocks, C.byref(ms)), "fmgpu_profile_stages")
-        self.blocks_enqueued += n_blocks
-        return dict(zip(("k1_fir4_discrim", "k2_mpx", "k3_pll", "k4_mix_fir", "k5_bpsk"), [float(x) for x in ms]))
+        self.blocks_enqueued += abs(n_blocks)
+        return dict(zip(("k1_fir4_discrim", "k2_mpx", "k3_pll", "k4_mix_fir", "k5_bpsk", "k6_rds"), [float(x) for x in ms]))
+
+    def partition(self):
+        """(SMs reserved for the recurrence stages, SMs of the FIR stages); (0, 0) = not partitioned."""
+        sms = (C.c_int * 2)()
+        _check(self.L.fmgpu_get_partition(self.h, C.byref(sms)), "fmgpu_get_partition")
+        return int(sms[0]), int(sms[1])
 
     @property
     def launch_count(self) -> int:
         return int(self.L.fmgpu_launch_count(self.h))
+
+    # ---- RDS decoded on the device (kernel K6) ----
+    def rds_fetch(self) -> None:
+        """Synchronises and copies every stream's decoder state + result rings to the host."""
+        _check(self.L.fmgpu_rds_device_fetch(self.h), "fmgpu_rds_device_fetch")
+
+    def rds_counts(self, stream: int = 0):
+        """(groups, packet bytes) decoded since creation, as of the last rds_fetch()."""
+        g, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        _check(self.L.fmgpu_rds_device_counts(self.h, stream, C.byref(g), C.byref(b), None), "fmgpu_rds_device_counts")
+        return int(g.value), int(b.value)
+
+    def rds_ring_caps(self):
+        caps = (C.c_int * 2)()
+        _check(self.L.fmgpu_rds_device_counts(self.h, 0, None, None, C.byref(caps)), "fmgpu_rds_device_counts")
+        return int(caps[0]), int(caps[1])
+
+    def rds_groups(self, stream: int = 0, first: int = 0):
+        """Groups [first, total) of `stream` as (data[n,4] u16, valid[n,4] u8, type[n,4] u8)."""
+        total, _ = self.rds_counts(stream)
+        n = max(total - first, 0)
+        arr = (RDSGroup * max(n, 1))()
+        got = self.L.fmgpu_rds_device_get_groups(self.h, stream, first, arr, n)
+        if got < 0:
+            _check(got, "fmgpu_rds_device_get_groups")
+        raw = np.frombuffer(arr, dtype=np.uint8, count=16 * got).reshape(got, 16) if got else np.zeros((0, 16), np.uint8)
+        data = raw[:, :8].copy().view(np.uint16).reshape(got, 4)
+        return data, raw[:, 8:12].copy(), raw[:, 12:16].copy()
+
+    def rds_bytes(self, stream: int = 0, first: int = 0) -> bytes:
+        _, total = self.rds_counts(stream)
+        n = max(total - first, 0)
+        out = np.zeros(max(n, 1), np.uint8)
+        got = self.L.fmgpu_rds_device_get_bytes(self.h, stream, first, out.ctypes.data, n)
+        if got < 0:
+            _check(got, "fmgpu_rds_device_get_bytes")
+        return out[:got].tobytes()
+
+    def rds_db(self, stream: int = 0) -> dict:
+        pi, pty = C.c_uint16(0), C.c_uint8(0)
+        ps, rt = C.create_string_buffer(8), C.create_string_buffer(64)
+        _check(self.L.fmgpu_rds_device_get_db(self.h, stream, C.byref(pi), ps, rt, C.byref(pty)), "fmgpu_rds_device_get_db")
+        return {"pi": pi.value, "pty": pty.value, "ps": ps.raw, "rt": rt.raw}
 
 
 class RDSDecoder:

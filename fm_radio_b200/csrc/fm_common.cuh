@@ -8,6 +8,7 @@
 //   K4  k4_mix_fir       harmonic mixdown x2/x3 fused with the three 128-tap decimators, stereo mix
 //   K4b k4b_lmr_phase    per-stream L-R phase-offset update (applied to the next block)
 //   K5  k5_bpsk          per-stream RDS AGC + BPSK symbol synchroniser -> soft symbols
+//   K6  k6_rds           per-stream RDS bit path: symbols -> groups -> PI / PS / RadioText
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -155,6 +156,11 @@ cudaError_t launch_k4(const float2* fm_out_iq, const float* pll_dt,
                       float* rds_power_partial, float* dbg_lpr, float* dbg_lmr, const K4Params& p, cudaStream_t st);
 cudaError_t launch_k5(const float2* rds_in, const float* rds_power_partial, float* state, float* pred_sym,
                       int* sym_count, const K5Debug& d, const K5Params& p, cudaStream_t st);
+// K6: RDS bit path on the device (k6_rds.cu); state is an array of rds::State, glog of fmgpu_rds_group
+cudaError_t launch_k6(const float* pred_sym, const int* sym_count, void* state, const void* tables, void* glog, uint8_t* blog,
+                      int n64, int gcap, int bcap, int n_streams, cudaStream_t st);
+cudaError_t launch_k6_init(void* state, int n_streams, cudaStream_t st);
+size_t k6_state_bytes();
 // debug-only finalisation of the GUI buffers: pilot *= gain, pll = (S(t+1/4), S(t))
 cudaError_t launch_kdbg(float2* pilot, const float* pll_state, const float* pll_dt, float2* pll_out,
                         int n, int n_streams, cudaStream_t st);

@@ -7,7 +7,9 @@
 // X(k) after X-1(k) and after the last reader of the slot's buffers.  The two latency-bound
 // recurrences (K3, K5: one thread per stream) therefore overlap with the FMA-bound kernels of the
 // neighbouring blocks instead of serialising the chain.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +18,9 @@
 #include <vector>
 #include "../../include/fmgpu.h"
 #include "fm_common.cuh"
+#include "rds_core.h"
+
+extern "C" const void* fmgpu_rds_tables_(size_t* bytes);     // rds_host.cpp
 
 namespace {
 
@@ -64,6 +69,9 @@ struct fmgpu_demod {
     int B = 0, S = 0, n4 = 0, n8 = 0, n32 = 0, n64 = 0, depth = 0, k4_tiles = 0;
     int device = 0;
     cudaStream_t stH = nullptr, stA = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stO = nullptr;
+    // SM partition (green contexts): the recurrence stages B, D get their own SMs
+    CUgreenCtx gctx_rec = nullptr, gctx_fir = nullptr;
+    int sms_rec = 0, sms_fir = 0;
     std::vector<Slot> slots;
     std::vector<HostMirror> mirrors;
     DebugBufs dbg;
@@ -76,6 +84,12 @@ struct fmgpu_demod {
     float2* k4_hist_m3[2] = { nullptr, nullptr };
     float* lmr_phase = nullptr;
     float* bpsk_state = nullptr;
+    // K6: device RDS decoders ([S] rds::State) and their result rings
+    void* rds_state = nullptr; void* rds_glog = nullptr; uint8_t* rds_blog = nullptr; void* rds_tables = nullptr;
+    int rds_gcap = 0, rds_bcap = 0;
+    std::vector<rds::State> rds_host_state;            // fmgpu_rds_device_fetch copies
+    std::vector<fmgpu_rds_group> rds_host_glog;
+    std::vector<uint8_t> rds_host_blog;
     float2* in_f32 = nullptr;      // cf32 path staging (lazy)
     // host-side configuration
     HostTaps taps{};
@@ -165,19 +179,80 @@ int init_state(fmgpu_demod* h) {
     return FMGPU_OK;
 }
 
+// Splits the device's SMs into {recurrence partition, FIR partition} with the driver's green-context API
+// (cuda.h "Green Contexts"; entry points fetched through the runtime, so libcuda is not a link dependency)
+// and creates stage streams B, D on the first and A, C on the second.  Returns false, with nothing
+// created, when partitioning is disabled or unsupported.
+bool create_partitioned_streams(fmgpu_demod* h, int prio_hi) {
+    if (std::getenv("FMGPU_NO_PARTITION")) return false;
+    unsigned want = 16;                                   // 64 recurrence warps at 1024 streams = one per SM sub-partition
+    if (const char* e = std::getenv("FMGPU_RECURRENCE_SMS")) want = (unsigned)std::atoi(e);
+    if (want == 0) return false;
+#define DRV(name) decltype(&name) p_##name = nullptr; { void* fp = nullptr; cudaDriverEntryPointQueryResult qr; \
+        if (cudaGetDriverEntryPoint(#name, &fp, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fp) { cudaGetLastError(); return false; } \
+        p_##name = (decltype(&name))fp; }
+    DRV(cuDeviceGet) DRV(cuDeviceGetDevResource) DRV(cuDevSmResourceSplitByCount) DRV(cuDevResourceGenerateDesc)
+    DRV(cuGreenCtxCreate) DRV(cuGreenCtxDestroy) DRV(cuGreenCtxStreamCreate)
+#undef DRV
+    CUdevice dev;
+    if (p_cuDeviceGet(&dev, h->device) != CUDA_SUCCESS) return false;
+    CUdevResource all{}, rec{}, rest{};
+    if (p_cuDeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned groups = 1;
+    if (p_cuDevSmResourceSplitByCount(&rec, &groups, &all, &rest, 0, want) != CUDA_SUCCESS || groups != 1) return false;
+    if (rec.sm.smCount == 0 || rest.sm.smCount == 0) return false;
+    CUdevResourceDesc d_rec = nullptr, d_rest = nullptr;
+    if (p_cuDevResourceGenerateDesc(&d_rec, &rec, 1) != CUDA_SUCCESS) return false;
+    if (p_cuDevResourceGenerateDesc(&d_rest, &rest, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx g_rec = nullptr, g_rest = nullptr;
+    if (p_cuGreenCtxCreate(&g_rec, d_rec, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (p_cuGreenCtxCreate(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(g_rec); return false; }
+    CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
+    const bool ok = p_cuGreenCtxStreamCreate(&a, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&b, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
+    if (!ok) {
+        for (CUstream st : { a, b, c, d }) if (st) cudaStreamDestroy((cudaStream_t)st);
+        p_cuGreenCtxDestroy(g_rec); p_cuGreenCtxDestroy(g_rest);
+        return false;
+    }
+    h->stA = (cudaStream_t)a; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d;
+    h->gctx_rec = g_rec; h->gctx_fir = g_rest;
+    h->sms_rec = (int)rec.sm.smCount; h->sms_fir = (int)rest.sm.smCount;
+    return true;
+}
+
+void destroy_partition(fmgpu_demod* h) {
+    if (!h->gctx_rec && !h->gctx_fir) return;
+    void* fp = nullptr; cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &fp, cudaEnableDefault, &qr) == cudaSuccess && fp) {
+        auto destroy = (decltype(&cuGreenCtxDestroy))fp;
+        if (h->gctx_rec) destroy(h->gctx_rec);
+        if (h->gctx_fir) destroy(h->gctx_fir);
+    }
+    h->gctx_rec = h->gctx_fir = nullptr;
+}
+
 int alloc_all(fmgpu_demod* h) {
     const size_t S = h->S;
     CU(cudaStreamCreateWithFlags(&h->stH, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->stA, cudaStreamNonBlocking));
-    // The two latency-bound recurrences get the highest CTA-scheduling priority: their 32 + 32
-    // one-warp CTAs must never queue behind the thousands of CTAs of the FMA-bound kernels.
+    CU(cudaStreamCreateWithFlags(&h->stO, cudaStreamNonBlocking));
+    // The two latency-bound recurrences (stage B: K3; stage D: K5, K6 -- one thread per stream, 32 + 32
+    // one-warp CTAs at 1024 streams) lose 1.5x when their warps share SM sub-partitions with the FFMA
+    // streams of K1/K2/K4 (measured: K3 0.278 ms alone, 0.428 ms inside the pipeline), and they are the
+    // pipeline's critical stages.  So the handle splits the GPU with green contexts: a small SM
+    // partition runs only stages B and D, the rest runs the FIR stages A and C.
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    if (std::getenv("FMGPU_NO_PRIORITY")) prio_hi = prio_lo;
-    CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_hi));
-    CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
-    CU(cudaStreamCreateWithFlags(&h->stO, cudaStreamNonBlocking));
+    if (!create_partitioned_streams(h, prio_hi)) {
+        // no partition (FMGPU_NO_PARTITION, or the driver refused): plain streams; the recurrences at
+        // least get the highest CTA-scheduling priority
+        CU(cudaStreamCreateWithFlags(&h->stA, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_hi));
+        CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
+    }
     for (int i = 0; i < 2; i++) {
         CU(dalloc(&h->k1_hist[i], S * fm::K1_HIST));
         CU(dalloc(&h->k4_hist_x[i], S * fm::K4_NN));
@@ -190,6 +265,22 @@ int alloc_all(fmgpu_demod* h) {
     CU(dalloc(&h->pll_state, S * fm::PLL_STATE_N));
     CU(dalloc(&h->bpsk_state, S * fm::BP_STATE_N));
     CU(dalloc(&h->lmr_phase, S));
+    // rings sized for what one block can produce (n64 chips -> n64/2 bits) plus slack, so a fetch
+    // every block never loses anything; at least 64 groups / 1 KiB of packets
+    h->rds_gcap = std::max(64, h->n64 / 2 / 104 * 2 + 8);
+    h->rds_bcap = std::max(1024, ((h->n64 / 16 * 2 + 64) + 15) / 16 * 16);
+    CU(cudaMalloc(&h->rds_state, S * fm::k6_state_bytes()));
+    CU(cudaMalloc(&h->rds_glog, S * h->rds_gcap * sizeof(fmgpu_rds_group)));
+    CU(cudaMemset(h->rds_glog, 0, S * h->rds_gcap * sizeof(fmgpu_rds_group)));
+    CU(dalloc(&h->rds_blog, S * h->rds_bcap));
+    {
+        size_t tb = 0;
+        const void* src = fmgpu_rds_tables_(&tb);
+        CU(cudaMalloc(&h->rds_tables, tb));
+        CU(cudaMemcpy(h->rds_tables, src, tb, cudaMemcpyHostToDevice));
+    }
+    CU(fm::launch_k6_init(h->rds_state, h->S, h->stD));
+    CU(cudaStreamSynchronize(h->stD));
     h->slots.resize(h->depth);
     h->mirrors.resize(h->depth);
     for (int i = 0; i < h->depth; i++) {
@@ -232,6 +323,7 @@ void free_all(fmgpu_demod* h) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int i = 0; i < 2; i++) { F(h->k1_hist[i]); F(h->k4_hist_x[i]); F(h->k4_hist_m2[i]); F(h->k4_hist_m3[i]); }
     F(h->k2_hist_demod); F(h->k2_hist_out); F(h->k2_scal); F(h->pll_state); F(h->bpsk_state); F(h->lmr_phase); F(h->in_f32);
+    F(h->rds_state); F(h->rds_glog); F(h->rds_blog); F(h->rds_tables);
     for (auto& sl : h->slots) {
         F(sl.in_u8); F(sl.fm_demod); F(sl.fm_out_iq); F(sl.theta); F(sl.power); F(sl.pll_dt); F(sl.audio); F(sl.rds);
         F(sl.est_partial); F(sl.rds_pw_partial); F(sl.pred_sym); F(sl.sym_count);
@@ -249,6 +341,7 @@ void free_all(fmgpu_demod* h) {
     F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
     cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
     for (auto st : sts) if (st) cudaStreamDestroy(st);
+    destroy_partition(h);
 }
 
 // Enqueue the chain for one block whose input is already ordered on stA (or signalled by ev_H).
@@ -349,8 +442,12 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, h->stD));
     }
     if (prof) CU(cudaEventRecord(prof[8], h->stD));
+    // ---- stage D, continued: K6 RDS bit path (symbols -> groups -> PI/PS/RT), per-stream state on the device ----
+    static const bool no_k6 = std::getenv("FMGPU_NO_K6") != nullptr;      // measurement aid
+    if (!no_k6) CU(fm::launch_k6(sl.pred_sym, sl.sym_count, h->rds_state, h->rds_tables, h->rds_glog, h->rds_blog, h->n64, h->rds_gcap, h->rds_bcap, h->S, h->stD));
+    if (prof) CU(cudaEventRecord(prof[9], h->stD));
     CU(cudaEventRecord(sl.ev_D, h->stD));
-    h->launches += 6;
+    h->launches += 7;
     h->step++;
     h->dbg_valid = false;
     return slot;
@@ -484,25 +581,33 @@ int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev) {
     return rc < 0 ? rc : FMGPU_OK;
 }
 
-int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[5]) {
-    if (!h || !iq_dev || !ms || n_blocks < 1) return fail(FMGPU_ERR_ARG, "profile_stages: bad argument");
+int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[6]) {
+    if (!h || !iq_dev || !ms || n_blocks == 0) return fail(FMGPU_ERR_ARG, "profile_stages: bad argument");
     CU(cudaSetDevice(h->device));
-    cudaEvent_t ev[9];
+    // n_blocks > 0: blocks one at a time (kernel times in isolation).  n_blocks < 0: |n_blocks| blocks
+    // enqueued back to back like the production path, so the times are those of the kernels while they
+    // share the GPU with the other stages' kernels (averaged over the second half of the run).
+    const bool piped = n_blocks < 0;
+    const int n = piped ? -n_blocks : n_blocks;
+    std::vector<cudaEvent_t> ev((size_t)10 * n);
     for (auto& e : ev) CU(cudaEventCreate(&e));
-    double acc[5] = { 0, 0, 0, 0, 0 };
-    const int pairs[5][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 } };
-    for (int b = 0; b < n_blocks; b++) {
-        if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
-        const int rc = enqueue_chain(h, iq_dev, true, false, ev);
+    double acc[6] = { 0, 0, 0, 0, 0, 0 };
+    const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 }, { 8, 9 } };
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    for (int b = 0; b < n; b++) {
+        const int rc = enqueue_chain(h, iq_dev, true, false, &ev[(size_t)10 * b]);
         if (rc < 0) return rc;
-        if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
-        for (int i = 0; i < 5; i++) {
+        if (!piped && sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    }
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    const int b0 = piped ? n / 2 : 0;
+    for (int b = b0; b < n; b++)
+        for (int i = 0; i < 6; i++) {
             float t = 0.0f;
-            CU(cudaEventElapsedTime(&t, ev[pairs[i][0]], ev[pairs[i][1]]));
+            CU(cudaEventElapsedTime(&t, ev[(size_t)10 * b + pairs[i][0]], ev[(size_t)10 * b + pairs[i][1]]));
             acc[i] += t;
         }
-    }
-    for (int i = 0; i < 5; i++) ms[i] = (float)(acc[i] / n_blocks);
+    for (int i = 0; i < 6; i++) ms[i] = (float)(acc[i] / (n - b0));
     for (auto& e : ev) cudaEventDestroy(e);
     return FMGPU_OK;
 }
@@ -703,6 +808,74 @@ int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out) {
 }
 
 long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
+
+int fmgpu_get_partition(fmgpu_demod* h, int sms[2]) {
+    if (!h || !sms) return fail(FMGPU_ERR_ARG, "get_partition: null argument");
+    sms[0] = h->sms_rec; sms[1] = h->sms_fir;
+    return FMGPU_OK;
+}
+
+// ---- device RDS decoders (K6) ----
+int fmgpu_rds_device_fetch(fmgpu_demod* h) {
+    if (!h) return fail(FMGPU_ERR_ARG, "rds_device_fetch: null handle");
+    CU(cudaSetDevice(h->device));
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    const size_t S = h->S;
+    h->rds_host_state.resize(S);
+    h->rds_host_glog.resize(S * h->rds_gcap);
+    h->rds_host_blog.resize(S * h->rds_bcap);
+    CU(cudaMemcpy(h->rds_host_state.data(), h->rds_state, S * sizeof(rds::State), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->rds_host_glog.data(), h->rds_glog, S * h->rds_gcap * sizeof(fmgpu_rds_group), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h->rds_host_blog.data(), h->rds_blog, S * h->rds_bcap, cudaMemcpyDeviceToHost));
+    return FMGPU_OK;
+}
+
+static const rds::State* rds_fetched(fmgpu_demod* h, int stream) {
+    if (!h || stream < 0 || stream >= h->S) { fail(FMGPU_ERR_ARG, "rds_device: bad argument"); return nullptr; }
+    if (h->rds_host_state.empty()) { fail(FMGPU_ERR_STATE, "rds_device: call fmgpu_rds_device_fetch first"); return nullptr; }
+    return &h->rds_host_state[stream];
+}
+
+int fmgpu_rds_device_counts(fmgpu_demod* h, int stream, unsigned long long* n_groups, unsigned long long* n_bytes, int* ring_caps) {
+    const rds::State* st = rds_fetched(h, stream);
+    if (!st) return FMGPU_ERR_STATE;
+    if (n_groups) *n_groups = st->n_groups;
+    if (n_bytes) *n_bytes = st->n_bytes;
+    if (ring_caps) { ring_caps[0] = h->rds_gcap; ring_caps[1] = h->rds_bcap; }
+    return FMGPU_OK;
+}
+
+int fmgpu_rds_device_get_groups(fmgpu_demod* h, int stream, unsigned long long first, fmgpu_rds_group* out, int max_groups) {
+    const rds::State* st = rds_fetched(h, stream);
+    if (!st || !out) return FMGPU_ERR_STATE;
+    const unsigned long long total = st->n_groups, cap = (unsigned long long)h->rds_gcap;
+    if (first > total || total - first > cap) return fail(FMGPU_ERR_STATE, "rds_device_get_groups: range no longer in the ring");
+    int n = 0;
+    for (unsigned long long g = first; g < total && n < max_groups; g++, n++)
+        out[n] = h->rds_host_glog[(size_t)stream * cap + (size_t)(g % cap)];
+    return n;
+}
+
+int fmgpu_rds_device_get_bytes(fmgpu_demod* h, int stream, unsigned long long first, uint8_t* out, int max_bytes) {
+    const rds::State* st = rds_fetched(h, stream);
+    if (!st || !out) return FMGPU_ERR_STATE;
+    const unsigned long long total = st->n_bytes, cap = (unsigned long long)h->rds_bcap;
+    if (first > total || total - first > cap) return fail(FMGPU_ERR_STATE, "rds_device_get_bytes: range no longer in the ring");
+    int n = 0;
+    for (unsigned long long b = first; b < total && n < max_bytes; b++, n++)
+        out[n] = h->rds_host_blog[(size_t)stream * cap + (size_t)(b % cap)];
+    return n;
+}
+
+int fmgpu_rds_device_get_db(fmgpu_demod* h, int stream, uint16_t* pi, char ps8[8], char rt64[64], uint8_t* pty) {
+    const rds::State* st = rds_fetched(h, stream);
+    if (!st) return FMGPU_ERR_STATE;
+    if (pi) *pi = st->pi;
+    if (pty) *pty = st->pty;
+    if (ps8) std::memcpy(ps8, st->ps, 8);
+    if (rt64) std::memcpy(rt64, st->rt, 64);
+    return FMGPU_OK;
+}
 
 // ---- stand-alone polyphase decimator (dsp/polyphase_filter.h:9-87) ----
 struct fmgpu_polyphase {

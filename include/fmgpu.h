@@ -23,6 +23,12 @@ extern "C" {
 
 typedef struct fmgpu_demod fmgpu_demod;
 typedef struct fmgpu_rds fmgpu_rds;
+/* one RDS group as RDS_Group_Sync hands it to RDS_Decoder (rds_decoder/rds_group.h) */
+typedef struct fmgpu_rds_group {
+    uint16_t data[4];
+    uint8_t  valid[4];
+    uint8_t  type[4];        /* BlockOffsetID: A=0 B=1 C=2 C1=3 D=4 (rds_constants.h:29)       */
+} fmgpu_rds_group;
 
 enum {
     FMGPU_OK = 0,
@@ -165,10 +171,34 @@ int fmgpu_get_rates(fmgpu_demod* h, int rates_hz[5]);
 int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out);
 /* Measurement aid: runs n_blocks blocks ONE AT A TIME (no overlap between blocks) on the device
  * input iq_dev with CUDA events recorded on the launching streams around each kernel, and returns
- * the average device time in ms of K1, K2, K3, K4(+K4b), K5.  Advances the demodulator state. */
-int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[5]);
+ * the average device time in ms of K1, K2, K3, K4(+K4b), K5, K6.  n_blocks < 0: |n_blocks| blocks
+ * enqueued back to back as in production, i.e. the kernels' times while the stages overlap.
+ * Advances the demodulator state. */
+int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[6]);
+/* SM partition of the handle: sms[0] = SMs reserved for the per-stream recurrences (pilot PLL, BPSK
+ * synchroniser, RDS bit path), sms[1] = SMs of the FIR stages; {0, 0} when the device is not
+ * partitioned (FMGPU_NO_PARTITION=1 in the environment, or the driver has no green contexts). */
+int fmgpu_get_partition(fmgpu_demod* h, int sms[2]);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long fmgpu_launch_count(fmgpu_demod* h);
+
+/* ---- RDS bit path on the device (kernel K6) -------------------------------------------------
+ * Every enqueue/process call also runs, per stream on the device, what App does on the host after
+ * each block (app.cpp:66-77): DifferentialManchesterDecoder::Process
+ * (rds_decoder/differential_manchester_decoder.h:25-59) -> RDS_Decoding_Chain::Process
+ * (rds_decoding_chain.h:24) -> RDS_Group_Sync / CalculateCRC10 / RDS_Decoder::ProcessGroup and the
+ * PI/PTY/PS/RT part of RDS_Database.  Results stay on the device: per stream the running totals,
+ * the database, and rings of the most recent groups and 16-byte packets (the rings hold at least
+ * what two blocks produce).  fmgpu_rds_device_fetch synchronises the handle and copies them to
+ * the host once; the getters then read that copy.  Indices are absolute (0 = first group / byte
+ * since creation); a range that has left the ring fails with FMGPU_ERR_STATE.
+ * The getters return the number of items copied (>= 0) or a negative error. */
+int fmgpu_rds_device_fetch(fmgpu_demod* h);
+int fmgpu_rds_device_counts(fmgpu_demod* h, int stream, unsigned long long* n_groups, unsigned long long* n_bytes,
+                            int ring_caps[2] /* out, may be NULL: groups, bytes */);
+int fmgpu_rds_device_get_groups(fmgpu_demod* h, int stream, unsigned long long first, fmgpu_rds_group* out, int max_groups);
+int fmgpu_rds_device_get_bytes(fmgpu_demod* h, int stream, unsigned long long first, uint8_t* out, int max_bytes);
+int fmgpu_rds_device_get_db(fmgpu_demod* h, int stream, uint16_t* pi, char ps8[8], char rt64[64], uint8_t* pty);
 
 /* ---- host-side filter designers: src/dsp/filter_designer.h:8-35, same signatures ----------- */
 void fmgpu_create_fir_lpf(float* b, int N, float k);
@@ -189,11 +219,6 @@ int  fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* 
 
 /* ---- RDS bit path on the host (differential_manchester_decoder.h:25-59, rds_group_sync.cpp,
  * crc10.cpp, and the PI/PTY/PS/RT subset of rds_decoder.cpp) ---------------------------------- */
-typedef struct fmgpu_rds_group {
-    uint16_t data[4];
-    uint8_t  valid[4];
-    uint8_t  type[4];        /* BlockOffsetID: A=0 B=1 C=2 C1=3 D=4 (rds_constants.h:29)       */
-} fmgpu_rds_group;
 fmgpu_rds* fmgpu_rds_create(void);
 void fmgpu_rds_destroy(fmgpu_rds* r);
 void fmgpu_rds_push_symbols(fmgpu_rds* r, const float* sym, size_t n);

@@ -182,6 +182,57 @@ def test_batched_streams_async_pipeline_matches_per_stream_checker():
     g.close(); gs.close()
 
 
+def test_device_rds_bit_path_equals_host_decoder_and_checker():
+    """K6 (RDS decoded on the device, per stream) against the host decoder fed with the same symbols and
+    against the checker's own decoder: groups, validity flags, block types, packet bytes, PI/PTY/PS/RT --
+    bit-exact.  Results are collected every 16 blocks while 3 blocks are in flight; 112 blocks make both
+    result rings wrap, and a range that has left the ring must be refused."""
+    import torch
+    S, nblk = 3, 112
+    caps = np.stack([synth.synth_u8_numpy(H.B * nblk, synth.StreamParams.for_stream(40 + s)) for s in range(S)])
+    dev_in = torch.from_numpy(caps).cuda()
+    g = fm.FMDemod(H.B, S, pipeline_depth=3)
+    g.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    decs = [fm.RDSDecoder() for _ in range(S)]
+    got_groups = [[np.zeros((0, 4), np.uint16), np.zeros((0, 4), np.uint8), np.zeros((0, 4), np.uint8)] for _ in range(S)]
+    got_bytes = [b"" for _ in range(S)]
+    keep = []
+    for k in range(nblk):
+        blk = dev_in[:, 2 * H.B * k:2 * H.B * (k + 1)].contiguous()
+        keep.append(blk)
+        slot = g.enqueue_u8_device(blk)
+        g.fetch_outputs(slot); g.sync()
+        for s in range(S):
+            decs[s].push_symbols(g.get(Buf.RDS_PRED_SYM, s))
+        if (k + 1) % 16 == 0:
+            g.rds_fetch()
+            for s in range(S):
+                d, v, t = g.rds_groups(s, first=len(got_groups[s][0]))
+                got_groups[s] = [np.concatenate([a, b]) for a, b in zip(got_groups[s], (d, v, t))]
+                got_bytes[s] += g.rds_bytes(s, first=len(got_bytes[s]))
+    gcap, bcap = g.rds_ring_caps()
+    for s in range(S):
+        hd, hv, ht = decs[s].groups()
+        assert len(hd) > gcap and len(decs[s].rds_bytes()) > bcap        # both rings wrapped
+        assert g.rds_counts(s) == (len(hd), len(decs[s].rds_bytes()))
+        assert np.array_equal(got_groups[s][0], hd) and np.array_equal(got_groups[s][1], hv) and np.array_equal(got_groups[s][2], ht)
+        assert got_bytes[s] == decs[s].rds_bytes()
+        assert g.rds_db(s) == decs[s].db()
+        assert g.rds_db(s)["pi"] == 0x1000 + 40 + s
+        with pytest.raises(fm.FMGPUError):
+            g.rds_groups(s, first=0)
+        with pytest.raises(fm.FMGPUError):
+            g.rds_bytes(s, first=0)
+    chk = bind.CpuDemod(H.B, "port")
+    for k in range(nblk):
+        chk.process_u8(caps[0, 2 * H.B * k:2 * H.B * (k + 1)])
+    for a, b in zip(got_groups[0], chk.groups()):
+        assert np.array_equal(a, b)
+    assert got_bytes[0] == chk.rds_bytes()
+    assert g.rds_db(0) == chk.db()
+    g.close()
+
+
 def test_overlapped_pipeline_equals_serial():
     """Many blocks in flight (no sync between enqueues) give bit-identical results to one at a time."""
     import torch
