@@ -23,9 +23,9 @@ constexpr int K1_TILE = K1_R * K1_THREADS;          // 2048 outputs = 8192 IQ sa
 constexpr int K1_SEG = 16 * 8 + 4;                  // floats per 16-frame segment (+4 pad: bank skew)
 constexpr int K1_HIST = 64;                         // IQ samples of history
 
-constexpr int K2_THREADS = 256;
+constexpr int K2_THREADS = 128;
 constexpr int K2_R = 8;
-constexpr int K2_CH = K2_THREADS * K2_R;            // 2048 fm_out samples per chunk
+constexpr int K2_CH = K2_THREADS * K2_R;            // 1024 fm_out samples per chunk (of each of the two streams of a CTA)
 constexpr int K2_NN = 64;                           // filt_poly_ds_lpf_fm_out (:146-157)
 constexpr int K2_HILB = 65;                         // filt_hilbert_transform (:192-195)
 
@@ -48,6 +48,53 @@ __device__ __forceinline__ float chebyshev_sine(float x) {
     b = fmaf(b, z, 64.83583069f);
     b = fmaf(b, z, -25.13274193f);
     return b * (z - 0.25f) * x;
+}
+
+// atan2 of the discriminator (K1) and of the pilot angle (K2), shared by every kernel (so the cf32 and u8
+// entry points give identical bits): minimax odd polynomial of degree 15 on [0, 1], 1.2e-7 rad max error in fp32, one MUFU.RCP.
+__device__ __forceinline__ float fm_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float q = __fdividef(mn, mx);
+    q = (mx == 0.0f) ? 0.0f : q;                         // atan2(0, 0) = 0 as the reference's libm
+    const float s = q * q;
+    float p = -0.004054562299f;
+    p = fmaf(p, s, 0.021862939178f);
+    p = fmaf(p, s, -0.05591229796f);
+    p = fmaf(p, s, 0.096421950378f);
+    p = fmaf(p, s, -0.139086285623f);
+    p = fmaf(p, s, 0.1994656543f);
+    p = fmaf(p, s, -0.333298607622f);
+    p = fmaf(p, s, 0.999999335572f);
+    float r = p * q;
+    r = (ay > ax) ? (0.5f * PI_F - r) : r;
+    r = (x < 0.0f) ? (PI_F - r) : r;
+    return copysignf(r, y);
+}
+
+// Two atan2 at once for the packed FP32 pipe (FFMA2 / FMUL2, sm_100): operation for operation the
+// same IEEE sequence as fm_atan2f, so both give identical bits for identical inputs.
+__device__ __forceinline__ float2 fm_atan2f_x2(float y0, float x0, float y1, float x1) {
+    const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    float2 q = make_float2(__fdividef(mn0, mx0), __fdividef(mn1, mx1));
+    q.x = (mx0 == 0.0f) ? 0.0f : q.x;
+    q.y = (mx1 == 0.0f) ? 0.0f : q.y;
+    const float2 s = __fmul2_rn(q, q);
+    float2 p = make_float2(-0.004054562299f, -0.004054562299f);
+    p = __ffma2_rn(p, s, make_float2(0.021862939178f, 0.021862939178f));
+    p = __ffma2_rn(p, s, make_float2(-0.05591229796f, -0.05591229796f));
+    p = __ffma2_rn(p, s, make_float2(0.096421950378f, 0.096421950378f));
+    p = __ffma2_rn(p, s, make_float2(-0.139086285623f, -0.139086285623f));
+    p = __ffma2_rn(p, s, make_float2(0.1994656543f, 0.1994656543f));
+    p = __ffma2_rn(p, s, make_float2(-0.333298607622f, -0.333298607622f));
+    p = __ffma2_rn(p, s, make_float2(0.999999335572f, 0.999999335572f));
+    float2 r = __fmul2_rn(p, q);
+    r.x = (ay0 > ax0) ? (0.5f * PI_F - r.x) : r.x;
+    r.y = (ay1 > ax1) ? (0.5f * PI_F - r.y) : r.y;
+    r.x = (x0 < 0.0f) ? (PI_F - r.x) : r.x;
+    r.y = (x1 < 0.0f) ? (PI_F - r.y) : r.y;
+    return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
 }
 
 // dsp/clamp.h:4-8
