@@ -1,7 +1,8 @@
 // C-ABI implementation (include/fmgpu.h): handle, per-stream device state, the stage pipeline.
 //
-// Execution model: five stage streams per handle.  Block k of the batch flows
-//     H (host->device copy) -> A (K1, K2) -> B (K3 pilot PLL) -> C (K4, K4b) -> D (K5 BPSK) -> O (device->host)
+// Execution model: six stage streams per handle.  Block k of the batch flows
+//     H (host->device copy) -> A (K1, K2) -> B (K3 pilot PLL) -> C (K4, K4b) -> D (K5 BPSK) -> E (K6 RDS bits)
+//                                                                               D -> O (device->host)
 // through ring slot k % depth; stage X of block k+1 follows stage X of block k on the same stream
 // (all cross-block filter/loop state is owned by exactly one stage), and CUDA events order stage
 // X(k) after X-1(k) and after the last reader of the slot's buffers.  The two latency-bound
@@ -49,7 +50,7 @@ struct Slot {
     float* rds_pw_partial = nullptr;
     float* pred_sym = nullptr;     // [S][B/64]
     int* sym_count = nullptr;      // [S]
-    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_O;
+    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_E, ev_O;
 };
 
 struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
@@ -68,7 +69,7 @@ struct fmgpu_demod {
     fmgpu_config cfg{};
     int B = 0, S = 0, n4 = 0, n8 = 0, n32 = 0, n64 = 0, depth = 0, k4_tiles = 0;
     int device = 0;
-    cudaStream_t stH = nullptr, stA = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stO = nullptr;
+    cudaStream_t stH = nullptr, stA = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stE = nullptr, stO = nullptr;
     // SM partition (green contexts): the recurrence stages B, D get their own SMs
     CUgreenCtx gctx_rec = nullptr, gctx_fir = nullptr;
     int sms_rec = 0, sms_fir = 0;
@@ -207,17 +208,18 @@ bool create_partitioned_streams(fmgpu_demod* h, int prio_hi) {
     CUgreenCtx g_rec = nullptr, g_rest = nullptr;
     if (p_cuGreenCtxCreate(&g_rec, d_rec, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     if (p_cuGreenCtxCreate(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(g_rec); return false; }
-    CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
+    CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr, e2 = nullptr;
     const bool ok = p_cuGreenCtxStreamCreate(&a, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&b, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
-                 && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
+                 && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&e2, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
     if (!ok) {
-        for (CUstream st : { a, b, c, d }) if (st) cudaStreamDestroy((cudaStream_t)st);
+        for (CUstream st : { a, b, c, d, e2 }) if (st) cudaStreamDestroy((cudaStream_t)st);
         p_cuGreenCtxDestroy(g_rec); p_cuGreenCtxDestroy(g_rest);
         return false;
     }
-    h->stA = (cudaStream_t)a; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d;
+    h->stA = (cudaStream_t)a; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d; h->stE = (cudaStream_t)e2;
     h->gctx_rec = g_rec; h->gctx_fir = g_rest;
     h->sms_rec = (int)rec.sm.smCount; h->sms_fir = (int)rest.sm.smCount;
     return true;
@@ -252,6 +254,7 @@ int alloc_all(fmgpu_demod* h) {
         CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_hi));
         CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
+        CU(cudaStreamCreateWithPriority(&h->stE, cudaStreamNonBlocking, prio_hi));
     }
     for (int i = 0; i < 2; i++) {
         CU(dalloc(&h->k1_hist[i], S * fm::K1_HIST));
@@ -296,7 +299,7 @@ int alloc_all(fmgpu_demod* h) {
         CU(dalloc(&sl.rds_pw_partial, S * h->k4_tiles));
         CU(dalloc(&sl.pred_sym, S * h->n64));
         CU(dalloc(&sl.sym_count, S));
-        cudaEvent_t* evs[6] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_O };
+        cudaEvent_t* evs[7] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_E, &sl.ev_O };
         for (auto* ev : evs) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         HostMirror& m = h->mirrors[i];
         CU(cudaMallocHost((void**)&m.audio, S * h->n32 * sizeof(float2)));
@@ -327,7 +330,7 @@ void free_all(fmgpu_demod* h) {
     for (auto& sl : h->slots) {
         F(sl.in_u8); F(sl.fm_demod); F(sl.fm_out_iq); F(sl.theta); F(sl.power); F(sl.pll_dt); F(sl.audio); F(sl.rds);
         F(sl.est_partial); F(sl.rds_pw_partial); F(sl.pred_sym); F(sl.sym_count);
-        cudaEvent_t evs[6] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_O };
+        cudaEvent_t evs[7] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_O };
         for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     }
     for (auto& m : h->mirrors) {
@@ -339,7 +342,7 @@ void free_all(fmgpu_demod* h) {
     F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr);
     F(d.k5.rds); F(d.k5.raw_sym); F(d.k5.pll_sym); F(d.k5.zcd); F(d.k5.dump_trig);
     F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
-    cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
+    cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) if (st) cudaStreamDestroy(st);
     destroy_partition(h);
 }
@@ -422,6 +425,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     // ---- stage D: K5 ----
     CU(cudaStreamWaitEvent(h->stD, sl.ev_C, 0));
     CU(cudaStreamWaitEvent(h->stD, sl.ev_O, 0));        // the fetch read sl.pred_sym / sl.sym_count
+    CU(cudaStreamWaitEvent(h->stD, sl.ev_E, 0));        // ... and so did K6 of the slot's previous block
     {
         fm::K5Params p{};
         std::memcpy(p.ted_b, h->taps.ted_b, 8); std::memcpy(p.ted_a, h->taps.ted_a, 8);
@@ -442,11 +446,14 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, h->stD));
     }
     if (prof) CU(cudaEventRecord(prof[8], h->stD));
-    // ---- stage D, continued: K6 RDS bit path (symbols -> groups -> PI/PS/RT), per-stream state on the device ----
-    static const bool no_k6 = std::getenv("FMGPU_NO_K6") != nullptr;      // measurement aid
-    if (!no_k6) CU(fm::launch_k6(sl.pred_sym, sl.sym_count, h->rds_state, h->rds_tables, h->rds_glog, h->rds_blog, h->n64, h->rds_gcap, h->rds_bcap, h->S, h->stD));
-    if (prof) CU(cudaEventRecord(prof[9], h->stD));
     CU(cudaEventRecord(sl.ev_D, h->stD));
+    // ---- stage E: K6 RDS bit path (symbols -> groups -> PI/PS/RT), per-stream state on the device.  Its own
+    //      stream, so that K6 of block k overlaps K5 of block k+1 (both are latency-bound one-warp CTAs) ----
+    CU(cudaStreamWaitEvent(h->stE, sl.ev_D, 0));
+    static const bool no_k6 = std::getenv("FMGPU_NO_K6") != nullptr;      // measurement aid
+    if (!no_k6) CU(fm::launch_k6(sl.pred_sym, sl.sym_count, h->rds_state, h->rds_tables, h->rds_glog, h->rds_blog, h->n64, h->rds_gcap, h->rds_bcap, h->S, h->stE));
+    if (prof) CU(cudaEventRecord(prof[9], h->stE));
+    CU(cudaEventRecord(sl.ev_E, h->stE));
     h->launches += 7;
     h->step++;
     h->dbg_valid = false;
@@ -472,6 +479,7 @@ int sync_all(fmgpu_demod* h) {
     CU(cudaStreamSynchronize(h->stB));
     CU(cudaStreamSynchronize(h->stC));
     CU(cudaStreamSynchronize(h->stD));
+    CU(cudaStreamSynchronize(h->stE));
     CU(cudaStreamSynchronize(h->stO));
     return FMGPU_OK;
 }
@@ -629,7 +637,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-    cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
+    cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) CU(cudaStreamWaitEvent(st, ev, 0));
     CU(cudaEventDestroy(ev));
     return FMGPU_OK;
@@ -637,7 +645,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
 
 int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream) {
     if (!h) return fail(FMGPU_ERR_ARG, "null handle");
-    cudaStream_t sts[6] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stO };
+    cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) {
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

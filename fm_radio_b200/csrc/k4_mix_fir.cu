@@ -10,58 +10,108 @@
 //   MixAudio                                                       :549-585
 //   AGC_Filter power sum for the RDS AGC (sum only)                dsp/agc.h:21-30
 //
-// One CTA = 1024 MPX-rate samples of one stream (+128 samples of FIR history).  The mixed signals
-// are produced ONCE per sample into bank-skewed planar shared arrays (the oscillator comes from the
-// reference's polynomial sine, coefficients verbatim) and the four warps then run the four FIR
-// roles: L+R (real FIR only: the reference discards the imaginary part, :477-479), L-R real,
-// L-R imag, RDS real+imag.  Each thread owns 8 (/4) or 4 (/8) consecutive outputs and slides a
-// register window of input quads: one LDS.128 of samples + one broadcast LDS.128 of taps per 32
-// (16) FFMAs.  History of the MIXED signals is carried (not recomputed) because the reference's
-// FIR history holds samples mixed with the previous block's phase offset.
+// One CTA = 1024 MPX-rate samples (+128 samples of FIR history) of TWO streams, 2p and 2p+1, held
+// as packed float2 (stream 2p, stream 2p+1) exactly like K2: the signals are real-valued planes, so
+// the pair for sm_100's two-wide FP32 instructions is made of two streams, every tap is one FFMA2
+// and every mixing / polynomial-sine step is a packed op.  (First version: one stream per CTA,
+// scalar FFMA, 34 % of the FP32 peak with the issue slots as the limit.)  An odd last stream is
+// paired with itself and its second half discarded.
+//
+// The mixed signals are produced ONCE per sample into bank-skewed planar shared arrays (the
+// oscillator is the reference's polynomial sine, coefficients verbatim); the global loads of a
+// thread's 9 samples are all issued before the first use.  Three of the four warps then run three FIR
+// roles of equal weight (1024 / 1152 / 1024 FFMA2 per lane; the fourth only mixes and post-processes --
+// measured faster than three-warp CTAs, 0.121 vs 0.133 ms, and than splitting RDS over two warps):
+//   warp 0  L+R   : /4 FIR of the real plane (the reference discards the imaginary part, :477-479)
+//   warp 1  L-R   : /4 FIR of the imaginary plane of the 38 kHz mixdown -- the audio -- and the real
+//                   part ONLY at every 10th output, the ones the phase estimator reads (:496-511)
+//   warp 2  RDS   : /8 FIR of the real, then the imaginary plane of the 57 kHz mixdown
+// each thread owning 8 (/4) or 4 (/8) consecutive outputs and sliding a register window of sample
+// quads (taps are stored duplicated in shared memory so that one broadcast LDS.128 yields two ready
+// FFMA2 operands).  Results go through shared memory (aliased onto the dead
+// sample planes) to the MixAudio / estimator epilogue, which writes coalesced.  History of the MIXED
+// signals is carried (not recomputed) because the reference's FIR history holds samples mixed with
+// the previous block's phase offset.
 #include "fm_common.cuh"
 
 namespace fm {
 
 constexpr int K4_LEN = K4_NN + K4_TS;                         // 1152 staged samples
-constexpr int K4_PLEN = K4_LEN + 4 * (K4_LEN >> 5);           // padded: +4 floats per 32
-__device__ __forceinline__ int a4(int i) { return i + 4 * (i >> 5); }
-__device__ __forceinline__ int a4q(int q) { return 4 * q + 4 * (q >> 3); }   // quad q = floats [4q,4q+4)
+__device__ __host__ __forceinline__ constexpr int a4(int i) { return i + 2 * (i >> 5); }   // pair units: +2 pairs per 32
+constexpr int K4_PLEN = a4(K4_LEN) + 8;                       // padded plane length (+ the quad a window may over-read)
+constexpr int K4_SPARSE_MAX = 32;                             // >= ceil(256 / 10) estimator outputs per tile
+constexpr int K4_SMEM_BYTES = (5 * K4_PLEN + 3 * K4_NN) * (int)sizeof(float2);
+// epilogue arrays, aliased onto the sample planes once every FIR has finished
+constexpr int K4_RES_LPR = 0, K4_RES_LMR = K4_TS / 4, K4_RES_SPARSE = 2 * (K4_TS / 4), K4_RES_EST = K4_RES_SPARSE + K4_SPARSE_MAX,
+              K4_RES_END = K4_RES_EST + K4_THREADS;
+static_assert(K4_RES_END <= 5 * K4_PLEN, "epilogue arrays must fit in the planes");
 
-__device__ __forceinline__ float dot4(const float4 x, const float4 b, float acc) {
-    acc = fmaf(x.x, b.x, acc); acc = fmaf(x.y, b.y, acc);
-    acc = fmaf(x.z, b.z, acc); acc = fmaf(x.w, b.w, acc);
-    return acc;
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+// x - nearest integer (ties to even, as the AVX path's _MM_FROUND_TO_NEAREST_INT, apply_harmonic_pll.cpp:129),
+// two at a time: the 1.5 * 2^23 trick is exact for |x| < 2^22
+__device__ __forceinline__ float2 wrap2(float2 x) {
+    const float2 big = bc2(12582912.0f);
+    return __fadd2_rn(x, neg2(__fadd2_rn(__fadd2_rn(x, big), neg2(big))));
 }
 
-// R consecutive outputs of a decimate-by-M 128-tap FIR (M = 4: R = 8, M = 8: R = 4).
-// Output r, tap quad pq reads array quad q0 + (M/4)*r + pq; the window of W = (M/4)*(R-1)+1 quads
-// slides by one quad per pq.  Sum order: taps ascending, as the scalar reference.
+// dsp/simd/chebyshev_sine.h:13-41, two at a time (same Horner order, every step one FFMA per half)
+__device__ __forceinline__ float2 chebyshev_sine2(float2 x) {
+    const float2 z = __fmul2_rn(x, x);
+    float2 b = bc2(3.20396066f);
+    b = __ffma2_rn(b, z, bc2(-14.07150173f));
+    b = __ffma2_rn(b, z, bc2(38.50016403f));
+    b = __ffma2_rn(b, z, bc2(-67.07687378f));
+    b = __ffma2_rn(b, z, bc2(64.83583069f));
+    b = __ffma2_rn(b, z, bc2(-25.13274193f));
+    return __fmul2_rn(__fmul2_rn(b, __fadd2_rn(z, bc2(-0.25f))), x);
+}
+
+// R consecutive outputs of a decimate-by-M 128-tap FIR over a skewed plane of pairs (M = 4: R = 8,
+// M = 8: R = 4).  Output r, tap quad pq reads sample quad (s0/4) + (M/4)*r + pq.  The register window is a
+// ring of 8 quads indexed modulo 8; the tap loop is unrolled by 8, so every ring index is static (the
+// window is renamed, never moved) while the code stays small enough for the instruction cache (the fully
+// unrolled version stalled on instruction fetch, ncu no_instruction 1.5).  Step pq's new quad, pq + 8,
+// goes into the slot of quad pq right after its last use.  taps2[k] = (b[k], b[k]).  Sum order: taps
+// ascending, as the scalar reference.
 template <int M, int R>
-__device__ __forceinline__ void fir128(const float* __restrict__ sig, const float* __restrict__ taps, int q0, float (&acc)[R])
+__device__ __forceinline__ void fir128(const float2* __restrict__ sig, const float2* __restrict__ taps2, int s0, float2 (&acc)[R])
 {
     constexpr int QS = M / 4;
-    constexpr int W = QS * (R - 1) + 1;
-    float4 win[W];
+    static_assert(QS * (R - 1) + 1 <= 8, "window must fit the ring");
+    float4 win[8][2];
 #pragma unroll
-    for (int j = 0; j < W; j++) win[j] = *(const float4*)(sig + a4q(q0 + j));
+    for (int j = 0; j < 8; j++) {
+        win[j][0] = *(const float4*)(sig + a4(s0 + 4 * j));
+        win[j][1] = *(const float4*)(sig + a4(s0 + 4 * j + 2));
+    }
 #pragma unroll
-    for (int r = 0; r < R; r++) acc[r] = 0.0f;
+    for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int pb = 0; pb < 32; pb += 8) {
 #pragma unroll
         for (int pp = 0; pp < 8; pp++) {
             const int pq = pb + pp;
-            const float4 b = *(const float4*)(taps + 4 * pq);
+            const float4 b01 = *(const float4*)(taps2 + 4 * pq);      // (b0, b0, b1, b1)
+            const float4 b23 = *(const float4*)(taps2 + 4 * pq + 2);
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = dot4(win[QS * r], b, acc[r]);
-#pragma unroll
-            for (int j = 0; j < W - 1; j++) win[j] = win[j + 1];
-            win[W - 1] = *(const float4*)(sig + a4q(q0 + W + pq));   // may read <= 1 quad past the data: padded
+            for (int r = 0; r < R; r++) {
+                const float4 x01 = win[(pp + QS * r) & 7][0], x23 = win[(pp + QS * r) & 7][1];
+                acc[r] = __ffma2_rn(make_float2(x01.x, x01.y), make_float2(b01.x, b01.y), acc[r]);
+                acc[r] = __ffma2_rn(make_float2(x01.z, x01.w), make_float2(b01.z, b01.w), acc[r]);
+                acc[r] = __ffma2_rn(make_float2(x23.x, x23.y), make_float2(b23.x, b23.y), acc[r]);
+                acc[r] = __ffma2_rn(make_float2(x23.z, x23.w), make_float2(b23.z, b23.w), acc[r]);
+                if (r == 0) {   // quad pq is dead now: its slot takes quad pq + 8 (<= 1 quad past the data at the very end: padded)
+                    win[pp][0] = *(const float4*)(sig + a4(s0 + 4 * (pq + 8)));
+                    win[pp][1] = *(const float4*)(sig + a4(s0 + 4 * (pq + 8) + 2));
+                }
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(K4_THREADS)
+__global__ void __launch_bounds__(K4_THREADS, 4)
 k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_dt,
            const float* __restrict__ hist_x_in, const float2* __restrict__ hist_m2_in, const float2* __restrict__ hist_m3_in,
            float* __restrict__ hist_x_out, float2* __restrict__ hist_m2_out, float2* __restrict__ hist_m3_out,
@@ -69,126 +119,197 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
            float* __restrict__ est_partial, float* __restrict__ rds_power_partial,
            float* __restrict__ dbg_lpr, float* __restrict__ dbg_lmr, const __grid_constant__ K4Params p)
 {
-    __shared__ __align__(16) float s_sig[5][K4_PLEN + 8];       // xr, m2r, m2i, m3r, m3i
-    __shared__ __align__(16) float s_taps[3][K4_NN];
-    __shared__ __align__(16) float s_res[3][K4_TS / 4];         // lpr, lmr_re, lmr_im
-    __shared__ float s_est[K4_THREADS];
+    extern __shared__ __align__(16) float2 smem4[];
+    float2* s_sig = smem4;                                      // [5][K4_PLEN]: xr, m2r, m2i, m3r, m3i
+    float2* s_taps = smem4 + 5 * K4_PLEN;                       // [3][K4_NN] duplicated taps: lpr, lmr, rds
+    float2* s_res = smem4;                                      // epilogue arrays (aliased, see K4_RES_*)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int tile = blockIdx.x, s = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int sA = 2 * blockIdx.y;
+    const bool hasB = sA + 1 < p.n_streams;
+    const int sB = hasB ? sA + 1 : sA;
     const int n0 = tile * K4_TS;
     const int nts = min(K4_TS, p.n - n0);                       // multiple of 128
 
     for (int k = t; k < K4_NN; k += K4_THREADS) {
-        s_taps[0][k] = p.taps_lpr[k]; s_taps[1][k] = p.taps_lmr[k]; s_taps[2][k] = p.taps_rds[k];
+        s_taps[k] = bc2(p.taps_lpr[k]); s_taps[K4_NN + k] = bc2(p.taps_lmr[k]); s_taps[2 * K4_NN + k] = bc2(p.taps_rds[k]);
     }
     if (t < 8) {
 #pragma unroll
-        for (int a = 0; a < 5; a++) s_sig[a][K4_PLEN + t] = 0.0f;   // the quad the window may over-read
+        for (int a = 0; a < 5; a++) s_sig[a * K4_PLEN + K4_PLEN - 8 + t] = make_float2(0.0f, 0.0f);   // the quad a window may over-read
     }
     // ---- stage + mix: sample idx of the staged array <-> MPX sample n0 - 128 + idx ----
-    const float off2 = lmr_phase[s];
-    for (int idx = t; idx < K4_NN + nts; idx += K4_THREADS) {
-        float xr, m2r, m2i, m3r, m3i;
+    const float2 off2 = make_float2(lmr_phase[sA], lmr_phase[sB]);
+    const float2* xA = fm_out_iq + (size_t)sA * p.n, * xB = fm_out_iq + (size_t)sB * p.n;
+    const float* dA = pll_dt + (size_t)sA * p.n, * dB = pll_dt + (size_t)sB * p.n;
+    constexpr int NIT = (K4_LEN + K4_THREADS - 1) / K4_THREADS;   // 9
+    float2 vxa[NIT], vxb[NIT], vdt[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {                          // every global load first
+        const int idx = t + it * K4_THREADS;
         const int n = n0 - K4_NN + idx;
-        if (n < 0) {
-            xr = hist_x_in[(size_t)s * K4_NN + idx];
-            const float2 h2 = hist_m2_in[(size_t)s * K4_NN + idx];
-            const float2 h3 = hist_m3_in[(size_t)s * K4_NN + idx];
-            m2r = h2.x; m2i = h2.y; m3r = h3.x; m3i = h3.y;
+        if (idx < K4_NN + nts && n >= 0) {
+            vxa[it] = __ldg(xA + n); vxb[it] = __ldg(xB + n);
+            vdt[it] = make_float2(__ldg(dA + n), __ldg(dB + n));
+        } else { vxa[it] = vxb[it] = vdt[it] = make_float2(0.0f, 0.0f); }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int idx = t + it * K4_THREADS;
+        const int n = n0 - K4_NN + idx;
+        if (idx >= K4_NN + nts) continue;
+        float2 xr, m2r, m2i, m3r, m3i;
+        if (n < 0) {                                            // tile 0: the halo is the carried history
+            xr = make_float2(hist_x_in[(size_t)sA * K4_NN + idx], hist_x_in[(size_t)sB * K4_NN + idx]);
+            const float2 h2a = hist_m2_in[(size_t)sA * K4_NN + idx], h2b = hist_m2_in[(size_t)sB * K4_NN + idx];
+            const float2 h3a = hist_m3_in[(size_t)sA * K4_NN + idx], h3b = hist_m3_in[(size_t)sB * K4_NN + idx];
+            m2r = make_float2(h2a.x, h2b.x); m2i = make_float2(h2a.y, h2b.y);
+            m3r = make_float2(h3a.x, h3b.x); m3i = make_float2(h3a.y, h3b.y);
         } else {
-            const float2 x = fm_out_iq[(size_t)s * p.n + n];
-            const float dt = pll_dt[(size_t)s * p.n + n];
-            xr = x.x;
-            {   // apply_harmonic_pll.cpp:16-23 with round-to-nearest-even as the AVX path (:129)
-                float ds = fmaf(dt, p.harmonic_lmr, off2);
-                float dc = ds + 0.25f;
-                ds = ds - rintf(ds); dc = dc - rintf(dc);
-                const float c = chebyshev_sine(dc), sn = chebyshev_sine(ds);
-                m2r = x.x * c - x.y * sn; m2i = x.x * sn + x.y * c;
+            xr = make_float2(vxa[it].x, vxb[it].x);
+            const float2 xi = make_float2(vxa[it].y, vxb[it].y);
+            {   // apply_harmonic_pll.cpp:16-23: y = x * (S(phi + 1/4 wrapped), S(phi wrapped)), phi = dt*h + off
+                const float2 ph = __ffma2_rn(vdt[it], bc2(p.harmonic_lmr), off2);
+                const float2 c = chebyshev_sine2(wrap2(__fadd2_rn(ph, bc2(0.25f)))), sn = chebyshev_sine2(wrap2(ph));
+                m2r = __ffma2_rn(xr, c, neg2(__fmul2_rn(xi, sn))); m2i = __ffma2_rn(xr, sn, __fmul2_rn(xi, c));
             }
             {
-                float ds = dt * p.harmonic_rds;
-                float dc = ds + 0.25f;
-                ds = ds - rintf(ds); dc = dc - rintf(dc);
-                const float c = chebyshev_sine(dc), sn = chebyshev_sine(ds);
-                m3r = x.x * c - x.y * sn; m3i = x.x * sn + x.y * c;
+                const float2 ph = __fmul2_rn(vdt[it], bc2(p.harmonic_rds));
+                const float2 c = chebyshev_sine2(wrap2(__fadd2_rn(ph, bc2(0.25f)))), sn = chebyshev_sine2(wrap2(ph));
+                m3r = __ffma2_rn(xr, c, neg2(__fmul2_rn(xi, sn))); m3i = __ffma2_rn(xr, sn, __fmul2_rn(xi, c));
             }
         }
         const int a = a4(idx);
-        s_sig[0][a] = xr; s_sig[1][a] = m2r; s_sig[2][a] = m2i; s_sig[3][a] = m3r; s_sig[4][a] = m3i;
+        s_sig[a] = xr; s_sig[K4_PLEN + a] = m2r; s_sig[2 * K4_PLEN + a] = m2i; s_sig[3 * K4_PLEN + a] = m3r; s_sig[4 * K4_PLEN + a] = m3i;
     }
     __syncthreads();
 
-    // ---- history for the next block: the last 128 staged samples of the stream's last tile ----
-    if (n0 + nts == p.n) {
-        const int a = a4(nts + t);                               // K4_THREADS == K4_NN
-        hist_x_out[(size_t)s * K4_NN + t] = s_sig[0][a];
-        hist_m2_out[(size_t)s * K4_NN + t] = make_float2(s_sig[1][a], s_sig[2][a]);
-        hist_m3_out[(size_t)s * K4_NN + t] = make_float2(s_sig[3][a], s_sig[4][a]);
+    // ---- history for the next block: the last 128 staged samples of the streams' last tile ----
+    if (n0 + nts == p.n) for (int i = t; i < K4_NN; i += K4_THREADS) {
+        const int a = a4(nts + i);
+        const float2 x = s_sig[a], r2 = s_sig[K4_PLEN + a], i2 = s_sig[2 * K4_PLEN + a], r3 = s_sig[3 * K4_PLEN + a], i3 = s_sig[4 * K4_PLEN + a];
+        hist_x_out[(size_t)sA * K4_NN + i] = x.x;
+        hist_m2_out[(size_t)sA * K4_NN + i] = make_float2(r2.x, i2.x);
+        hist_m3_out[(size_t)sA * K4_NN + i] = make_float2(r3.x, i3.x);
+        if (hasB) {
+            hist_x_out[(size_t)sB * K4_NN + i] = x.y;
+            hist_m2_out[(size_t)sB * K4_NN + i] = make_float2(r2.y, i2.y);
+            hist_m3_out[(size_t)sB * K4_NN + i] = make_float2(r3.y, i3.y);
+        }
     }
 
+    // ---- the FIR roles; results stay in registers until every warp has finished with the planes ----
     const int n_audio = nts >> 2, n_rds = nts >> 3;
-    float rds_pw = 0.0f;
-    if (warp < 3) {
-        // /4 FIR: output o = 8*lane + r reads staged samples 4o+4+k, i.e. quads o+1+pq
-        if (8 * lane < n_audio) {
-            float acc[8];
-            fir128<4, 8>(s_sig[warp], s_taps[warp == 0 ? 0 : 1], 8 * lane + 1, acc);
-            float4* d = (float4*)(&s_res[warp][8 * lane]);
-            d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    const int gi0 = n0 >> 2;                                    // audio index of the tile's first output within the block
+    const int o_first = (10 - gi0 % 10) % 10;                   // first output of the tile the estimator reads
+    float2 acc8[8], sparse = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc8[r] = make_float2(0.0f, 0.0f);
+    if (warp < 2) {
+        // /4 FIR: output o = 8*lane + r reads staged samples 4o + 4 + k
+        if (8 * lane < n_audio)
+            fir128<4, 8>(s_sig + (warp == 0 ? 0 : 2 * K4_PLEN), s_taps + (warp == 0 ? 0 : K4_NN), 32 * lane + 4, acc8);
+        if (warp == 1) {
+            // real part of L-R where the estimator looks: output o_first + 10*lane, taps ascending
+            const int o = o_first + 10 * lane;
+            if (o < n_audio) {
+                const float2* sg = s_sig + K4_PLEN;
+                const float2* tp = s_taps + K4_NN;
+#pragma unroll 4
+                for (int q = 0; q < 32; q++) {
+                    const float4 x01 = *(const float4*)(sg + a4(4 * o + 4 + 4 * q)), x23 = *(const float4*)(sg + a4(4 * o + 4 + 4 * q + 2));
+                    const float4 b01 = *(const float4*)(tp + 4 * q), b23 = *(const float4*)(tp + 4 * q + 2);
+                    sparse = __ffma2_rn(make_float2(x01.x, x01.y), make_float2(b01.x, b01.y), sparse);
+                    sparse = __ffma2_rn(make_float2(x01.z, x01.w), make_float2(b01.z, b01.w), sparse);
+                    sparse = __ffma2_rn(make_float2(x23.x, x23.y), make_float2(b23.x, b23.y), sparse);
+                    sparse = __ffma2_rn(make_float2(x23.z, x23.w), make_float2(b23.z, b23.w), sparse);
+                }
+            }
         }
-    } else {
-        // /8 FIR: output o = 4*lane + r reads staged samples 8o+8+k, i.e. quads 2o+2+pq
+    } else if (warp == 2) {
+        // /8 FIR, real then imaginary plane: output o = 4*lane + r reads staged samples 8o + 8 + k.
+        // This warp owns its outputs completely: RDS samples and their AGC power partial leave from registers.
+        float2 pw = make_float2(0.0f, 0.0f);
         if (4 * lane < n_rds) {
-            float re[4], im[4];
-            fir128<8, 4>(s_sig[3], s_taps[2], 8 * lane + 2, re);
-            fir128<8, 4>(s_sig[4], s_taps[2], 8 * lane + 2, im);
-            float4* d = (float4*)(rds_out + (size_t)s * (p.n >> 3) + (n0 >> 3) + 4 * lane);
-            d[0] = make_float4(re[0], im[0], re[1], im[1]);
-            d[1] = make_float4(re[2], im[2], re[3], im[3]);
+            float2 re[4], im[4];
+            fir128<8, 4>(s_sig + 3 * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, re);
+            fir128<8, 4>(s_sig + 4 * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, im);
+            float4* dA4 = (float4*)(rds_out + (size_t)sA * (p.n >> 3) + (n0 >> 3) + 4 * lane);
+            dA4[0] = make_float4(re[0].x, im[0].x, re[1].x, im[1].x);
+            dA4[1] = make_float4(re[2].x, im[2].x, re[3].x, im[3].x);
+            if (hasB) {
+                float4* dB4 = (float4*)(rds_out + (size_t)sB * (p.n >> 3) + (n0 >> 3) + 4 * lane);
+                dB4[0] = make_float4(re[0].y, im[0].y, re[1].y, im[1].y);
+                dB4[1] = make_float4(re[2].y, im[2].y, re[3].y, im[3].y);
+            }
 #pragma unroll
-            for (int r = 0; r < 4; r++) rds_pw += re[r] * re[r] + im[r] * im[r];
+            for (int r = 0; r < 4; r++) pw = __fadd2_rn(pw, __ffma2_rn(re[r], re[r], __fmul2_rn(im[r], im[r])));
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) rds_pw += __shfl_xor_sync(0xffffffffu, rds_pw, off);
-        if (lane == 0) rds_power_partial[(size_t)s * p.n_tiles + tile] = rds_pw;
+        for (int off = 16; off > 0; off >>= 1) { pw.x += __shfl_xor_sync(0xffffffffu, pw.x, off); pw.y += __shfl_xor_sync(0xffffffffu, pw.y, off); }
+        if (lane == 0) {
+            rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
+            if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
+        }
+    }
+    __syncthreads();                                            // planes and taps are dead from here on
+    if (warp < 2) {
+        float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 8 * lane;
+#pragma unroll
+        for (int q = 0; q < 4; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
+        if (warp == 1) s_res[K4_RES_SPARSE + lane] = sparse;
     }
     __syncthreads();
 
     // ---- MixAudio (:549-585) + phase-estimator partial sum (:496-511), 2 outputs per thread ----
-    float est = 0.0f;
-    if (2 * t < n_audio) {
-        const int o = 2 * t;
-        const size_t gi = (size_t)(n0 >> 2) + o;                // audio index within the block
-        float4 fr;
-        float* f = &fr.x;
+    float2 est = make_float2(0.0f, 0.0f);
+    for (int it = t; 2 * it < n_audio; it += K4_THREADS) {
+        const int o = 2 * it;
+        const size_t gi = (size_t)gi0 + o;                      // audio index within the block
+        float4 frA, frB;
+        float* fA = &frA.x; float* fB = &frB.x;
+        float2 lprs[2], lmrs[2];
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const float lpr = s_res[0][o + j], lre = s_res[1][o + j], lmr = s_res[2][o + j];
-            float L, R;
-            if (p.audio_out_mode == 2) { L = fmaf(p.stereo_mix, lmr, lpr); R = fmaf(-p.stereo_mix, lmr, lpr); }
+            const float2 lpr = s_res[K4_RES_LPR + o + j], lmr = s_res[K4_RES_LMR + o + j];
+            lprs[j] = lpr; lmrs[j] = lmr;
+            float2 L, R;
+            if (p.audio_out_mode == 2) { L = __ffma2_rn(bc2(p.stereo_mix), lmr, lpr); R = __ffma2_rn(bc2(-p.stereo_mix), lmr, lpr); }
             else if (p.audio_out_mode == 1) { L = lmr; R = lmr; }
             else { L = lpr; R = lpr; }
-            f[2 * j] = L * 2.0f; f[2 * j + 1] = R * 2.0f;
+            fA[2 * j] = L.x * 2.0f; fA[2 * j + 1] = R.x * 2.0f;
+            fB[2 * j] = L.y * 2.0f; fB[2 * j + 1] = R.y * 2.0f;
             if ((gi + j) % 10 == 0) {
-                const float phase = atan2f(lmr, lre);
-                est += (phase > 0.0f) ? (PI_F / 2.0f - phase) : (-PI_F / 2.0f - phase);
+                const float2 lre = s_res[K4_RES_SPARSE + (o + j - o_first) / 10];
+                const float pa = atan2f(lmr.x, lre.x), pb = atan2f(lmr.y, lre.y);
+                est.x += (pa > 0.0f) ? (PI_F / 2.0f - pa) : (-PI_F / 2.0f - pa);
+                est.y += (pb > 0.0f) ? (PI_F / 2.0f - pb) : (-PI_F / 2.0f - pb);
             }
         }
-        *(float4*)(audio_out + (size_t)s * (p.n >> 2) + gi) = fr;
+        *(float4*)(audio_out + (size_t)sA * (p.n >> 2) + gi) = frA;
+        if (hasB) *(float4*)(audio_out + (size_t)sB * (p.n >> 2) + gi) = frB;
         if (p.keep) {
-            *(float2*)(dbg_lpr + (size_t)s * (p.n >> 2) + gi) = make_float2(s_res[0][o], s_res[0][o + 1]);
-            *(float2*)(dbg_lmr + (size_t)s * (p.n >> 2) + gi) = make_float2(s_res[2][o], s_res[2][o + 1]);
+            *(float2*)(dbg_lpr + (size_t)sA * (p.n >> 2) + gi) = make_float2(lprs[0].x, lprs[1].x);
+            *(float2*)(dbg_lmr + (size_t)sA * (p.n >> 2) + gi) = make_float2(lmrs[0].x, lmrs[1].x);
+            if (hasB) {
+                *(float2*)(dbg_lpr + (size_t)sB * (p.n >> 2) + gi) = make_float2(lprs[0].y, lprs[1].y);
+                *(float2*)(dbg_lmr + (size_t)sB * (p.n >> 2) + gi) = make_float2(lmrs[0].y, lmrs[1].y);
+            }
         }
     }
-    s_est[t] = est;
+    s_res[K4_RES_EST + t] = est;
     __syncthreads();
     if (warp == 0) {
-        float v = (s_est[4 * lane] + s_est[4 * lane + 1]) + (s_est[4 * lane + 2] + s_est[4 * lane + 3]);
+        constexpr int EPL = K4_THREADS / 32;                    // partial sums per lane
+        float2 v = s_res[K4_RES_EST + EPL * lane];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) est_partial[(size_t)s * p.n_tiles + tile] = v;
+        for (int q = 1; q < EPL; q++) { const float2 e = s_res[K4_RES_EST + EPL * lane + q]; v.x += e.x; v.y += e.y; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, off); v.y += __shfl_xor_sync(0xffffffffu, v.y, off); }
+        if (lane == 0) {
+            est_partial[(size_t)sA * p.n_tiles + tile] = v.x;
+            if (hasB) est_partial[(size_t)sB * p.n_tiles + tile] = v.y;
+        }
     }
 }
 
@@ -214,8 +335,14 @@ cudaError_t launch_k4(const float2* fm_out_iq, const float* pll_dt,
                       float* lmr_phase, float2* audio_out, float2* rds_out, float* est_partial,
                       float* rds_power_partial, float* dbg_lpr, float* dbg_lmr, const K4Params& p, cudaStream_t st)
 {
-    const dim3 grid(p.n_tiles, p.n_streams);
-    k4_mix_fir<<<grid, K4_THREADS, 0, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k4_mix_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const dim3 grid(p.n_tiles, (p.n_streams + 1) / 2);
+    k4_mix_fir<<<grid, K4_THREADS, K4_SMEM_BYTES, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,
                                             hist_x_out, hist_m2_out, hist_m3_out, lmr_phase, audio_out, rds_out,
                                             est_partial, rds_power_partial, dbg_lpr, dbg_lmr, p);
     cudaError_t e = cudaGetLastError();
