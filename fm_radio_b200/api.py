@@ -99,6 +99,18 @@ class _Config(C.Structure):
                 ("keep_intermediates", C.c_int), ("pipeline_depth", C.c_int)]
 
 
+class _ChanConfig(C.Structure):
+    _fields_ = [("fs_in_hz", C.c_double), ("decimation", C.c_int), ("n_taps", C.c_int), ("cutoff_k", C.c_float),
+                ("n_channels", C.c_int), ("block_out", C.c_int), ("device", C.c_int), ("mode", C.c_int),
+                ("ring_depth", C.c_int)]
+
+
+class ChanMode(enum.IntEnum):
+    AUTO = 0
+    TENSOR = 1
+    FP32 = 2
+
+
 class RDSGroup(C.Structure):
     _fields_ = [("data", C.c_uint16 * 4), ("valid", C.c_uint8 * 4), ("type", C.c_uint8 * 4)]
 
@@ -117,6 +129,10 @@ EXPORTED_SYMBOLS = [
     "fmgpu_rds_get_bytes", "fmgpu_rds_get_db", "fmgpu_last_error", "fmgpu_version",
     "fmgpu_rds_device_fetch", "fmgpu_rds_device_counts", "fmgpu_rds_device_get_groups",
     "fmgpu_rds_device_get_bytes", "fmgpu_rds_device_get_db", "fmgpu_get_partition",
+    "fmgpu_enqueue_cf32_device", "fmgpu_stream_wait_input_free",
+    "fmgpu_chan_create", "fmgpu_chan_destroy", "fmgpu_chan_get_b", "fmgpu_chan_get_config", "fmgpu_chan_get_freqs",
+    "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
+    "fmgpu_chan_wait_external_stream", "fmgpu_chan_sync", "fmgpu_chan_stream", "fmgpu_chan_launch_count",
 ]
 
 _lib = None
@@ -190,6 +206,24 @@ def lib():
     L.fmgpu_rds_device_get_groups.argtypes = [vp, ci, C.c_ulonglong, C.POINTER(RDSGroup), ci]
     L.fmgpu_rds_device_get_bytes.argtypes = [vp, ci, C.c_ulonglong, vp, ci]
     L.fmgpu_rds_device_get_db.argtypes = [vp, ci, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
+    L.fmgpu_enqueue_cf32_device.argtypes = [vp, vp, vp]
+    L.fmgpu_stream_wait_input_free.argtypes = [vp, vp]
+    L.fmgpu_chan_create.argtypes = [C.POINTER(_ChanConfig), C.POINTER(C.c_double), C.POINTER(vp)]
+    L.fmgpu_chan_destroy.argtypes = [vp]
+    L.fmgpu_chan_destroy.restype = None
+    L.fmgpu_chan_get_b.argtypes = [vp]
+    L.fmgpu_chan_get_b.restype = C.POINTER(C.c_float)
+    L.fmgpu_chan_get_config.argtypes = [vp, C.POINTER(_ChanConfig)]
+    L.fmgpu_chan_get_freqs.argtypes = [vp, vp, vp]
+    L.fmgpu_chan_process_u8.argtypes = [vp, vp, cs, vp]
+    L.fmgpu_chan_enqueue_u8_device.argtypes = [vp, vp, C.POINTER(vp)]
+    L.fmgpu_chan_feed_device.argtypes = [vp, vp, vp]
+    L.fmgpu_chan_wait_external_stream.argtypes = [vp, vp]
+    L.fmgpu_chan_sync.argtypes = [vp]
+    L.fmgpu_chan_stream.argtypes = [vp]
+    L.fmgpu_chan_stream.restype = vp
+    L.fmgpu_chan_launch_count.argtypes = [vp]
+    L.fmgpu_chan_launch_count.restype = C.c_longlong
     L.fmgpu_last_error.restype = C.c_char_p
     L.fmgpu_version.restype = C.c_char_p
     _lib = L
@@ -273,6 +307,13 @@ class FMDemod:
     def enqueue_u8_host(self, iq_host) -> int:
         slot = self.blocks_enqueued % self.depth
         _check(self.L.fmgpu_enqueue_u8_host(self.h, _ptr(iq_host)), "fmgpu_enqueue_u8_host")
+        self.blocks_enqueued += 1
+        return slot
+
+    def enqueue_cf32_device(self, iq_dev, after_stream: int = 0) -> int:
+        """Queues one block of complex64 [n_streams, block_size] device input (the channelizer's output)."""
+        slot = self.blocks_enqueued % self.depth
+        _check(self.L.fmgpu_enqueue_cf32_device(self.h, _ptr(iq_dev), after_stream or None), "fmgpu_enqueue_cf32_device")
         self.blocks_enqueued += 1
         return slot
 
@@ -392,6 +433,86 @@ class FMDemod:
         ps, rt = C.create_string_buffer(8), C.create_string_buffer(64)
         _check(self.L.fmgpu_rds_device_get_db(self.h, stream, C.byref(pi), ps, rt, C.byref(pty)), "fmgpu_rds_device_get_db")
         return {"pi": pi.value, "pty": pty.value, "ps": ps.raw, "rt": rt.raw}
+
+
+class Channelizer:
+    """Wideband channelizer (include/fmgpu.h, fmgpu_chan_*): one u8 IQ capture at `fs_in_hz` ->
+    len(centres_hz) complex channels at fs_in_hz / decimation, laid out as the cf32 input of an
+    FMDemod(block_out, n_channels).  New component (the reference has none)."""
+
+    def __init__(self, fs_in_hz: float, centres_hz, decimation: int = 20, n_taps: int = 192, block_out: int = 65536,
+                 device: int = -1, mode: ChanMode = ChanMode.AUTO, ring_depth: int = 0, cutoff_k: float = 0.0):
+        self.L = lib()
+        centres = np.ascontiguousarray(centres_hz, np.float64)
+        cfg = _ChanConfig(float(fs_in_hz), decimation, n_taps, float(cutoff_k), centres.size, block_out, device, int(mode), ring_depth)
+        h = C.c_void_p()
+        _check(self.L.fmgpu_chan_create(C.byref(cfg), centres.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h)), "fmgpu_chan_create")
+        self.h = h
+        out = _ChanConfig()
+        self.L.fmgpu_chan_get_config(self.h, C.byref(out))
+        self.fs_in_hz, self.decimation, self.n_taps = out.fs_in_hz, out.decimation, out.n_taps
+        self.n_channels, self.block_out, self.mode, self.depth = out.n_channels, out.block_out, ChanMode(out.mode), out.ring_depth
+        self.block_in = self.block_out * self.decimation
+        self.blocks = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fmgpu_chan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_b(self) -> np.ndarray:
+        """The prototype taps (reference order); writes take effect at the next block."""
+        return np.ctypeslib.as_array(self.L.fmgpu_chan_get_b(self.h), shape=(self.n_taps,))
+
+    def freqs(self):
+        """(quantised centre frequencies in Hz, phase increments per input sample in turns * 2^32)."""
+        hz = np.zeros(self.n_channels, np.float64)
+        inc = np.zeros(self.n_channels, np.uint32)
+        _check(self.L.fmgpu_chan_get_freqs(self.h, hz.ctypes.data, inc.ctypes.data), "fmgpu_chan_get_freqs")
+        return hz, inc
+
+    def process_u8(self, iq) -> np.ndarray:
+        """iq: uint8 [2 * block_in] host array -> complex64 [n_channels, block_out]."""
+        iq = np.ascontiguousarray(iq, np.uint8)
+        out = np.zeros((self.n_channels, self.block_out), np.complex64)
+        _check(self.L.fmgpu_chan_process_u8(self.h, iq.ctypes.data, iq.size // 2, out.ctypes.data), "fmgpu_chan_process_u8")
+        self.blocks += 1
+        return out
+
+    def enqueue_u8_device(self, iq_dev) -> int:
+        """Asynchronous; returns the device address of the [n_channels, block_out] complex64 output."""
+        p = C.c_void_p()
+        _check(self.L.fmgpu_chan_enqueue_u8_device(self.h, _ptr(iq_dev), C.byref(p)), "fmgpu_chan_enqueue_u8_device")
+        self.blocks += 1
+        return p.value
+
+    def feed(self, demod: "FMDemod", iq_dev) -> int:
+        """One wideband block through the channelizer and `demod` (asynchronous); returns demod's ring slot."""
+        slot = demod.blocks_enqueued % demod.depth
+        _check(self.L.fmgpu_chan_feed_device(self.h, demod.h, _ptr(iq_dev)), "fmgpu_chan_feed_device")
+        self.blocks += 1
+        demod.blocks_enqueued += 1
+        return slot
+
+    def wait_external_stream(self, cuda_stream: int) -> None:
+        _check(self.L.fmgpu_chan_wait_external_stream(self.h, cuda_stream), "fmgpu_chan_wait_external_stream")
+
+    def sync(self) -> None:
+        _check(self.L.fmgpu_chan_sync(self.h), "fmgpu_chan_sync")
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.fmgpu_chan_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.fmgpu_chan_launch_count(self.h))
 
 
 class RDSDecoder:

@@ -1,0 +1,585 @@
+// Wideband channelizer (BASELINE config 4): one wideband u8 IQ capture -> C narrow-band complex
+// channels at Fs/D, each feeding one demodulator stream of the chain in fmgpu.cu.
+//
+// The reference has no channelizer (SURVEY.md section 7 "No channelizer in the reference", section
+// 8(f) rank 2; the reference's own TODO on a configurable front end is broadcast_fm_demod.cpp:67).
+// The definition implemented here -- and restated in float64 by the checker, oracle/fm_oracle.c
+// fmo_channelize_f64 -- keeps the reference's conventions on either side of it:
+//   unpack    x[n] = (float)u8 - 127                                       app.cpp:56-65
+//   shift     xs[n] = x[n] * exp(-j 2 pi ph_c(n) / 2^32), ph_c(n) = inc_c * n mod 2^32
+//   decimate  y_c[i] = sum_{k<NN} b[k] * xs[(i+1) D - NN + k]              dsp/polyphase_filter.h:41-64
+//   taps      b = create_fir_lpf(NN, k) in ReverseArray order              dsp/filter_designer.cpp:84-107
+//
+// Because exp(-j ph(n - d)) = exp(-j ph(n)) exp(+j ph(d)), the shift moves into the taps:
+//   y_c[i] = exp(-j ph_c(n_i)) * sum_k g_c[k] x[n_i - (NN-1-k)],   g_c[k] = b[k] exp(+j ph_c(NN-1-k)),
+// n_i = the newest sample of output i.  For all channels at once that sum is a DENSE CONTRACTION
+//   Y[i, (c, re|im)] = sum_{K < 2 NN} X[i, K] * G[K, (c, re|im)],  X[i, K] = byte K of the window of output i
+// (rows of X are overlapping 2*NN-byte windows of the raw capture, 2*D bytes apart), which is the one
+// place of this path where the north star allows tensor cores.  Two kernels:
+//
+//   chan_mma_i8    tcgen05.mma kind::i8 (sm_100a): X is the RAW u8 capture (unsigned 8-bit A operand,
+//                  no unpack pass), G is split into three balanced signed base-256 digit planes
+//                  (24-bit fixed point, as exact as the fp32 taps), accumulators are int32 in TMEM, so the
+//                  contraction is EXACT integer arithmetic; the -127 offset is removed as an integer
+//                  constant per column, the three planes are recombined in fp32 and the result is rotated
+//                  by exp(-j ph_c(n_i)) in the epilogue.
+//   chan_fir_fp32  the same sum on the FP32 FMA pipe (one lane per channel, taps in shared memory).
+//                  Kept as the measured alternative and as an on-device cross-check of the MMA path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/fmgpu.h"
+
+extern "C" int fmgpu_set_last_error_(int code, const char* msg);            // fmgpu.cu
+
+namespace {
+
+#define CHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    return fmgpu_set_last_error_(FMGPU_ERR_CUDA, (std::string(#call) + ": " + cudaGetErrorString(e_)).c_str()); } } while (0)
+
+constexpr int CH_ROWS = 128;            // output times per MMA tile (= TMEM lanes)
+constexpr int CH_SLOTS = 32;            // channel slots per group
+constexpr int CH_NG = 2 * CH_SLOTS;     // accumulator columns per digit plane (re, im per slot)
+constexpr int CH_PLANES = 3;
+constexpr int CH_KCHUNK = 128;          // bytes of K per staged chunk = one 128-byte swizzle row
+constexpr int CH_A_BYTES = CH_ROWS * CH_KCHUNK;                 // 16 KB
+constexpr int CH_BSUB_BYTES = CH_NG * CH_KCHUNK;                // 8 KB: one (chunk, plane) sub-tile of G
+constexpr int CH_TMEM_COLS = 256;       // 3 x 64 used
+
+struct ChanMmaParams {
+    const uint8_t* iq;          // staged capture: history ++ block; window of output i starts at byte i * row_bytes
+    const int8_t* bimg;         // [group][chunk][plane][8 KB]: G digit planes in the shared-memory (swizzled) image
+    const int* offs;            // [group][plane][64]: 127 * column sums of the digit planes
+    const uint4* meta;          // [group][32]: { inc, inc * D, output channel or 0xffffffff, 0 }
+    float2* out;                // [C][n_out]
+    uint32_t n_newest0;         // (absolute index of the newest sample of output 0) mod 2^32
+    int n_out, row_bytes, n_kchunks, n_tiles;
+    float w0, w1, w2;           // weights of the digit planes
+};
+
+// ---------------------------------------------------------------- PTX wrappers (sm_100a) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// bounded spin: a broken pipeline traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 28); it++) {
+        uint32_t ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::i8, int32 accumulate
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (start address >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 >> 4 in [32,46),
+// descriptor version 1 in [46,48), layout type 2 = SWIZZLE_128B in [61,64))
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::i8: D = s32 (c_format 2, bits [4,6)), A = unsigned 8-bit (0, bits [7,10)),
+// B = signed 8-bit (1, bits [10,13)), both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t CH_IDESC = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(CH_NG >> 3) << 17) | ((uint32_t)(CH_ROWS >> 4) << 24);
+
+// ---------------------------------------------------------------- tensor-core kernel -------------
+// grid (ctas_per_group, n_groups), 128 threads, persistent over the time tiles of its group; two CTAs per SM
+// (104 KB of shared memory and 256 TMEM columns each) so that one CTA's epilogue overlaps the other's MMAs.
+__global__ void __launch_bounds__(128)
+chan_mma_i8(const __grid_constant__ ChanMmaParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms need 1024-byte alignment
+    uint8_t* sB = smem;                                              // n_kchunks x 3 x 8 KB, resident
+    uint8_t* sA = sB + (size_t)p.n_kchunks * CH_PLANES * CH_BSUB_BYTES;   // 2 x 16 KB ring
+    __shared__ __align__(8) uint64_t bar_free[2];                    // MMAs that read ring buffer b have completed
+    __shared__ __align__(8) uint64_t bar_acc;                        // the tile's accumulators are complete
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_off[CH_PLANES * CH_NG];
+    __shared__ uint4 s_meta[CH_SLOTS];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int group = blockIdx.y;
+
+    {   // G of this group: a linear copy, the image is already swizzled
+        const uint4* src = (const uint4*)(p.bimg + (size_t)group * p.n_kchunks * CH_PLANES * CH_BSUB_BYTES);
+        const int n16 = p.n_kchunks * CH_PLANES * CH_BSUB_BYTES / 16;
+        for (int i = tid; i < n16; i += 128) ((uint4*)sB)[i] = __ldg(src + i);
+    }
+    for (int i = tid; i < CH_PLANES * CH_NG; i += 128) s_off[i] = p.offs[(size_t)group * CH_PLANES * CH_NG + i];
+    if (tid < CH_SLOTS) s_meta[tid] = p.meta[(size_t)group * CH_SLOTS + tid];
+    if (tid == 0) {
+        mbar_init(&bar_free[0], 1); mbar_init(&bar_free[1], 1); mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(CH_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();                   // sB was written through the generic proxy, the MMA reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    int n_valid = 0;
+    for (int s = 0; s < CH_SLOTS; s++) if (s_meta[s].z != 0xffffffffu) n_valid = s + 1;
+
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const int row8 = tid & 7;
+    uint8_t* a_row = sA + (tid >> 3) * 1024 + row8 * 128;            // this thread's row in ring buffer 0
+    uint32_t chunk = 0, acc_parity = 0;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint8_t* src_row = p.iq + (size_t)(tile * CH_ROWS + tid) * p.row_bytes;
+        for (int kc = 0; kc < p.n_kchunks; kc++, chunk++) {
+            const uint32_t buf = chunk & 1u, use = chunk >> 1;
+            if (use > 0) mbar_wait(&bar_free[buf], (use - 1) & 1u);
+            // ---- im2col: 128 bytes of this thread's window -> its (swizzled) row of the ring buffer ----
+            const uint2* s8 = (const uint2*)(src_row + kc * CH_KCHUNK);          // 8-byte aligned (row_bytes % 8 == 0)
+            uint8_t* dst = a_row + buf * CH_A_BYTES;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint2 lo = __ldg(s8 + 2 * u), hi = __ldg(s8 + 2 * u + 1);
+                *(uint4*)(dst + ((u ^ row8) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_base = sA_addr + buf * CH_A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < CH_KCHUNK / 32; ks++) {                    // K = 32 per tcgen05.mma kind::i8
+                    const uint64_t a_desc = smem_desc_sw128(a_base + ks * 32);
+#pragma unroll
+                    for (int j = 0; j < CH_PLANES; j++) {
+                        const uint64_t b_desc = smem_desc_sw128(sB_addr + (kc * CH_PLANES + j) * CH_BSUB_BYTES + ks * 32);
+                        tc_mma_i8(tmem + j * CH_NG, a_desc, b_desc, CH_IDESC, (kc | ks) != 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(&bar_free[buf]);
+                if (kc == p.n_kchunks - 1) tc_commit(&bar_acc);
+            }
+        }
+        mbar_wait(&bar_acc, acc_parity);
+        acc_parity ^= 1u;
+        tc_fence_after();
+
+        // ---- epilogue: TMEM lane tid = output time i; 8 channel slots (16 columns) per step ----
+        const int i_out = tile * CH_ROWS + tid;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int q = 0; q * 8 < n_valid; q++) {
+            uint32_t a0[16], a1[16], a2[16];
+            tmem_ld16(lane_addr + 0 * CH_NG + q * 16, a0);
+            tmem_ld16(lane_addr + 1 * CH_NG + q * 16, a1);
+            tmem_ld16(lane_addr + 2 * CH_NG + q * 16, a2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const int slot = q * 8 + s;
+                const uint4 m = s_meta[slot];
+                if (m.z == 0xffffffffu) continue;
+                const int c0 = 2 * slot, c1 = 2 * slot + 1;
+                const float r0 = (float)((int)a0[2 * s] - s_off[c0]), r1 = (float)((int)a1[2 * s] - s_off[CH_NG + c0]),
+                            r2 = (float)((int)a2[2 * s] - s_off[2 * CH_NG + c0]);
+                const float q0 = (float)((int)a0[2 * s + 1] - s_off[c1]), q1 = (float)((int)a1[2 * s + 1] - s_off[CH_NG + c1]),
+                            q2 = (float)((int)a2[2 * s + 1] - s_off[2 * CH_NG + c1]);
+                const float re = fmaf(r0, p.w0, fmaf(r1, p.w1, r2 * p.w2));
+                const float im = fmaf(q0, p.w0, fmaf(q1, p.w1, q2 * p.w2));
+                const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)i_out;            // exact mod 2^32
+                float sn, cs;
+                sincospif((float)(int)ph * 4.656612873077393e-10f, &sn, &cs);             // turns * 2 -> pi units
+                p.out[(size_t)m.z * p.n_out + i_out] = make_float2(fmaf(re, cs, im * sn), fmaf(im, cs, -re * sn));
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                  // every lane has drained its accumulators before the next tile overwrites them
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(CH_TMEM_COLS) : "memory");
+}
+
+// ---------------------------------------------------------------- FP32 FMA-pipe kernel -----------
+// grid (n_out / 32, ceil(C / 32)), 128 threads: lane = channel, each warp owns 8 consecutive outputs.
+constexpr int CF_R = 8, CF_TILE = 4 * CF_R;
+struct ChanFp32Params {
+    const uint8_t* iq; const float2* g;      // g: [NN][c_pad] tap-major
+    const uint2* meta;                       // [C]: { inc, inc * D }
+    float2* out; uint32_t n_newest0; int n_out, D, NN, C, c_pad;
+};
+
+__global__ void __launch_bounds__(128)
+chan_fir_fp32(const __grid_constant__ ChanFp32Params p)
+{
+    extern __shared__ float2 s_x[];                                  // CF_TILE * D + NN - D samples
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * CF_TILE;
+    const int n_stage = CF_TILE * p.D + p.NN - p.D;
+    const uint8_t* src = p.iq + (size_t)i0 * p.D * 2;
+    for (int j = tid; j < n_stage; j += 128) s_x[j] = make_float2((float)src[2 * j] - 127.0f, (float)src[2 * j + 1] - 127.0f);
+    __syncthreads();
+    const int c = blockIdx.y * 32 + lane;
+    if (c >= p.C) return;
+    float ar[CF_R], ai[CF_R];
+#pragma unroll
+    for (int r = 0; r < CF_R; r++) { ar[r] = 0.0f; ai[r] = 0.0f; }
+    const float2* gp = p.g + c;
+    const float2* xw = s_x + warp * CF_R * p.D;
+    for (int k = 0; k < p.NN; k++) {
+        const float2 g = gp[(size_t)k * p.c_pad];
+#pragma unroll
+        for (int r = 0; r < CF_R; r++) {
+            const float2 x = xw[r * p.D + k];
+            ar[r] = fmaf(g.x, x.x, ar[r]); ar[r] = fmaf(-g.y, x.y, ar[r]);
+            ai[r] = fmaf(g.y, x.x, ai[r]); ai[r] = fmaf(g.x, x.y, ai[r]);
+        }
+    }
+    const uint2 m = p.meta[c];
+#pragma unroll
+    for (int r = 0; r < CF_R; r++) {
+        const int i_out = i0 + warp * CF_R + r;
+        const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)i_out;
+        float sn, cs;
+        sincospif((float)(int)ph * 4.656612873077393e-10f, &sn, &cs);
+        p.out[(size_t)c * p.n_out + i_out] = make_float2(fmaf(ar[r], cs, ai[r] * sn), fmaf(ai[r], cs, -ar[r] * sn));
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- C-ABI object -------------------
+struct fmgpu_chan {
+    fmgpu_chan_config cfg{};
+    int C = 0, D = 0, NN = 0, n_out = 0, depth = 0, device = 0, mode = 0;
+    int n_groups = 0, per_group = 0, n_kchunks = 0, c_pad = 0;
+    size_t hist_bytes = 0, in_bytes = 0;
+    std::vector<float> b;                    // prototype taps (get_b)
+    std::vector<double> fc;                  // requested centres
+    std::vector<uint32_t> inc;               // quantised: f = inc * Fs / 2^32
+    bool taps_dirty = true;
+    unsigned long long n_abs = 0;            // absolute index of the next block's first sample
+    unsigned long long step = 0;
+    long long launches = 0;
+    cudaStream_t st = nullptr;
+    uint8_t* d_stage = nullptr;
+    std::vector<float2*> d_out;
+    std::vector<cudaEvent_t> ev_done;
+    float2* d_g = nullptr; uint2* d_meta32 = nullptr;
+    int8_t* d_bimg = nullptr; int* d_offs = nullptr; uint4* d_meta = nullptr;
+    float w0 = 0, w1 = 0, w2 = 0;
+    float2* h_out = nullptr;                 // pinned mirror for the host entry point
+};
+
+namespace {
+
+int chan_upload_taps(fmgpu_chan* h) {
+    const int C = h->C, NN = h->NN;
+    const double TWO_PI = 6.283185307179586476925286766559;
+    // g_c[k] = b[k] * exp(+j 2 pi (inc_c (NN-1-k) mod 2^32) / 2^32), float64
+    std::vector<double> gr((size_t)C * NN), gi((size_t)C * NN);
+    double gmax = 0.0;
+    for (int c = 0; c < C; c++)
+        for (int k = 0; k < NN; k++) {
+            const uint32_t ph = (uint32_t)((uint64_t)h->inc[c] * (uint64_t)(NN - 1 - k));
+            const double th = TWO_PI * ((double)ph / 4294967296.0);
+            gr[(size_t)c * NN + k] = (double)h->b[k] * std::cos(th);
+            gi[(size_t)c * NN + k] = (double)h->b[k] * std::sin(th);
+            gmax = std::max(gmax, std::max(std::fabs(gr[(size_t)c * NN + k]), std::fabs(gi[(size_t)c * NN + k])));
+        }
+    if (!(gmax > 0.0)) gmax = 1.0;
+    // FP32 path: tap-major float2
+    {
+        std::vector<float2> g((size_t)NN * h->c_pad, make_float2(0.0f, 0.0f));
+        for (int c = 0; c < C; c++)
+            for (int k = 0; k < NN; k++) g[(size_t)k * h->c_pad + c] = make_float2((float)gr[(size_t)c * NN + k], (float)gi[(size_t)c * NN + k]);
+        CHK(cudaMemcpy(h->d_g, g.data(), g.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        std::vector<uint2> m(C);
+        for (int c = 0; c < C; c++) m[c] = make_uint2(h->inc[c], (uint32_t)((uint64_t)h->inc[c] * (uint64_t)h->D));
+        CHK(cudaMemcpy(h->d_meta32, m.data(), m.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
+    if (h->n_kchunks == 0) return FMGPU_OK;      // shape not eligible for the MMA kernel
+    // MMA path: three balanced base-256 digit planes of round(G * 2^e), |value| < 127 * 65536
+    const int e = (int)std::floor(std::log2(8.29e6 / gmax));
+    const double S = std::ldexp(1.0, e);
+    h->w0 = (float)(65536.0 / S); h->w1 = (float)(256.0 / S); h->w2 = (float)(1.0 / S);
+    const int KB = 2 * NN;
+    const size_t img_bytes = (size_t)h->n_groups * h->n_kchunks * CH_PLANES * CH_BSUB_BYTES;
+    std::vector<int8_t> img(img_bytes, 0);
+    std::vector<int> offs((size_t)h->n_groups * CH_PLANES * CH_NG, 0);
+    std::vector<uint4> meta((size_t)h->n_groups * CH_SLOTS, make_uint4(0, 0, 0xffffffffu, 0));
+    for (int c = 0; c < C; c++) {
+        const int grp = c / h->per_group, slot = c % h->per_group;
+        meta[(size_t)grp * CH_SLOTS + slot] = make_uint4(h->inc[c], (uint32_t)((uint64_t)h->inc[c] * (uint64_t)h->D), (uint32_t)c, 0);
+        for (int K = 0; K < KB; K++) {
+            const int k = K >> 1, comp = K & 1;
+            // column 2 slot (re): gr * xr - gi * xi; column 2 slot + 1 (im): gi * xr + gr * xi
+            const double v_re = comp == 0 ? gr[(size_t)c * NN + k] : -gi[(size_t)c * NN + k];
+            const double v_im = comp == 0 ? gi[(size_t)c * NN + k] : gr[(size_t)c * NN + k];
+            for (int col = 0; col < 2; col++) {
+                long long v = std::llround((col == 0 ? v_re : v_im) * S);
+                int d[3];
+                d[2] = (int)(int8_t)(v & 0xff); v = (v - d[2]) >> 8;
+                d[1] = (int)(int8_t)(v & 0xff); v = (v - d[1]) >> 8;
+                d[0] = (int)v;                  // |d0| <= 127 by the choice of e
+                const int n = 2 * slot + col, kc = K / CH_KCHUNK, kk = K % CH_KCHUNK;
+                for (int j = 0; j < CH_PLANES; j++) {
+                    const size_t base = (((size_t)grp * h->n_kchunks + kc) * CH_PLANES + j) * CH_BSUB_BYTES;
+                    img[base + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((kk >> 4) ^ (n & 7)) << 4) + (kk & 15)] = (int8_t)d[j];
+                    offs[((size_t)grp * CH_PLANES + j) * CH_NG + n] += 127 * d[j];
+                }
+            }
+        }
+    }
+    CHK(cudaMemcpy(h->d_bimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    CHK(cudaMemcpy(h->d_offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CHK(cudaMemcpy(h->d_meta, meta.data(), meta.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    return FMGPU_OK;
+}
+
+size_t chan_mma_smem(const fmgpu_chan* h) { return (size_t)h->n_kchunks * CH_PLANES * CH_BSUB_BYTES + 2 * CH_A_BYTES + 1024; }
+
+// staged buffer already holds history ++ block; writes slot, then rolls the history
+int chan_run(fmgpu_chan* h, int slot) {
+    if (h->taps_dirty) {
+        CHK(cudaStreamSynchronize(h->st));
+        const int rc = chan_upload_taps(h);
+        if (rc != FMGPU_OK) return rc;
+        h->taps_dirty = false;
+    }
+    const uint32_t n_newest0 = (uint32_t)(h->n_abs + (unsigned long long)h->D - 1ull);
+    if (h->mode == FMGPU_CHAN_MODE_TENSOR) {
+        ChanMmaParams p{};
+        p.iq = h->d_stage; p.bimg = h->d_bimg; p.offs = h->d_offs; p.meta = h->d_meta; p.out = h->d_out[slot];
+        p.n_newest0 = n_newest0; p.n_out = h->n_out; p.row_bytes = 2 * h->D; p.n_kchunks = h->n_kchunks;
+        p.n_tiles = h->n_out / CH_ROWS; p.w0 = h->w0; p.w1 = h->w1; p.w2 = h->w2;
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+        const int per_group = std::max(1, std::min(p.n_tiles, (2 * n_sm) / h->n_groups));
+        chan_mma_i8<<<dim3(per_group, h->n_groups), 128, chan_mma_smem(h), h->st>>>(p);
+    } else {
+        ChanFp32Params p{};
+        p.iq = h->d_stage; p.g = h->d_g; p.meta = h->d_meta32; p.out = h->d_out[slot]; p.n_newest0 = n_newest0;
+        p.n_out = h->n_out; p.D = h->D; p.NN = h->NN; p.C = h->C; p.c_pad = h->c_pad;
+        const size_t smem = (size_t)(CF_TILE * h->D + h->NN - h->D) * sizeof(float2);
+        chan_fir_fp32<<<dim3(h->n_out / CF_TILE, (h->C + 31) / 32), 128, smem, h->st>>>(p);
+    }
+    CHK(cudaGetLastError());
+    h->launches++;
+    // history for the next block = the last NN - D samples of (history ++ block)
+    if (h->hist_bytes) CHK(cudaMemcpyAsync(h->d_stage, h->d_stage + h->in_bytes, h->hist_bytes, cudaMemcpyDeviceToDevice, h->st));
+    CHK(cudaEventRecord(h->ev_done[slot], h->st));
+    h->n_abs += (unsigned long long)h->n_out * (unsigned long long)h->D;
+    h->step++;
+    return FMGPU_OK;
+}
+
+void chan_free(fmgpu_chan* h) {
+    cudaDeviceSynchronize();
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(h->d_stage); F(h->d_g); F(h->d_meta32); F(h->d_bimg); F(h->d_offs); F(h->d_meta);
+    for (auto p : h->d_out) F(p);
+    for (auto e : h->ev_done) if (e) cudaEventDestroy(e);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->st) cudaStreamDestroy(h->st);
+}
+
+} // namespace
+
+extern "C" {
+
+int fmgpu_chan_create(const fmgpu_chan_config* cfg, const double* centre_hz, fmgpu_chan** out) {
+    if (!cfg || !centre_hz || !out) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: null argument");
+    *out = nullptr;
+    const int D = cfg->decimation, NN = cfg->n_taps, C = cfg->n_channels, n_out = cfg->block_out;
+    if (D < 1 || NN < D || NN > 1024 || C < 1 || !(cfg->fs_in_hz > 0.0))
+        return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: need decimation >= 1, decimation <= n_taps <= 1024, n_channels >= 1, fs_in_hz > 0");
+    if (n_out < CH_ROWS || n_out % CH_ROWS != 0)
+        return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: block_out must be a positive multiple of 128");
+    if ((size_t)n_out * D * 2 < (size_t)(NN - D) * 2)
+        return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: block shorter than the filter history");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fmgpu_set_last_error_(FMGPU_ERR_CUDA, (std::string("chan_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e)).c_str());
+    int dev = cfg->device;
+    if (dev < 0) CHK(cudaGetDevice(&dev));
+    if (dev >= n_dev) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: bad device ordinal");
+    CHK(cudaSetDevice(dev));
+    cudaDeviceProp prop{};
+    CHK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fmgpu_set_last_error_(FMGPU_ERR_CUDA, "chan_create: kernels are built for sm_100a only");
+    // the tensor-core kernel needs 8-byte aligned windows and whole 128-byte K chunks
+    const bool mma_ok = (D % 4 == 0) && ((2 * NN) % CH_KCHUNK == 0) && (2 * NN / CH_KCHUNK) <= 8;
+    int mode = cfg->mode;
+    if (mode == FMGPU_CHAN_MODE_AUTO) mode = mma_ok ? FMGPU_CHAN_MODE_TENSOR : FMGPU_CHAN_MODE_FP32;
+    if (mode == FMGPU_CHAN_MODE_TENSOR && !mma_ok)
+        return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: tensor mode needs decimation % 4 == 0 and n_taps % 64 == 0, n_taps <= 512");
+    if (mode != FMGPU_CHAN_MODE_TENSOR && mode != FMGPU_CHAN_MODE_FP32) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_create: unknown mode");
+
+    auto* h = new fmgpu_chan();
+    h->cfg = *cfg; h->cfg.device = dev; h->cfg.mode = mode;
+    h->C = C; h->D = D; h->NN = NN; h->n_out = n_out; h->device = dev; h->mode = mode;
+    h->depth = cfg->ring_depth > 0 ? cfg->ring_depth : 4;
+    h->cfg.ring_depth = h->depth;
+    h->n_groups = (C + CH_SLOTS - 1) / CH_SLOTS;
+    h->per_group = (C + h->n_groups - 1) / h->n_groups;
+    h->n_kchunks = mma_ok ? 2 * NN / CH_KCHUNK : 0;
+    h->c_pad = (C + 31) / 32 * 32;
+    h->hist_bytes = (size_t)(NN - D) * 2;
+    h->in_bytes = (size_t)n_out * D * 2;
+    h->fc.assign(centre_hz, centre_hz + C);
+    h->inc.resize(C);
+    for (int c = 0; c < C; c++) {
+        const double turns = centre_hz[c] / cfg->fs_in_hz;                    // cycles per input sample
+        h->inc[c] = (uint32_t)(long long)std::llround((turns - std::floor(turns)) * 4294967296.0);
+    }
+    h->b.assign(NN, 0.0f);
+    const float k = cfg->cutoff_k > 0.0f ? cfg->cutoff_k : 0.95f / (float)D;  // the reference's ROLLOFF (broadcast_fm_demod.cpp:129)
+    fmgpu_create_fir_lpf(h->b.data(), NN, k);
+    int rc = FMGPU_OK;
+    auto A = [&](cudaError_t err) { if (err != cudaSuccess && rc == FMGPU_OK) rc = fmgpu_set_last_error_(FMGPU_ERR_CUDA, cudaGetErrorString(err)); };
+    A(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    A(cudaMalloc((void**)&h->d_stage, h->hist_bytes + h->in_bytes + 256));
+    if (rc == FMGPU_OK) A(cudaMemset(h->d_stage, 127, h->hist_bytes + h->in_bytes + 256));   // empty history: x = 0 <-> u8 127
+    h->d_out.assign(h->depth, nullptr); h->ev_done.assign(h->depth, nullptr);
+    for (int i = 0; i < h->depth; i++) {
+        A(cudaMalloc((void**)&h->d_out[i], (size_t)C * n_out * sizeof(float2)));
+        A(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    A(cudaMalloc((void**)&h->d_g, (size_t)NN * h->c_pad * sizeof(float2)));
+    A(cudaMalloc((void**)&h->d_meta32, (size_t)C * sizeof(uint2)));
+    if (h->n_kchunks) {
+        A(cudaMalloc((void**)&h->d_bimg, (size_t)h->n_groups * h->n_kchunks * CH_PLANES * CH_BSUB_BYTES));
+        A(cudaMalloc((void**)&h->d_offs, (size_t)h->n_groups * CH_PLANES * CH_NG * sizeof(int)));
+        A(cudaMalloc((void**)&h->d_meta, (size_t)h->n_groups * CH_SLOTS * sizeof(uint4)));
+        A(cudaFuncSetAttribute(chan_mma_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma_smem(h)));
+    }
+    {
+        const size_t smem = (size_t)(CF_TILE * D + NN - D) * sizeof(float2);
+        if (smem > 48 * 1024) A(cudaFuncSetAttribute(chan_fir_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (rc != FMGPU_OK) { chan_free(h); delete h; return rc; }
+    *out = h;
+    return FMGPU_OK;
+}
+
+void fmgpu_chan_destroy(fmgpu_chan* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    chan_free(h);
+    delete h;
+}
+
+float* fmgpu_chan_get_b(fmgpu_chan* h) { if (!h) return nullptr; h->taps_dirty = true; return h->b.data(); }
+
+int fmgpu_chan_get_config(fmgpu_chan* h, fmgpu_chan_config* out) {
+    if (!h || !out) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_get_config: null argument");
+    *out = h->cfg;
+    return FMGPU_OK;
+}
+
+int fmgpu_chan_get_freqs(fmgpu_chan* h, double* hz, uint32_t* inc) {
+    if (!h) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_get_freqs: null handle");
+    for (int c = 0; c < h->C; c++) {
+        if (inc) inc[c] = h->inc[c];
+        if (hz) {
+            double f = (double)h->inc[c] / 4294967296.0;
+            if (f >= 0.5) f -= 1.0;
+            hz[c] = f * h->cfg.fs_in_hz;
+        }
+    }
+    return FMGPU_OK;
+}
+
+int fmgpu_chan_enqueue_u8_device(fmgpu_chan* h, const uint8_t* iq_dev, float** out_dev) {
+    if (!h || !iq_dev) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_enqueue: null argument");
+    CHK(cudaSetDevice(h->device));
+    const int slot = (int)(h->step % (unsigned long long)h->depth);
+    CHK(cudaMemcpyAsync(h->d_stage + h->hist_bytes, iq_dev, h->in_bytes, cudaMemcpyDeviceToDevice, h->st));
+    const int rc = chan_run(h, slot);
+    if (rc != FMGPU_OK) return rc;
+    if (out_dev) *out_dev = (float*)h->d_out[slot];
+    return FMGPU_OK;
+}
+
+int fmgpu_chan_process_u8(fmgpu_chan* h, const uint8_t* iq_host, size_t n_in_samples, float* out_host) {
+    if (!h || !iq_host) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_process: null argument");
+    if (n_in_samples != (size_t)h->n_out * h->D) return fmgpu_set_last_error_(FMGPU_ERR_SIZE, "chan_process: n_in_samples != block_out * decimation");
+    CHK(cudaSetDevice(h->device));
+    const int slot = (int)(h->step % (unsigned long long)h->depth);
+    CHK(cudaMemcpyAsync(h->d_stage + h->hist_bytes, iq_host, h->in_bytes, cudaMemcpyHostToDevice, h->st));
+    const int rc = chan_run(h, slot);
+    if (rc != FMGPU_OK) return rc;
+    if (out_host) CHK(cudaMemcpyAsync(out_host, h->d_out[slot], (size_t)h->C * h->n_out * sizeof(float2), cudaMemcpyDeviceToHost, h->st));
+    CHK(cudaStreamSynchronize(h->st));
+    return FMGPU_OK;
+}
+
+int fmgpu_chan_sync(fmgpu_chan* h) {
+    if (!h) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_sync: null handle");
+    CHK(cudaSetDevice(h->device));
+    CHK(cudaStreamSynchronize(h->st));
+    return FMGPU_OK;
+}
+
+int fmgpu_chan_wait_external_stream(fmgpu_chan* h, void* cuda_stream) {
+    if (!h) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_wait_external_stream: null handle");
+    cudaEvent_t ev;
+    CHK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CHK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
+    CHK(cudaStreamWaitEvent(h->st, ev, 0));
+    CHK(cudaEventDestroy(ev));
+    return FMGPU_OK;
+}
+
+void* fmgpu_chan_stream(fmgpu_chan* h) { return h ? (void*)h->st : nullptr; }
+long long fmgpu_chan_launch_count(fmgpu_chan* h) { return h ? h->launches : 0; }
+
+// One wideband block through channelizer + demodulators: the channelizer's output slot becomes the
+// cf32 input of the demodulator handle (n_streams = n_channels, block_size = block_out).
+int fmgpu_chan_feed_device(fmgpu_chan* h, fmgpu_demod* demod, const uint8_t* iq_dev) {
+    if (!h || !demod || !iq_dev) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_feed: null argument");
+    fmgpu_config dc{};
+    int rc = fmgpu_get_config(demod, &dc);
+    if (rc != FMGPU_OK) return rc;
+    if (dc.n_streams != h->C || dc.block_size != h->n_out || dc.pipeline_depth > h->depth)
+        return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_feed: demodulator must have n_streams = n_channels, block_size = block_out, pipeline_depth <= ring_depth");
+    // the slot about to be overwritten was the input of the demodulator's block `depth` enqueues ago
+    rc = fmgpu_stream_wait_input_free(demod, (void*)h->st);
+    if (rc != FMGPU_OK) return rc;
+    float* out = nullptr;
+    rc = fmgpu_chan_enqueue_u8_device(h, iq_dev, &out);
+    if (rc != FMGPU_OK) return rc;
+    return fmgpu_enqueue_cf32_device(demod, out, (void*)h->st);
+}
+
+} // extern "C"

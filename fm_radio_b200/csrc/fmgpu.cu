@@ -589,6 +589,35 @@ int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev) {
     return rc < 0 ? rc : FMGPU_OK;
 }
 
+// cf32 input already on the device (the channelizer's output): K1's cf32 variant reads it in place.
+// after_stream (may be NULL): CUDA stream whose queued work produces iq_dev.
+int fmgpu_enqueue_cf32_device(fmgpu_demod* h, const float* iq_dev, void* after_stream) {
+    if (!h || !iq_dev) return fail(FMGPU_ERR_ARG, "enqueue: null argument");
+    CU(cudaSetDevice(h->device));
+    if (after_stream) {
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, (cudaStream_t)after_stream));
+        CU(cudaStreamWaitEvent(h->stA, ev, 0));
+        CU(cudaEventDestroy(ev));
+    }
+    const int rc = enqueue_chain(h, iq_dev, false, false);
+    return rc < 0 ? rc : FMGPU_OK;
+}
+
+// Makes `cuda_stream` wait until the input of the block enqueued pipeline_depth enqueues ago has been
+// consumed (its stage A is complete), i.e. until a producer that recycles its output buffers with the
+// same period may overwrite the oldest one.
+int fmgpu_stream_wait_input_free(fmgpu_demod* h, void* cuda_stream) {
+    if (!h) return fail(FMGPU_ERR_ARG, "stream_wait_input_free: null handle");
+    CU(cudaSetDevice(h->device));
+    const int slot = (int)(h->step % (unsigned long long)h->depth);
+    CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->slots[slot].ev_A, 0));
+    return FMGPU_OK;
+}
+
+int fmgpu_set_last_error_(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+
 int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[6]) {
     if (!h || !iq_dev || !ms || n_blocks == 0) return fail(FMGPU_ERR_ARG, "profile_stages: bad argument");
     CU(cudaSetDevice(h->device));

@@ -183,3 +183,80 @@ def synth_u8_torch(n_samples: int, params: list[StreamParams], device):
         iq = torch.stack((p.amplitude * torch.cos(phi), p.amplitude * torch.sin(phi)), dim=1).to(torch.float32) + noise
         out[s] = torch.clamp(torch.round(127.0 + iq), 0, 255).to(torch.uint8).reshape(-1)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Wideband capture (BASELINE config 4): many stations on a raster in one complex u8 stream.
+# ---------------------------------------------------------------------------------------------
+FS_WIDEBAND = 20_480_000          # = 20 x the chain's 1.024 MS/s: "20 MHz" of spectrum, integer decimation
+RASTER_HZ = 200_000.0
+
+
+def wideband_centres(n_stations: int = 100, spacing_hz: float = RASTER_HZ) -> np.ndarray:
+    """Centre frequencies (Hz, relative to the capture's centre) of n stations on a raster, symmetric about 0
+    and never at 0 Hz for even n (100 stations: -9.9 MHz ... +9.9 MHz)."""
+    return (np.arange(n_stations, dtype=np.float64) - (n_stations - 1) / 2.0) * spacing_hz
+
+
+def wideband_amplitude(n_stations: int) -> float:
+    """Per-station amplitude that puts the 4-sigma point of the sum at the u8 rails."""
+    return 127.0 / (4.0 * np.sqrt(max(n_stations, 1) / 2.0))
+
+
+def _mpx_chunk(xp, t, p: StreamParams, chips, fs):
+    left = _audio(t, p.tones_left, xp)
+    right = _audio(t, p.tones_right, xp)
+    wp = 2 * np.pi * F_PILOT * t + p.pilot_phase
+    u = t * RDS_CHIP_RATE
+    ci = xp.floor(u)
+    frac = u - ci
+    ci = ci.astype(np.int64) if xp is np else ci.to(chips.device).long()
+    rds = chips[ci] * xp.sin(np.pi * frac) ** 2
+    return (0.40 * (left + right) / 1.4 + 0.10 * xp.sin(wp)
+            + 0.40 * (left - right) / 1.4 * xp.sin(2 * wp) + 0.06 * rds * xp.sin(3 * wp))
+
+
+def synth_wideband_u8(n_samples: int, centres_hz, params: list[StreamParams], fs: float = FS_WIDEBAND,
+                      amplitude: float | None = None, device=None, chunk: int = 1 << 21):
+    """uint8 [2*n_samples] (I,Q interleaved): sum over stations of A exp(j(phi_s(t) + 2 pi (f_c + f_off) t)),
+    phi_s the FM phase of the same stereo+RDS multiplex as synth_u8_numpy evaluated at the wideband
+    rate, quantised like an SDR front end: clip(round(127 + .), 0, 255).  device=None: float64 numpy
+    (bit-reproducible); otherwise a torch device (same formulas, returns a torch tensor there)."""
+    centres_hz = np.asarray(centres_hz, np.float64)
+    assert len(centres_hz) == len(params)
+    amp = wideband_amplitude(len(params)) if amplitude is None else float(amplitude)
+    n_chips = int(np.ceil(n_samples * RDS_CHIP_RATE / fs)) + 2
+    if device is None:
+        xp = np
+        out = np.empty(2 * n_samples, np.uint8)
+        chips = [rds_chips(p, n_chips) for p in params]
+        carry = [0.0] * len(params)
+    else:
+        import torch
+        xp = torch
+        dev = torch.device(device)
+        out = torch.empty(2 * n_samples, dtype=torch.uint8, device=dev)
+        chips = [torch.from_numpy(rds_chips(p, n_chips)).to(dev) for p in params]
+        carry = [0.0] * len(params)
+    for n0 in range(0, n_samples, chunk):
+        n1 = min(n0 + chunk, n_samples)
+        if device is None:
+            t = np.arange(n0, n1, dtype=np.float64) / fs
+            re = np.zeros(n1 - n0); im = np.zeros(n1 - n0)
+        else:
+            t = torch.arange(n0, n1, dtype=torch.float64, device=dev) / fs
+            re = torch.zeros(n1 - n0, dtype=torch.float64, device=dev); im = torch.zeros_like(re)
+        for s, p in enumerate(params):
+            mpx = _mpx_chunk(xp, t, p, chips[s], fs)
+            phi = carry[s] + 2 * np.pi * F_DEVIATION * xp.cumsum(mpx, 0) / fs
+            carry[s] = float(phi[-1])
+            ang = phi + 2 * np.pi * (centres_hz[s] + p.f_offset_hz) * t
+            re += amp * xp.cos(ang)
+            im += amp * xp.sin(ang)
+        if device is None:
+            out[2 * n0:2 * n1:2] = np.clip(np.rint(127.0 + re), 0, 255).astype(np.uint8)
+            out[2 * n0 + 1:2 * n1:2] = np.clip(np.rint(127.0 + im), 0, 255).astype(np.uint8)
+        else:
+            out[2 * n0:2 * n1:2] = torch.clamp(torch.round(127.0 + re), 0, 255).to(torch.uint8)
+            out[2 * n0 + 1:2 * n1:2] = torch.clamp(torch.round(127.0 + im), 0, 255).to(torch.uint8)
+    return out

@@ -79,6 +79,13 @@ int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev);
 /* Same, but iq_host is a (preferably pinned) HOST pointer: the host->device copy is queued on the
  * handle's copy stream and overlaps with the kernels of the blocks already in flight. */
 int fmgpu_enqueue_u8_host(fmgpu_demod* h, const uint8_t* iq_host);
+/* Same for cf32 input that is already on the device ([n_streams][block_size] complex float), e.g. the
+ * channelizer's output.  after_stream (cudaStream_t as void*, may be NULL): work queued on it produces
+ * iq_dev. */
+int fmgpu_enqueue_cf32_device(fmgpu_demod* h, const float* iq_dev, void* after_stream);
+/* Makes cuda_stream wait until the input buffer of the block enqueued pipeline_depth enqueues ago has
+ * been consumed, so a producer that recycles pipeline_depth output buffers may overwrite the oldest. */
+int fmgpu_stream_wait_input_free(fmgpu_demod* h, void* cuda_stream);
 int fmgpu_sync(fmgpu_demod* h);
 /* Copies slot's audio + symbols to the pinned host mirrors (asynchronously on the output stream;
  * valid after fmgpu_sync). */
@@ -227,6 +234,54 @@ int  fmgpu_rds_get_groups(const fmgpu_rds* r, fmgpu_rds_group* out, int max_grou
 int  fmgpu_rds_n_bytes(const fmgpu_rds* r);
 int  fmgpu_rds_get_bytes(const fmgpu_rds* r, uint8_t* out, int max_bytes);
 void fmgpu_rds_get_db(const fmgpu_rds* r, uint16_t* pi, char ps8[8], char rt64[64], uint8_t* pty);
+
+/* ---- wideband channelizer (BASELINE config 4) --------------------------
+ * New component: the reference tunes ONE station in hardware and has no channelizer (its TODO on a
+ * configurable front end is broadcast_fm_demod.cpp:67).  One wideband u8 IQ capture at fs_in_hz is
+ * split into n_channels complex channels at fs_in_hz / decimation, channel c centred on centre_hz[c]:
+ *   y_c[i] = sum_{k < n_taps} b[k] * xs_c[(i+1) * decimation - n_taps + k],
+ *   xs_c[n] = ((float)u8[n] - 127) * exp(-j 2 pi f_c n / fs)
+ * i.e. the reference's unpack (app.cpp:56-65) and PolyphaseDownsampler convention
+ * (dsp/polyphase_filter.h:41-64) around a per-channel frequency shift; b is create_fir_lpf
+ * (dsp/filter_designer.cpp:84-107).  f_c is quantised to fs / 2^32 so the phase is exact integer
+ * arithmetic over any capture length (fmgpu_chan_get_freqs returns the quantised values).
+ * Output [n_channels][block_out] complex float on the device is exactly the cf32 input layout of a
+ * demodulator handle with n_streams = n_channels, block_size = block_out. */
+typedef struct fmgpu_chan fmgpu_chan;
+enum { FMGPU_CHAN_MODE_AUTO = 0,     /* tensor cores when the shape allows, else FP32                    */
+       FMGPU_CHAN_MODE_TENSOR = 1,   /* tcgen05.mma kind::i8 on the raw u8 capture, exact int32 sums     */
+       FMGPU_CHAN_MODE_FP32 = 2 };   /* direct form on the FP32 FMA pipe                                 */
+typedef struct fmgpu_chan_config {
+    double fs_in_hz;         /* wideband sample rate, e.g. 20 480 000                                   */
+    int decimation;          /* D: channel rate = fs_in_hz / D (20 -> the chain's 1.024 MS/s)           */
+    int n_taps;              /* prototype low-pass length (tensor mode: multiple of 64, <= 512)          */
+    float cutoff_k;          /* prototype cutoff relative to the input Nyquist; 0 = 0.95 / D            */
+    int n_channels;
+    int block_out;           /* outputs per channel per call (multiple of 128) = the demodulator's block_size;
+                                one call consumes block_out * D wideband samples                       */
+    int device;              /* CUDA ordinal, -1 = current                                               */
+    int mode;                /* FMGPU_CHAN_MODE_*                                                        */
+    int ring_depth;          /* output buffers recycled round-robin (0 = 4); >= the demodulator's pipeline_depth */
+} fmgpu_chan_config;
+int  fmgpu_chan_create(const fmgpu_chan_config* cfg, const double* centre_hz, fmgpu_chan** out);
+void fmgpu_chan_destroy(fmgpu_chan* c);
+/* Host array of n_taps prototype taps in the reference's order (like get_b()); edits take effect at the next block. */
+float* fmgpu_chan_get_b(fmgpu_chan* c);
+int  fmgpu_chan_get_config(fmgpu_chan* c, fmgpu_chan_config* out);
+/* Quantised centre frequencies (Hz) and their phase increments per input sample (turns * 2^32); either may be NULL. */
+int  fmgpu_chan_get_freqs(fmgpu_chan* c, double* centre_hz, uint32_t* phase_inc);
+/* Host in, host out (out_host may be NULL); synchronous.  n_in_samples must be block_out * decimation. */
+int  fmgpu_chan_process_u8(fmgpu_chan* c, const uint8_t* iq_host, size_t n_in_samples, float* out_host);
+/* Device in; asynchronous on the channelizer's stream.  *out_dev (may be NULL) receives the device
+ * pointer of the output buffer this block was written to. */
+int  fmgpu_chan_enqueue_u8_device(fmgpu_chan* c, const uint8_t* iq_dev, float** out_dev);
+/* One wideband block through channelizer and demodulators (demod: n_streams = n_channels,
+ * block_size = block_out, pipeline_depth <= ring_depth); asynchronous. */
+int  fmgpu_chan_feed_device(fmgpu_chan* c, fmgpu_demod* demod, const uint8_t* iq_dev);
+int  fmgpu_chan_wait_external_stream(fmgpu_chan* c, void* cuda_stream);
+int  fmgpu_chan_sync(fmgpu_chan* c);
+void* fmgpu_chan_stream(fmgpu_chan* c);
+long long fmgpu_chan_launch_count(fmgpu_chan* c);
 
 const char* fmgpu_last_error(void);
 const char* fmgpu_version(void);

@@ -904,3 +904,50 @@ void fmo_get_groups(void* hv, uint16_t* data, uint8_t* valid, uint8_t* type) { c
 int fmo_n_rds_bytes(void* hv) { return ((demod_t*)hv)->rdsdec.n_bytes; }
 void fmo_get_rds_bytes(void* hv, uint8_t* out) { demod_t* d = (demod_t*)hv; memcpy(out, d->rdsdec.bytes, d->rdsdec.n_bytes); }
 void fmo_get_db(void* hv, uint16_t* pi, char* ps8, char* rt64, uint8_t* pty) { copy_db(&((demod_t*)hv)->rdsdec, pi, ps8, rt64, pty); }
+
+/* ------------------------------------------------------------------------------------------
+ * Wideband channelizer oracle (BASELINE config 4).  The reference has NO channelizer (SURVEY.md
+ * section 7, "No channelizer in the reference"), so this is the definition the CUDA channelizer is
+ * checked against: per channel, frequency shift in float64 followed by a decimating direct-form FIR
+ * in float64, in the reference's own conventions --
+ *   unpack       x[n] = (u8 - 127)                                      app.cpp:56-65
+ *   shift        xs[n] = x[n] * exp(-j 2 pi ph_c(n) / 2^32),  ph_c(n) = (inc_c * n) mod 2^32
+ *                (inc_c = round(f_c / Fs * 2^32): the centre frequency quantised to Fs / 2^32)
+ *   decimate     y[i] = sum_{k<NN} b[k] * xs[(i+1)*D - NN + k]          dsp/polyphase_filter.h:41-64
+ *                (newest sample <-> b[NN-1]; samples before the first are zero = empty history)
+ * iq: n_in interleaved (I,Q) u8 pairs; n0: absolute index of iq[0]; hist: the NN samples before
+ * iq[0] (u8 pairs, or NULL = zeros... i.e. u8 value 127); out: n_ch x n_out complex double.
+ * ---------------------------------------------------------------------------------------- */
+void fmo_channelize_f64(const uint8_t* iq, size_t n_in, const uint8_t* hist, uint64_t n0, int D, int NN,
+                        const float* b, const uint32_t* inc, int n_ch, double* out)
+{
+    const size_t n_out = n_in / (size_t)D;
+    const double TWO_PI = 6.283185307179586476925286766559;
+    double* xr = (double*)malloc(sizeof(double) * (n_in + (size_t)NN));
+    double* xi = (double*)malloc(sizeof(double) * (n_in + (size_t)NN));
+    for (int c = 0; c < n_ch; c++) {
+        for (size_t j = 0; j < n_in + (size_t)NN; j++) {
+            /* j = 0 is absolute sample n0 - NN */
+            double re, im;
+            if (j < (size_t)NN) {
+                if (hist) { re = (double)hist[2*j] - 127.0; im = (double)hist[2*j+1] - 127.0; }
+                else { re = 0.0; im = 0.0; }
+            } else { re = (double)iq[2*(j - NN)] - 127.0; im = (double)iq[2*(j - NN) + 1] - 127.0; }
+            const uint64_t n = n0 + (uint64_t)j - (uint64_t)NN;                 /* wraps like the phase does */
+            const uint32_t ph = (uint32_t)((uint64_t)inc[c] * n);
+            const double th = -TWO_PI * ((double)ph / 4294967296.0);
+            const double cs = cos(th), sn = sin(th);
+            xr[j] = re * cs - im * sn;
+            xi[j] = re * sn + im * cs;
+        }
+        for (size_t i = 0; i < n_out; i++) {
+            const double* pr = xr + (i + 1) * (size_t)D;       /* element k of the window = index (i+1)*D - NN + k, +NN for the prefix */
+            const double* pi = xi + (i + 1) * (size_t)D;
+            double ar = 0.0, ai = 0.0;
+            for (int k = 0; k < NN; k++) { ar += (double)b[k] * pr[k]; ai += (double)b[k] * pi[k]; }
+            out[2 * ((size_t)c * n_out + i)] = ar;
+            out[2 * ((size_t)c * n_out + i) + 1] = ai;
+        }
+    }
+    free(xr); free(xi);
+}

@@ -59,6 +59,10 @@ void fmo_polyphase_ds_f32(int M, int K, const float* b, const float* x, float* y
 void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls);
 void fmo_polyphase_us_f32(int L, int K, const float* b, const float* x, float* y, int N_in, int n_calls);
 
+/* wideband channelizer oracle (config 4; no reference counterpart): float64 shift + decimating FIR */
+void fmo_channelize_f64(const uint8_t* iq, size_t n_in, const uint8_t* hist, uint64_t n0, int D, int NN,
+                        const float* b, const uint32_t* inc, int n_ch, double* out);
+
 #ifdef __cplusplus
 }
 #endif
