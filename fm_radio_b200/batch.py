@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .api import Buf, FMDemod, RDSDecoder
+from .api import Buf, ChanMode, Channelizer, FMDemod, RDSDecoder
 
 
 def shard_streams(n_streams: int, rank: int, world_size: int) -> range:
@@ -66,3 +66,63 @@ def gather_results(local_results, group=None):
     gathered = [None] * dist.get_world_size(group)
     dist.all_gather_object(gathered, local_results, group=group)
     return sorted(r for part in gathered for r in part)
+
+
+def shard_channels(n_channels: int, rank: int, world_size: int) -> list[int]:
+    """Channels of a wideband capture owned by `rank`: {c : c mod world_size = rank}, so
+    neighbouring (equally loaded) channels spread over the ranks."""
+    return list(range(rank, n_channels, world_size))
+
+
+class WidebandReceiver:
+    """BASELINE config 4 / 5: one wideband u8 capture -> this rank's channels -> demodulators.
+
+    Every rank needs the SAME wideband block, so the only data-path collective of the whole framework
+    is one broadcast of the u8 block per step (`broadcast_and_feed`, NCCL over NVLink on GPUs; gloo in
+    the CPU tests); each rank then channelizes and demodulates only the channels it owns -- it
+    computes only its own columns of the channelizer's contraction -- and results (PI / PS / RT per
+    channel) are gathered on the host with `gather_results`."""
+
+    def __init__(self, fs_in_hz: float, centres_hz, rank: int = 0, world_size: int = 1, block_out: int = 65536,
+                 decimation: int = 20, n_taps: int = 192, device: int = -1, mode: ChanMode = ChanMode.AUTO,
+                 pipeline_depth: int = 0, chan=None, demod=None):
+        centres_hz = np.asarray(centres_hz, np.float64)
+        self.channel_ids = shard_channels(len(centres_hz), rank, world_size)
+        self.centres_hz = centres_hz[self.channel_ids]
+        self.block_in = block_out * decimation
+        # chan / demod are injectable so the shard / broadcast / gather logic runs without a GPU in the CPU
+        # suite; the product always builds the CUDA objects
+        self.demod = demod if demod is not None else FMDemod(block_out, len(self.channel_ids), device=device,
+                                                             pipeline_depth=pipeline_depth)
+        self.chan = chan if chan is not None else Channelizer(fs_in_hz, self.centres_hz, decimation, n_taps, block_out,
+                                                              device=device, mode=mode,
+                                                              ring_depth=getattr(self.demod, "depth", 0))
+
+    def feed(self, iq_block, producer_stream: int = 0) -> int:
+        """One wideband block (device u8 tensor / pointer of 2 * block_in bytes), asynchronous."""
+        if producer_stream:
+            self.chan.wait_external_stream(producer_stream)
+        return self.chan.feed(self.demod, iq_block)
+
+    def broadcast_and_feed(self, iq_block, src: int = 0, group=None) -> int:
+        """iq_block: torch.uint8 tensor of 2 * block_in bytes, valid on rank `src`, overwritten elsewhere."""
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(iq_block, src=src, group=group)
+        stream = torch.cuda.current_stream().cuda_stream if iq_block.is_cuda else 0
+        return self.feed(iq_block, stream)
+
+    def results(self):
+        """[(channel id, PI, PS, RT, n_groups)] of this rank's channels, decoded on the device (K6)."""
+        self.demod.rds_fetch()
+        out = []
+        for i, c in enumerate(self.channel_ids):
+            db = self.demod.rds_db(i)
+            out.append((c, db["pi"], db["ps"], db["rt"], self.demod.rds_counts(i)[0]))
+        return out
+
+    def close(self):
+        for o in (self.chan, self.demod):
+            if hasattr(o, "close"):
+                o.close()
