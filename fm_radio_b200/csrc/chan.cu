@@ -3,8 +3,8 @@
 //
 // The reference has no channelizer (SURVEY.md section 7 "No channelizer in the reference", section
 // 8(f) rank 2; the reference's own TODO on a configurable front end is broadcast_fm_demod.cpp:67).
-// The definition implemented here -- and restated in float64 by the checker, oracle/fm_oracle.c
-// fmo_channelize_f64 -- keeps the reference's conventions on either side of it:
+// The definition implemented here -- and restated in float64 by the test-side checker
+// (fmo_channelize_f64) -- keeps the reference's conventions on either side of it:
 //   unpack    x[n] = (float)u8 - 127                                       app.cpp:56-65
 //   shift     xs[n] = x[n] * exp(-j 2 pi ph_c(n) / 2^32), ph_c(n) = inc_c * n mod 2^32
 //   decimate  y_c[i] = sum_{k<NN} b[k] * xs[(i+1) D - NN + k]              dsp/polyphase_filter.h:41-64
