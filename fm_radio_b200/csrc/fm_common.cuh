@@ -22,6 +22,8 @@ constexpr int K1_THREADS = 128;
 constexpr int K1_TILE = K1_R * K1_THREADS;          // 2048 outputs = 8192 IQ samples per CTA
 constexpr int K1_SEG = 16 * 8 + 4;                  // floats per 16-frame segment (+4 pad: bank skew)
 constexpr int K1_HIST = 64;                         // IQ samples of history
+constexpr float K1_TAP_SCALE = 1.2676506002282294e30f;   // 2^100
+constexpr float K1_UNSCALE = 562949953421312.0f;         // 2^49 = 2^149 / 2^100
 
 constexpr int K2_THREADS = 128;
 constexpr int K2_R = 8;
@@ -109,10 +111,14 @@ __device__ __forceinline__ float round_half_away(float x) { return roundf(x); }
 
 struct K1Params {
     float taps[K1_NN];          // reference memory order: b[NN-1] multiplies the newest sample
+    float taps_s[K1_NN];        // taps * 2^100: the u8 kernel multiplies them with the bytes taken as fp32 denormals (u * 2^-149)
+    float neg_dc;               // -127 * sum(taps): the reference's "- 127.0f" (app.cpp:59-60), applied once per output
+    float first_neg_dc[K1_R];   // stream start: output r of the first block met real samples on its last 4(r+1) taps only
     float discrim_gain;         // A = 0.5*Fs/(2 pi Fd) (fm_demod.cpp:36-39)
     int n_out;                  // B/4 outputs per stream
     int parity;                 // history ping-pong: read [parity], write [parity^1]
     int n_streams;
+    int first_block;            // no block before this one: the discriminator's previous angle is 0
 };
 
 struct K2Params {

@@ -361,11 +361,23 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     {
         fm::K1Params p{};
         std::memcpy(p.taps, h->taps.fm_in, sizeof(p.taps));
+        // DC term of the u8 kernel: the float the kernel's own FMA sequence yields for a window of bytes 127
+        // (each step one correctly rounded fma, reproduced here in double: a 24-bit float plus an exact
+        // 31-bit product fits 53 bits).  A silent capture (all bytes 127) then gives EXACT zeros like the
+        // reference's (float)u8 - 127.0f, and so does the zero history of a stream's first block.
+        auto dc127 = [&](int k0) {
+            float a = 0.0f;
+            for (int k = k0; k < fm::K1_NN; k++) a = (float)((double)a + (double)p.taps_s[k] * (127.0 * 0x1p-149));
+            return -(a * fm::K1_UNSCALE);
+        };
+        for (int k = 0; k < fm::K1_NN; k++) p.taps_s[k] = p.taps[k] * fm::K1_TAP_SCALE;
+        p.neg_dc = dc127(0);
+        for (int r = 0; r < fm::K1_R; r++) p.first_neg_dc[r] = dc127(fm::K1_NN - 4 * (r + 1));
         // fm_demod.cpp:36-39 with Fd = 75 kHz, Fs = 256 kHz (broadcast_fm_demod.cpp:396-398)
         const float Wd = 75e3f * 2.0f * 3.14159265358979323846f;
         const float Ts = 1.0f / 256000.0f;
         p.discrim_gain = 1.0f / (Wd * Ts) * 0.5f;
-        p.n_out = h->n4; p.parity = parity; p.n_streams = h->S;
+        p.n_out = h->n4; p.parity = parity; p.n_streams = h->S; p.first_block = (h->step == 0);
         if (prof) CU(cudaEventRecord(prof[0], h->stA));
         CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
     }

@@ -155,13 +155,19 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 // two frames (8 IQ samples) from one 16-byte chunk, applied to every output they feed.
-// One (re, im) pair per 64-bit register pair: the unpack is 2 PRMT + 1 FADD2 per IQ sample and every
-// tap costs ONE FFMA2 (re and im together) whose tap operand is a uniform-register scalar broadcast
-// to both halves (SASS: FFMA2 R, R.F32x2.HI_LO, UR.F32, R.F32x2.HI_LO).
+// One (re, im) pair per 64-bit register pair.  The unpack is 2 PRMT per IQ sample and NOTHING on the
+// FMA pipe: each byte is isolated into an otherwise zero word, i.e. the fp32 DENORMAL u * 2^-149,
+// which the FMA datapath takes at full rate and multiplies exactly; the taps ride pre-scaled by 2^100
+// (K1Params::taps_s), so every FFMA2 accumulates tap * u * 2^-49 with one IEEE rounding -- the same
+// rounding, up to the power-of-two scale, as fma(tap, (float)u, acc).  The reference's "- 127.0f"
+// (app.cpp:59-60) is linear and leaves once per OUTPUT instead of once per input sample:
+// sum tap (u - 127) = sum tap u - 127 sum tap, applied together with the 2^49 rescale as ONE FFMA2 in
+// the epilogue (k1u_finish).  Versus PRMT + FADD2 per sample this removes 128 of the 1152 FMA-pipe
+// instructions a thread issued per 16 outputs.  Every tap costs ONE FFMA2 (re and im together) whose
+// tap operand is a uniform-register scalar (SASS: FFMA2 R, R.F32x2.HI_LO, UR.F32, R.F32x2.HI_LO).
 template <int J0>   // J0 = index of the chunk's first frame relative to the thread's window (even, 0 .. 30)
 __device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], const K1Params& p) {
     const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
-    const float2 bias = make_float2(-8388735.0f, -8388735.0f);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int j = J0 + h;                           // frame index: output r uses frames r+1 .. r+16
@@ -169,9 +175,8 @@ __device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], co
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             const uint32_t v = ws[2 * h + (m >> 1)];
-            const uint32_t sel = 0x7440u | (uint32_t)((m & 1) * 2);
-            x[m] = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, sel)),
-                                          __uint_as_float(__byte_perm(v, 0x4B000000u, sel + 1u))), bias);
+            const uint32_t sel = 0x4440u | (uint32_t)((m & 1) * 2);
+            x[m] = make_float2(__uint_as_float(__byte_perm(v, 0u, sel)), __uint_as_float(__byte_perm(v, 0u, sel + 1u)));
         }
 #pragma unroll
         for (int r = 0; r < K1_R; r++) {
@@ -179,12 +184,17 @@ __device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], co
             if (g >= 0 && g < 16) {
 #pragma unroll
                 for (int m = 0; m < 4; m++) {
-                    const float tap = p.taps[4 * g + m];
+                    const float tap = p.taps_s[4 * g + m];
                     acc[r] = __ffma2_rn(x[m], make_float2(tap, tap), acc[r]);
                 }
             }
         }
     }
+}
+
+// acc = 2^-49 * sum tap u  ->  sum tap (u - 127): one FFMA2 per output (exact rescale, one rounding)
+__device__ __forceinline__ float2 k1u_finish(float2 acc, const K1Params& p) {
+    return __ffma2_rn(acc, make_float2(K1_UNSCALE, K1_UNSCALE), make_float2(p.neg_dc, p.neg_dc));
 }
 
 
@@ -218,6 +228,9 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
             wv[k] = (uint32_t)(int)(a.x + 127.0f) | ((uint32_t)(int)(a.y + 127.0f) << 8)
                   | ((uint32_t)(int)(b.x + 127.0f) << 16) | ((uint32_t)(int)(b.y + 127.0f) << 24);
         }
+        // stream start: no samples yet.  The reference's zero history adds exact zeros; byte 0 (the
+        // denormal 0.0f) does the same here, and the outputs that see it take their own DC term (below)
+        if (p.first_block) wv[0] = wv[1] = wv[2] = wv[3] = 0u;
         *(uint4*)(s_tile + ((t ^ 0) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);   // row 0: swizzle key 0
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -262,17 +275,32 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
 #pragma unroll
                     for (int m = 0; m < 4; m++) {
                         const uint32_t v = ws[2 * h + (m >> 1)];
-                        er = fmaf(u8_to_f32_m127(v, (m & 1) * 2), p.taps[4 * (2 * c + h) + m], er);
-                        ei = fmaf(u8_to_f32_m127(v, (m & 1) * 2 + 1), p.taps[4 * (2 * c + h) + m], ei);
+                        const uint32_t sel = 0x4440u | (uint32_t)((m & 1) * 2);
+                        er = fmaf(__uint_as_float(__byte_perm(v, 0u, sel)), p.taps_s[4 * (2 * c + h) + m], er);
+                        ei = fmaf(__uint_as_float(__byte_perm(v, 0u, sel + 1u)), p.taps_s[4 * (2 * c + h) + m], ei);
                     }
                 }
             }
-            th_prev_own = fm_atan2f(ei, er);
+            er = fmaf(er, K1_UNSCALE, p.neg_dc); ei = fmaf(ei, K1_UNSCALE, p.neg_dc);
+            // stream start: the reference's prev_theta is 0 (fm_demod.cpp:41, zero FIR history gives atan2(0, 0));
+            // here the all-127 history sums to rounding noise instead of an exact 0, so the case is named
+            th_prev_own = (tile == 0 && p.first_block) ? 0.0f : fm_atan2f(ei, er);
         }
         float prev = 0.0f;
 #pragma unroll
+        if (tile == 0 && t == 0 && p.first_block) {
+            // the first 16 outputs of a stream: only the taps that met real samples carry the 127 offset
+#pragma unroll
+            for (int r = 0; r < K1_R; r++)
+                acc[r] = __ffma2_rn(acc[r], make_float2(K1_UNSCALE, K1_UNSCALE), make_float2(p.first_neg_dc[r], p.first_neg_dc[r]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < K1_R; r++) acc[r] = k1u_finish(acc[r], p);
+        }
+#pragma unroll
         for (int r = 0; r < K1_R; r += 2) {
-            const float2 th = fm_atan2f_x2(acc[r].y, acc[r].x, acc[r + 1].y, acc[r + 1].x);
+            const float2 z0 = acc[r], z1 = acc[r + 1];
+            const float2 th = fm_atan2f_x2(z0.y, z0.x, z1.y, z1.x);
             out[r] = (r == 0) ? th.x : th.x - prev;      // r = 0 fixed up below
             out[r + 1] = th.y - th.x;
             prev = th.y;

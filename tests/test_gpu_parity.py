@@ -290,6 +290,11 @@ def test_controls_match_checker():
 
 
 def test_cf32_entry_point_equals_u8_entry_point():
+    """Process(span<cf32>) and the fused u8 entry point are the same chain.  They are not bit-identical:
+    the u8 kernel multiplies the raw bytes (as fp32 denormals) and removes the reference's "- 127.0f" once
+    per FIR output (k1_fir4_discrim.cu), the cf32 kernel is handed already-offset floats.  Both are exact
+    products with one rounding per tap, so they differ by rounding noise only: 1e-5 of full scale here,
+    hard symbol decisions identical."""
     iq = H.capture("seed0")
     a, b = fm.FMDemod(H.B, 1), fm.FMDemod(H.B, 1)
     for k in range(6):
@@ -297,8 +302,11 @@ def test_cf32_entry_point_equals_u8_entry_point():
         a.process_u8(blk)
         f = (blk.astype(np.float32) - 127.0).view(np.complex64)     # App::Run, src/app.cpp:56-65
         b.process_cf32(f)
-        assert np.array_equal(a.get(Buf.AUDIO_OUT), b.get(Buf.AUDIO_OUT))
-        assert np.array_equal(a.get(Buf.RDS_PRED_SYM), b.get(Buf.RDS_PRED_SYM))
+        au, ac = a.get(Buf.AUDIO_OUT), b.get(Buf.AUDIO_OUT)
+        assert np.abs(au - ac).max() <= 1e-5 * max(1.0, np.abs(ac).max())
+        su, sc = a.get(Buf.RDS_PRED_SYM), b.get(Buf.RDS_PRED_SYM)
+        assert len(su) == len(sc) and np.array_equal(su > 0, sc > 0)
+        assert np.abs(su - sc).max() <= 1e-4 * max(1e-3, np.abs(sc).max())
     a.close(); b.close()
 
 

@@ -33,5 +33,9 @@ for rep in range(3):
         for k in range(steps): L.fmgpu_enqueue_u8_device(h, cap[(6 + k) % n_in].data_ptr())
         L.fmgpu_signal_external_stream(h, ext); e1.record()
         L.fmgpu_sync(h); torch.cuda.synchronize()
-        print(f"{os.path.basename(path):24s} {e0.elapsed_time(e1) / steps:.4f} ms/step", flush=True)
+        ms = (C.c_float * 6)()
+        L.fmgpu_profile_stages.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_float * 6)]
+        L.fmgpu_profile_stages(h, cap[0].data_ptr(), 8, C.byref(ms))
+        print(f"{os.path.basename(path):24s} {e0.elapsed_time(e1) / steps:.4f} ms/step   serial k1..k6 ms: "
+              + " ".join(f"{x:.4f}" for x in ms), flush=True)
         L.fmgpu_destroy(h)
