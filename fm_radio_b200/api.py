@@ -44,6 +44,8 @@ class Buf(enum.IntEnum):
     BPSK_PLL_RAW_PHASE_ERROR = 19
     BPSK_PLL_PI_PHASE_ERROR = 20
     BPSK_INT_DUMP_FILTER = 21
+    AUDIO_PCM_F32 = 22
+    AUDIO_PCM_S16 = 23
 
 
 _BUF_DTYPE = {
@@ -56,6 +58,7 @@ _BUF_DTYPE = {
     Buf.BPSK_TED_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_TED_PI_PHASE_ERROR: (np.float32, 1),
     Buf.BPSK_PLL_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_PLL_PI_PHASE_ERROR: (np.float32, 1),
     Buf.BPSK_INT_DUMP_FILTER: (np.complex64, 1),
+    Buf.AUDIO_PCM_F32: (np.float32, 2), Buf.AUDIO_PCM_S16: (np.int16, 2),
 }
 
 
@@ -72,6 +75,7 @@ class Control(enum.IntEnum):
     DEEMPHASIS_TUS = 3
     AUDIO_LPR_CUTOFF_HZ = 4
     AUDIO_LMR_CUTOFF_HZ = 5
+    AUDIO_PCM_RATE_HZ = 6
 
 
 class Filter(enum.IntEnum):
@@ -133,6 +137,8 @@ EXPORTED_SYMBOLS = [
     "fmgpu_chan_create", "fmgpu_chan_destroy", "fmgpu_chan_get_b", "fmgpu_chan_get_config", "fmgpu_chan_get_freqs",
     "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
     "fmgpu_chan_wait_external_stream", "fmgpu_chan_sync", "fmgpu_chan_stream", "fmgpu_chan_launch_count",
+    "fmgpu_profile_stages7", "fmgpu_polyphase_us_create", "fmgpu_polyphase_us_process", "fmgpu_resample_linear",
+    "fmgpu_frames_to_s16",
 ]
 
 _lib = None
@@ -169,6 +175,7 @@ def lib():
     L.fmgpu_get_config.argtypes = [vp, C.POINTER(_Config)]
     L.fmgpu_launch_count.argtypes = [vp]
     L.fmgpu_profile_stages.argtypes = [vp, vp, ci, C.POINTER(C.c_float * 6)]
+    L.fmgpu_profile_stages7.argtypes = [vp, vp, ci, C.POINTER(C.c_float * 7)]
     L.fmgpu_launch_count.restype = C.c_longlong
     for name in ("lpf", "hpf"):
         getattr(L, f"fmgpu_create_fir_{name}").argtypes = [vp, ci, C.c_float]
@@ -189,6 +196,10 @@ def lib():
     L.fmgpu_polyphase_get_b.argtypes = [vp]
     L.fmgpu_polyphase_get_b.restype = C.POINTER(C.c_float)
     L.fmgpu_polyphase_ds_process.argtypes = [vp, vp, vp, ci]
+    L.fmgpu_polyphase_us_create.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
+    L.fmgpu_polyphase_us_process.argtypes = [vp, vp, vp, ci]
+    L.fmgpu_resample_linear.argtypes = [vp, ci, vp, ci]
+    L.fmgpu_frames_to_s16.argtypes = [vp, cs, vp]
     L.fmgpu_rds_create.restype = vp
     L.fmgpu_rds_destroy.argtypes = [vp]
     L.fmgpu_rds_destroy.restype = None
@@ -267,6 +278,7 @@ class FMDemod:
         self.depth, self.device = out.pipeline_depth, out.device
         self.keep_intermediates = bool(out.keep_intermediates)
         self.blocks_enqueued = 0
+        self.pcm_rate = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -355,6 +367,8 @@ class FMDemod:
 
     def set_control(self, which: Control, value: float) -> None:
         _check(self.L.fmgpu_set_control(self.h, int(which), float(value)), "fmgpu_set_control")
+        if which == Control.AUDIO_PCM_RATE_HZ:
+            self.pcm_rate = int(value)
 
     def upload_taps(self, which: Filter, b, a=None) -> None:
         b = np.ascontiguousarray(b, np.float32)
@@ -375,11 +389,15 @@ class FMDemod:
         return dict(zip(("baseband", "fm_in", "fm_out", "rds", "audio"), list(r)))
 
     def profile_stages(self, iq_dev, n_blocks: int = 4) -> dict:
-        """Average device ms per kernel with blocks run one at a time (CUDA events inside the library)."""
-        ms = (C.c_float * 6)()
-        _check(self.L.fmgpu_profile_stages(self.h, _ptr(iq_dev), n_blocks, C.byref(ms)), "fmgpu_profile_stages")
+        """Average device ms per kernel with blocks run one at a time (CUDA events inside the library).
+        k7_audio_pcm is present when the audio output stage is on (Control.AUDIO_PCM_RATE_HZ)."""
+        ms = (C.c_float * 7)()
+        _check(self.L.fmgpu_profile_stages7(self.h, _ptr(iq_dev), n_blocks, C.byref(ms)), "fmgpu_profile_stages7")
         self.blocks_enqueued += abs(n_blocks)
-        return dict(zip(("k1_fir4_discrim", "k2_mpx", "k3_pll", "k4_mix_fir", "k5_bpsk", "k6_rds"), [float(x) for x in ms]))
+        out = dict(zip(("k1_fir4_discrim", "k2_mpx", "k3_pll", "k4_mix_fir", "k5_bpsk", "k6_rds", "k7_audio_pcm"), [float(x) for x in ms]))
+        if not self.pcm_rate:
+            del out["k7_audio_pcm"]
+        return out
 
     def partition(self):
         """(SMs reserved for the recurrence stages, SMs of the FIR stages); (0, 0) = not partitioned."""
@@ -582,6 +600,47 @@ class PolyphaseDownsampler:
         y = np.zeros(n_out, dt)
         _check(self.L.fmgpu_polyphase_ds_process(self.h, x.ctypes.data, y.ctypes.data, n_out), "fmgpu_polyphase_ds_process")
         return y
+
+
+class PolyphaseUpsampler:
+    """dsp/polyphase_filter.h:90-185 on the GPU: PolyphaseUpsampler<T>(b, L, K), process(x, y, N)."""
+
+    def __init__(self, b: np.ndarray, L: int, K: int, is_complex: bool):
+        self.lib = lib()
+        self.Lf, self.K, self.is_complex = L, K, bool(is_complex)
+        b = np.ascontiguousarray(b, np.float32)
+        assert b.size == L * K
+        h = C.c_void_p()
+        _check(self.lib.fmgpu_polyphase_us_create(b.ctypes.data, L, K, int(is_complex), C.byref(h)), "fmgpu_polyphase_us_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.fmgpu_polyphase_destroy(self.h)
+            self.h = None
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        dt = np.complex64 if self.is_complex else np.float32
+        x = np.ascontiguousarray(x, dt)
+        y = np.zeros(x.size * self.Lf, dt)
+        _check(self.lib.fmgpu_polyphase_us_process(self.h, x.ctypes.data, y.ctypes.data, x.size), "fmgpu_polyphase_us_process")
+        return y
+
+
+def resample_linear(frames: np.ndarray, n_out: int) -> np.ndarray:
+    """Resample() of audio/resampled_pcm_player.cpp:37-54 on the GPU: frames [n_in, 2] f32 -> [n_out, 2]."""
+    frames = np.ascontiguousarray(frames, np.float32).reshape(-1, 2)
+    out = np.zeros((n_out, 2), np.float32)
+    _check(lib().fmgpu_resample_linear(frames.ctypes.data, frames.shape[0], out.ctypes.data, n_out), "fmgpu_resample_linear")
+    return out
+
+
+def frames_to_s16(frames: np.ndarray) -> np.ndarray:
+    """Audio_Scraper::on_audio_data's float -> int16 conversion (fm_scraper.cpp:74-78) on the GPU."""
+    frames = np.ascontiguousarray(frames, np.float32).reshape(-1, 2)
+    out = np.zeros((frames.shape[0], 2), np.int16)
+    _check(lib().fmgpu_frames_to_s16(frames.ctypes.data, frames.shape[0], out.ctypes.data), "fmgpu_frames_to_s16")
+    return out
 
 
 def _designer(name, n_b, n_a, *args):

@@ -9,6 +9,7 @@
 //   K4b k4b_lmr_phase    per-stream L-R phase-offset update (applied to the next block)
 //   K5  k5_bpsk          per-stream RDS AGC + BPSK symbol synchroniser -> soft symbols
 //   K6  k6_rds           per-stream RDS bit path: symbols -> groups -> PI / PS / RadioText
+//   K7  k7_audio_pcm     audio output stage: 32 kHz frames -> device-rate frames (48 kHz) + int16 PCM
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -207,6 +208,13 @@ cudaError_t launch_k4(const float2* fm_out_iq, const float* pll_dt,
                       float* hist_x_out, float2* hist_m2_out, float2* hist_m3_out,
                       float* lmr_phase, float2* audio_out, float2* rds_out, float* est_partial,
                       float* rds_power_partial, float* dbg_lpr, float* dbg_lmr, const K4Params& p, cudaStream_t st);
+struct K7Entry { int j0; float k; };     // read position of one output frame of Resample(): in[j0]*(1-k) + in[j0+1]*k
+void k7_build_table(int n_in, int n_out, K7Entry* out);
+cudaError_t launch_k7(const float2* audio, const K7Entry* table, float2* pcm_f32, short2* pcm_s16,
+                      int n_in, int n_out, int n_streams, cudaStream_t st);
+cudaError_t launch_frames_to_s16(const float2* frames, short2* out, size_t n, cudaStream_t st);
+cudaError_t launch_polyphase_us(const float* ext, const float* bp, float* y, int L, int K, int n_in,
+                                int is_complex, cudaStream_t st);
 cudaError_t launch_k5(const float2* rds_in, const float* rds_power_partial, float* state, float* pred_sym,
                       int* sym_count, const K5Debug& d, const K5Params& p, cudaStream_t st);
 // K6: RDS bit path on the device (k6_rds.cu); state is an array of rds::State, glog of fmgpu_rds_group

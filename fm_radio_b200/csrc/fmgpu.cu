@@ -50,7 +50,9 @@ struct Slot {
     float* rds_pw_partial = nullptr;
     float* pred_sym = nullptr;     // [S][B/64]
     int* sym_count = nullptr;      // [S]
-    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_E, ev_O;
+    float2* pcm_f32 = nullptr;     // [S][pcm_n] audio at the PCM rate (K7; allocated when the stage is switched on)
+    short2* pcm_s16 = nullptr;     // [S][pcm_n]
+    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_E, ev_O, ev_P;
 };
 
 struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
@@ -61,6 +63,7 @@ struct DebugBufs {                 // keep_intermediates only (single set, not r
 
 struct HostMirror {                // pinned
     float2* audio = nullptr; float* pred_sym = nullptr; int* sym_count = nullptr;
+    short2* pcm_s16 = nullptr;     // K7 on: the int16 PCM block is fetched with the audio
 };
 
 } // namespace
@@ -96,6 +99,9 @@ struct fmgpu_demod {
     HostTaps taps{};
     int ctl_audio_out = 2; float ctl_stereo_mix = 1.0f; int ctl_use_deemph = 0;
     int ctl_deemph_tus = 1, ctl_lpr_hz = 15000, ctl_lmr_hz = 15000;
+    // K7 audio output stage: 0 = off; else output frames per block = (int)((rate / 32000.f) * n32)
+    int ctl_pcm_rate = 0, pcm_rate_built = 0, pcm_n = 0;
+    fm::K7Entry* pcm_table = nullptr;
     bool dirty_deemph = true, dirty_lpr = true, dirty_lmr = true;
     // bookkeeping
     unsigned long long step = 0;   // blocks enqueued so far
@@ -299,7 +305,7 @@ int alloc_all(fmgpu_demod* h) {
         CU(dalloc(&sl.rds_pw_partial, S * h->k4_tiles));
         CU(dalloc(&sl.pred_sym, S * h->n64));
         CU(dalloc(&sl.sym_count, S));
-        cudaEvent_t* evs[7] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_E, &sl.ev_O };
+        cudaEvent_t* evs[8] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_E, &sl.ev_O, &sl.ev_P };
         for (auto* ev : evs) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         HostMirror& m = h->mirrors[i];
         CU(cudaMallocHost((void**)&m.audio, S * h->n32 * sizeof(float2)));
@@ -326,17 +332,18 @@ void free_all(fmgpu_demod* h) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int i = 0; i < 2; i++) { F(h->k1_hist[i]); F(h->k4_hist_x[i]); F(h->k4_hist_m2[i]); F(h->k4_hist_m3[i]); }
     F(h->k2_hist_demod); F(h->k2_hist_out); F(h->k2_scal); F(h->pll_state); F(h->bpsk_state); F(h->lmr_phase); F(h->in_f32);
-    F(h->rds_state); F(h->rds_glog); F(h->rds_blog); F(h->rds_tables);
+    F(h->rds_state); F(h->rds_glog); F(h->rds_blog); F(h->rds_tables); F(h->pcm_table);
     for (auto& sl : h->slots) {
         F(sl.in_u8); F(sl.fm_demod); F(sl.fm_out_iq); F(sl.theta); F(sl.power); F(sl.pll_dt); F(sl.audio); F(sl.rds);
-        F(sl.est_partial); F(sl.rds_pw_partial); F(sl.pred_sym); F(sl.sym_count);
-        cudaEvent_t evs[7] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_O };
+        F(sl.est_partial); F(sl.rds_pw_partial); F(sl.pred_sym); F(sl.sym_count); F(sl.pcm_f32); F(sl.pcm_s16);
+        cudaEvent_t evs[8] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_O, sl.ev_P };
         for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     }
     for (auto& m : h->mirrors) {
         if (m.audio) cudaFreeHost(m.audio);
         if (m.pred_sym) cudaFreeHost(m.pred_sym);
         if (m.sym_count) cudaFreeHost(m.sym_count);
+        if (m.pcm_s16) cudaFreeHost(m.pcm_s16);
     }
     DebugBufs& d = h->dbg;
     F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr);
@@ -345,6 +352,38 @@ void free_all(fmgpu_demod* h) {
     cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) if (st) cudaStreamDestroy(st);
     destroy_partition(h);
+}
+
+int sync_all(fmgpu_demod* h);
+
+// K7's buffers and read-position table, (re)built when FMGPU_CTL_AUDIO_PCM_RATE_HZ changes.
+int prepare_pcm(fmgpu_demod* h) {
+    if (h->pcm_rate_built == h->ctl_pcm_rate) return FMGPU_OK;
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    // Resampled_PCM_Player::ConsumeBuffer (audio/resampled_pcm_player.cpp:22-24): L = out / in, M = (int)(L * N)
+    const float L = (float)h->ctl_pcm_rate / 32000.0f;
+    const int M = (int)(L * (float)h->n32);
+    const size_t S = h->S;
+    for (int i = 0; i < h->depth; i++) {
+        Slot& sl = h->slots[i];
+        HostMirror& m = h->mirrors[i];
+        if (sl.pcm_f32) cudaFree(sl.pcm_f32);
+        if (sl.pcm_s16) cudaFree(sl.pcm_s16);
+        if (m.pcm_s16) cudaFreeHost(m.pcm_s16);
+        sl.pcm_f32 = nullptr; sl.pcm_s16 = nullptr; m.pcm_s16 = nullptr;
+        CU(dalloc(&sl.pcm_f32, S * M));
+        CU(dalloc(&sl.pcm_s16, S * M));
+        CU(cudaMallocHost((void**)&m.pcm_s16, S * M * sizeof(short2)));
+    }
+    std::vector<fm::K7Entry> tab((size_t)M);
+    fm::k7_build_table(h->n32, M, tab.data());
+    if (h->pcm_table) cudaFree(h->pcm_table);
+    h->pcm_table = nullptr;
+    CU(cudaMalloc((void**)&h->pcm_table, sizeof(fm::K7Entry) * (size_t)M));
+    CU(cudaMemcpy(h->pcm_table, tab.data(), sizeof(fm::K7Entry) * (size_t)M, cudaMemcpyHostToDevice));
+    h->pcm_n = M;
+    h->pcm_rate_built = h->ctl_pcm_rate;
+    return FMGPU_OK;
 }
 
 // Enqueue the chain for one block whose input is already ordered on stA (or signalled by ev_H).
@@ -433,6 +472,15 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     }
     if (prof) CU(cudaEventRecord(prof[6], h->stC));
     CU(cudaEventRecord(sl.ev_C, h->stC));
+    // ---- K7 (audio output stage, off by default): after ev_C, so the RDS stages do not wait for it ----
+    if (h->ctl_pcm_rate > 0) {
+        const int rc7 = prepare_pcm(h);
+        if (rc7 != FMGPU_OK) return rc7;
+        CU(fm::launch_k7(sl.audio, h->pcm_table, sl.pcm_f32, sl.pcm_s16, h->n32, h->pcm_n, h->S, h->stC));
+        h->launches++;
+    }
+    if (prof) CU(cudaEventRecord(prof[10], h->stC));
+    CU(cudaEventRecord(sl.ev_P, h->stC));
 
     // ---- stage D: K5 ----
     CU(cudaStreamWaitEvent(h->stD, sl.ev_C, 0));
@@ -480,6 +528,10 @@ int fetch_slot(fmgpu_demod* h, int slot) {
     CU(cudaMemcpyAsync(m.audio, sl.audio, S * h->n32 * sizeof(float2), cudaMemcpyDeviceToHost, h->stO));
     CU(cudaMemcpyAsync(m.pred_sym, sl.pred_sym, S * h->n64 * sizeof(float), cudaMemcpyDeviceToHost, h->stO));
     CU(cudaMemcpyAsync(m.sym_count, sl.sym_count, S * sizeof(int), cudaMemcpyDeviceToHost, h->stO));
+    if (h->pcm_rate_built > 0 && h->ctl_pcm_rate == h->pcm_rate_built) {
+        CU(cudaStreamWaitEvent(h->stO, sl.ev_P, 0));
+        CU(cudaMemcpyAsync(m.pcm_s16, sl.pcm_s16, S * h->pcm_n * sizeof(short2), cudaMemcpyDeviceToHost, h->stO));
+    }
     CU(cudaEventRecord(sl.ev_O, h->stO));
     h->last_fetched_slot = slot;
     return FMGPU_OK;
@@ -631,6 +683,13 @@ int fmgpu_stream_wait_input_free(fmgpu_demod* h, void* cuda_stream) {
 int fmgpu_set_last_error_(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 
 int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[6]) {
+    float m7[7];
+    const int rc = fmgpu_profile_stages7(h, iq_dev, n_blocks, m7);
+    if (rc == FMGPU_OK && ms) std::memcpy(ms, m7, 6 * sizeof(float));
+    return rc;
+}
+
+int fmgpu_profile_stages7(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[7]) {
     if (!h || !iq_dev || !ms || n_blocks == 0) return fail(FMGPU_ERR_ARG, "profile_stages: bad argument");
     CU(cudaSetDevice(h->device));
     // n_blocks > 0: blocks one at a time (kernel times in isolation).  n_blocks < 0: |n_blocks| blocks
@@ -638,25 +697,26 @@ int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, fl
     // share the GPU with the other stages' kernels (averaged over the second half of the run).
     const bool piped = n_blocks < 0;
     const int n = piped ? -n_blocks : n_blocks;
-    std::vector<cudaEvent_t> ev((size_t)10 * n);
+    constexpr int NE = 11;
+    std::vector<cudaEvent_t> ev((size_t)NE * n);
     for (auto& e : ev) CU(cudaEventCreate(&e));
-    double acc[6] = { 0, 0, 0, 0, 0, 0 };
-    const int pairs[6][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 }, { 8, 9 } };
+    double acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    const int pairs[7][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 }, { 8, 9 }, { 6, 10 } };
     if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
     for (int b = 0; b < n; b++) {
-        const int rc = enqueue_chain(h, iq_dev, true, false, &ev[(size_t)10 * b]);
+        const int rc = enqueue_chain(h, iq_dev, true, false, &ev[(size_t)NE * b]);
         if (rc < 0) return rc;
         if (!piped && sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
     }
     if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
     const int b0 = piped ? n / 2 : 0;
     for (int b = b0; b < n; b++)
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < 7; i++) {
             float t = 0.0f;
-            CU(cudaEventElapsedTime(&t, ev[(size_t)10 * b + pairs[i][0]], ev[(size_t)10 * b + pairs[i][1]]));
+            CU(cudaEventElapsedTime(&t, ev[(size_t)NE * b + pairs[i][0]], ev[(size_t)NE * b + pairs[i][1]]));
             acc[i] += t;
         }
-    for (int i = 0; i < 6; i++) ms[i] = (float)(acc[i] / (n - b0));
+    for (int i = 0; i < 7; i++) ms[i] = (float)(acc[i] / (n - b0));
     for (auto& e : ev) cudaEventDestroy(e);
     return FMGPU_OK;
 }
@@ -708,6 +768,8 @@ static bool buf_info(const fmgpu_demod* h, fmgpu_buffer b, BufInfo* bi, const vo
     case FMGPU_BUF_FM_DEMOD: *bi = { 4, h->n4 }; *dev = sl.fm_demod; return true;
     case FMGPU_BUF_FM_OUT_IQ: *bi = { 8, h->n8 }; *dev = sl.fm_out_iq; return true;
     case FMGPU_BUF_PLL_DT: *bi = { 4, h->n8 }; *dev = sl.pll_dt; return true;
+    case FMGPU_BUF_AUDIO_PCM_F32: if (!sl.pcm_f32) return false; *bi = { 8, h->pcm_n }; *dev = sl.pcm_f32; return true;
+    case FMGPU_BUF_AUDIO_PCM_S16: if (!sl.pcm_s16) return false; *bi = { 4, h->pcm_n }; *dev = sl.pcm_s16; return true;
     default: break;
     }
     if (!keep) return false;
@@ -743,12 +805,15 @@ int fmgpu_get_buffer(fmgpu_demod* h, int stream, fmgpu_buffer buf, const void** 
     case FMGPU_BUF_AUDIO_OUT: *host_ptr = m.audio + (size_t)stream * h->n32; *n_elems = h->n32; return FMGPU_OK;
     case FMGPU_BUF_RDS_PRED_SYM: *host_ptr = m.pred_sym + (size_t)stream * h->n64; *n_elems = (size_t)count; return FMGPU_OK;
     case FMGPU_BUF_RDS_SYM_COUNT: *host_ptr = m.sym_count + stream; *n_elems = 1; return FMGPU_OK;
+    case FMGPU_BUF_AUDIO_PCM_S16:
+        if (!m.pcm_s16 || h->pcm_rate_built <= 0) return fail(FMGPU_ERR_STATE, "get_buffer: the audio output stage is off (FMGPU_CTL_AUDIO_PCM_RATE_HZ)");
+        *host_ptr = m.pcm_s16 + (size_t)stream * h->pcm_n; *n_elems = (size_t)h->pcm_n; return FMGPU_OK;
     default: break;
     }
     // Everything else is copied on demand from the device (GUI / test path, not the hot path).
     BufInfo bi{}; const void* dev = nullptr;
     if (!buf_info(h, buf, &bi, &dev, slot))
-        return fail(FMGPU_ERR_STATE, "get_buffer: buffer needs keep_intermediates = 1");
+        return fail(FMGPU_ERR_STATE, "get_buffer: buffer needs keep_intermediates = 1 (GUI buffers) or FMGPU_CTL_AUDIO_PCM_RATE_HZ > 0 (PCM buffers)");
     CU(cudaSetDevice(h->device));
     if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
     const size_t bytes = bi.elem * (size_t)bi.per_stream;
@@ -797,6 +862,9 @@ int fmgpu_set_control(fmgpu_demod* h, fmgpu_control which, double value) {
     case FMGPU_CTL_DEEMPHASIS_TUS: h->ctl_deemph_tus = (int)value; h->dirty_deemph = true; break;
     case FMGPU_CTL_AUDIO_LPR_CUTOFF_HZ: h->ctl_lpr_hz = (int)value; h->dirty_lpr = true; break;
     case FMGPU_CTL_AUDIO_LMR_CUTOFF_HZ: h->ctl_lmr_hz = (int)value; h->dirty_lmr = true; break;
+    case FMGPU_CTL_AUDIO_PCM_RATE_HZ:
+        if ((int)value != 0 && ((int)value < 8000 || (int)value > 192000)) return fail(FMGPU_ERR_ARG, "set_control: audio PCM rate must be 0 (off) or 8000..192000 Hz");
+        h->ctl_pcm_rate = (int)value; break;
     default: return fail(FMGPU_ERR_ARG, "set_control: unknown id");
     }
     return FMGPU_OK;
@@ -929,6 +997,7 @@ int fmgpu_rds_device_get_db(fmgpu_demod* h, int stream, uint16_t* pi, char ps8[8
 // ---- stand-alone polyphase decimator (dsp/polyphase_filter.h:9-87) ----
 struct fmgpu_polyphase {
     int M, K, NN, is_complex;
+    int up = 0;                    // 1: PolyphaseUpsampler (M holds L; hist holds the last K inputs)
     std::vector<float> b;          // host taps (get_b)
     std::vector<float> hist;       // last NN inputs
     float* d_ext = nullptr; float* d_taps = nullptr; float* d_y = nullptr;
@@ -975,6 +1044,74 @@ int fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* y
     // new history = last NN samples of (hist ++ x)
     CU(cudaMemcpy(f->hist.data(), f->d_ext + n_in * C, (size_t)f->NN * C * 4, cudaMemcpyDeviceToHost));
     return FMGPU_OK;
+}
+
+// ---- PolyphaseUpsampler<T> (dsp/polyphase_filter.h:90-185) ----
+int fmgpu_polyphase_us_create(const float* b, int L, int K, int is_complex, fmgpu_polyphase** out) {
+    if (!out || !b || L < 1 || K < 1) return fail(FMGPU_ERR_ARG, "polyphase_us_create: bad argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(FMGPU_ERR_CUDA, "polyphase_us_create: no CUDA device (there is no CPU fallback)");
+    auto* f = new fmgpu_polyphase();
+    f->M = L; f->K = K; f->NN = L * K; f->is_complex = is_complex ? 1 : 0; f->up = 1;
+    f->b.assign(f->NN, 0.0f);
+    // the constructor's repack (:106-116): phase-contiguous taps, gain L
+    for (int phase = 0; phase < L; phase++) {
+        const int phase_c = (L - 1) - phase;
+        for (int i = 0; i < K; i++) f->b[(size_t)phase_c * K + i] = b[(f->NN - 1) - (phase + i * L)] * (float)L;
+    }
+    f->hist.assign((size_t)K * (is_complex ? 2 : 1), 0.0f);
+    cudaError_t e = cudaMalloc((void**)&f->d_taps, f->NN * sizeof(float));
+    if (e != cudaSuccess) { delete f; return fail(FMGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = f;
+    return FMGPU_OK;
+}
+
+int fmgpu_polyphase_us_process(fmgpu_polyphase* f, const float* x_host, float* y_host, int n_in) {
+    if (!f || !f->up || !x_host || !y_host || n_in < 0) return fail(FMGPU_ERR_ARG, "polyphase_us_process: bad argument");
+    if (n_in == 0) return FMGPU_OK;
+    const int C = f->is_complex ? 2 : 1, L = f->M, K = f->K;
+    const size_t ext_floats = ((size_t)K + n_in) * C, y_floats = (size_t)n_in * L * C;
+    if (f->cap_ext < ext_floats) { if (f->d_ext) cudaFree(f->d_ext); CU(cudaMalloc((void**)&f->d_ext, ext_floats * 4)); f->cap_ext = ext_floats; }
+    if (f->cap_y < y_floats) { if (f->d_y) cudaFree(f->d_y); CU(cudaMalloc((void**)&f->d_y, y_floats * 4)); f->cap_y = y_floats; }
+    CU(cudaMemcpy(f->d_taps, f->b.data(), f->NN * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(f->d_ext, f->hist.data(), (size_t)K * C * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(f->d_ext + (size_t)K * C, x_host, (size_t)n_in * C * 4, cudaMemcpyHostToDevice));
+    CU(fm::launch_polyphase_us(f->d_ext, f->d_taps, f->d_y, L, K, n_in, f->is_complex, 0));
+    CU(cudaMemcpy(y_host, f->d_y, y_floats * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(f->hist.data(), f->d_ext + (size_t)n_in * C, (size_t)K * C * 4, cudaMemcpyDeviceToHost));   // last K of (hist ++ x)
+    return FMGPU_OK;
+}
+
+// ---- Resample() and the scraper's int16 conversion, stand-alone (host buffers) ----
+int fmgpu_resample_linear(const float* frames_in_host, int n_in, float* frames_out_host, int n_out) {
+    if (!frames_in_host || !frames_out_host || n_in < 1 || n_out < 0) return fail(FMGPU_ERR_ARG, "resample_linear: bad argument");
+    if (n_out == 0) return FMGPU_OK;
+    std::vector<fm::K7Entry> tab((size_t)n_out);
+    fm::k7_build_table(n_in, n_out, tab.data());
+    if (tab.back().j0 >= n_in) return fail(FMGPU_ERR_ARG, "resample_linear: read position leaves the input (the reference would read out of bounds)");
+    float2* d_in = nullptr; float2* d_out = nullptr; fm::K7Entry* d_tab = nullptr;
+    auto done = [&](int rc) { if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out); if (d_tab) cudaFree(d_tab); return rc; };
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(FMGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    CUF(cudaMalloc((void**)&d_in, (size_t)n_in * 8)); CUF(cudaMalloc((void**)&d_out, (size_t)n_out * 8));
+    CUF(cudaMalloc((void**)&d_tab, (size_t)n_out * sizeof(fm::K7Entry)));
+    CUF(cudaMemcpy(d_in, frames_in_host, (size_t)n_in * 8, cudaMemcpyHostToDevice));
+    CUF(cudaMemcpy(d_tab, tab.data(), (size_t)n_out * sizeof(fm::K7Entry), cudaMemcpyHostToDevice));
+    CUF(fm::launch_k7(d_in, d_tab, d_out, nullptr, n_in, n_out, 1, 0));
+    CUF(cudaMemcpy(frames_out_host, d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost));
+    return done(FMGPU_OK);
+}
+
+int fmgpu_frames_to_s16(const float* frames_host, size_t n_frames, int16_t* out_host) {
+    if (!frames_host || !out_host) return fail(FMGPU_ERR_ARG, "frames_to_s16: bad argument");
+    if (n_frames == 0) return FMGPU_OK;
+    float2* d_in = nullptr; short2* d_out = nullptr;
+    auto done = [&](int rc) { if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out); return rc; };
+    CUF(cudaMalloc((void**)&d_in, n_frames * 8)); CUF(cudaMalloc((void**)&d_out, n_frames * 4));
+    CUF(cudaMemcpy(d_in, frames_host, n_frames * 8, cudaMemcpyHostToDevice));
+    CUF(fm::launch_frames_to_s16(d_in, d_out, n_frames, 0));
+    CUF(cudaMemcpy(out_host, d_out, n_frames * 4, cudaMemcpyDeviceToHost));
+    return done(FMGPU_OK);
+#undef CUF
 }
 
 } // extern "C"

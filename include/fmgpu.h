@@ -122,6 +122,9 @@ typedef enum fmgpu_buffer {
     FMGPU_BUF_BPSK_PLL_RAW_PHASE_ERROR, /* f32[B/64]                                            */
     FMGPU_BUF_BPSK_PLL_PI_PHASE_ERROR,  /* f32[B/64]                                            */
     FMGPU_BUF_BPSK_INT_DUMP_FILTER, /* cf32[B/64]                                               */
+    /* audio output stage K7 (needs FMGPU_CTL_AUDIO_PCM_RATE_HZ > 0), M = (int)((rate / 32000.f) * (B/32)) */
+    FMGPU_BUF_AUDIO_PCM_F32,        /* Frame<float>[M]: Resample() of GetAudioOut (audio/resampled_pcm_player.cpp:37-54) */
+    FMGPU_BUF_AUDIO_PCM_S16,        /* Frame<int16_t>[M]: the same frames as Audio_Scraper writes them (fm_scraper.cpp:74-78); pinned mirror */
     FMGPU_BUF__COUNT
 } fmgpu_buffer;
 
@@ -147,7 +150,12 @@ typedef enum fmgpu_control {
     FMGPU_CTL_USE_DEEMPHASIS,           /* bool, default 0                                      */
     FMGPU_CTL_DEEMPHASIS_TUS,           /* int microseconds; redesigns the 1-pole IIR (:337-352)*/
     FMGPU_CTL_AUDIO_LPR_CUTOFF_HZ,      /* int Hz; redesigns the L+R FIR (:355-370)             */
-    FMGPU_CTL_AUDIO_LMR_CUTOFF_HZ       /* int Hz; redesigns the L-R FIR (:373-388)             */
+    FMGPU_CTL_AUDIO_LMR_CUTOFF_HZ,      /* int Hz; redesigns the L-R FIR (:373-388)             */
+    FMGPU_CTL_AUDIO_PCM_RATE_HZ         /* int Hz, default 0 = off.  > 0 switches on the audio output stage (kernel K7): every
+                                           block's GetAudioOut is resampled from 32 kHz to this rate exactly as
+                                           Resampled_PCM_Player::ConsumeBuffer does for the sound device
+                                           (audio/resampled_pcm_player.cpp:15-28, 37-54; the drivers use 48000) and converted
+                                           to int16 as Audio_Scraper::on_audio_data (fm_scraper.cpp:74-78).  8000..192000. */
 } fmgpu_control;
 /* Latched at the next process/enqueue call (the reference reads controls at Process entry,
  * UpdateFilters, broadcast_fm_demod.cpp:316).  Applies to every stream of the handle. */
@@ -182,6 +190,8 @@ int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out);
  * enqueued back to back as in production, i.e. the kernels' times while the stages overlap.
  * Advances the demodulator state. */
 int fmgpu_profile_stages(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[6]);
+/* The same with ms[6] = K7 (audio output stage; 0 when it is off). */
+int fmgpu_profile_stages7(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, float ms[7]);
 /* SM partition of the handle: sms[0] = SMs reserved for the per-stream recurrences (pilot PLL, BPSK
  * synchroniser, RDS bit path), sms[1] = SMs of the FIR stages; {0, 0} when the device is not
  * partitioned (FMGPU_NO_PARTITION=1 in the environment, or the driver has no green contexts). */
@@ -223,6 +233,19 @@ int  fmgpu_polyphase_ds_create(int M, int K, int is_complex, fmgpu_polyphase** o
 void fmgpu_polyphase_destroy(fmgpu_polyphase* f);
 float* fmgpu_polyphase_get_b(fmgpu_polyphase* f);       /* host array of M*K taps, like get_b() */
 int  fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* y_host, int n_out);
+/* PolyphaseUpsampler<T>(const float* b, L, K) and ::process(x, y, N) (dsp/polyphase_filter.h:90-185): b holds L*K
+ * prototype taps in the designers' order (the constructor's repack and gain L are applied inside); y receives
+ * n_in*L samples.  State: the last K inputs.  Destroy with fmgpu_polyphase_destroy. */
+int  fmgpu_polyphase_us_create(const float* b, int L, int K, int is_complex, fmgpu_polyphase** out);
+int  fmgpu_polyphase_us_process(fmgpu_polyphase* f, const float* x_host, float* y_host, int n_in);
+
+/* ---- audio output helpers, stand-alone (host buffers; the in-chain version is FMGPU_CTL_AUDIO_PCM_RATE_HZ) ----
+ * fmgpu_resample_linear = Resample(buf_in, buf_out) of audio/resampled_pcm_player.cpp:37-54 on stereo
+ * Frame<float> arrays (2 floats per frame): linear interpolation at read positions j += (float)n_in/(float)n_out.
+ * fmgpu_frames_to_s16 = Audio_Scraper::on_audio_data's conversion (fm_scraper.cpp:74-78):
+ * (int16_t)(channel * (32767 * 0.95f)), truncating, wrapping like the reference's x86 build when out of range. */
+int  fmgpu_resample_linear(const float* frames_in_host, int n_in, float* frames_out_host, int n_out);
+int  fmgpu_frames_to_s16(const float* frames_host, size_t n_frames, int16_t* out_host);
 
 /* ---- RDS bit path on the host (differential_manchester_decoder.h:25-59, rds_group_sync.cpp,
  * crc10.cpp, and the PI/PTY/PS/RT subset of rds_decoder.cpp) ---------------------------------- */

@@ -87,6 +87,8 @@ def lib(kind: str = "ref"):
         L.polyphase_ds_f32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.polyphase_ds_cf32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.polyphase_us_f32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.resample_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.frames_to_s16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         if kind == "port":
             L.set_taps.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         _libs[kind] = L

@@ -171,6 +171,43 @@ void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* 
     for (int c = 0; c < n_calls; c++) polyds_process(&f, x + (size_t)c*N_out*M*2, y + (size_t)c*N_out*2, N_out);
     polyds_free(&f);
 }
+/* audio/resampled_pcm_player.cpp:37-54  Resample(buf_in, buf_out) on stereo Frame<float> arrays:
+ * the read position j walks in float (j += step), j0 = (int)j, k = j - j0, the last frame is held;
+ * out = f0*(1-k) + f1*k with one rounding per Frame operator (audio/frame.h:10-16, 42-49). */
+void fmo_resample_linear(const float* in, int n_in, float* out, int n_out) {
+    const float step = (float)n_in / (float)n_out;
+    float j = 0.0f;
+    for (int i = 0; i < n_out; i++) {
+        const int j0 = (int)j;
+        const int j1 = j0 + 1;
+        const float* f0 = in + 2*(size_t)j0;
+        const float* f1 = (j1 < n_in) ? in + 2*(size_t)j1 : f0;
+        const float k = j - (float)j0;
+        const float a = 1.0f - k;
+        for (int c = 0; c < 2; c++) {
+            const float u = f0[c]*a, v = f1[c]*k;
+            out[2*(size_t)i + c] = u + v;
+        }
+        j += step;
+    }
+}
+
+/* fm_scraper.cpp:74-78  convert_buffer[i] = Frame<int16_t>(data[i]*CONVERT_RESCALE), CONVERT_RESCALE =
+ * 32767 * 0.95f; the Frame conversion is a static_cast per channel (audio/frame.h:67-74).  Out of the int16
+ * range the C++ cast is undefined; the reference's x86 build truncates (cvttss2si, 0x80000000 when out of
+ * the int32 range or NaN) and keeps the low 16 bits -- restated here explicitly so it does not depend on
+ * this file's compiler. */
+void fmo_frames_to_s16(const float* frames, size_t n_frames, int16_t* out) {
+    const float scale = 32767.0f * 0.95f;
+    for (size_t i = 0; i < 2*n_frames; i++) {
+        const float v = frames[i] * scale;
+        int32_t q;
+        if (v != v || v >= 2147483648.0f || v <= -2147483904.0f) q = (int32_t)0x80000000u;
+        else q = (int32_t)v;                         /* truncation toward zero */
+        out[i] = (int16_t)(uint16_t)((uint32_t)q & 0xFFFFu);
+    }
+}
+
 /* dsp/polyphase_filter.h:90-185 PolyphaseUpsampler<float>: coefficient repack (:108-117) and
  * y[i*L+phase] = sum_{j<K} X[i-(K-1)+j] * bp[phase*K + j]. */
 void fmo_polyphase_us_f32(int L, int K, const float* _b, const float* x, float* y, int N_in, int n_calls) {

@@ -58,6 +58,8 @@ void fmo_create_iir_peak_1_filter(float* b, float* a, float k, float r);
 void fmo_polyphase_ds_f32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls);
 void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls);
 void fmo_polyphase_us_f32(int L, int K, const float* b, const float* x, float* y, int N_in, int n_calls);
+void fmo_resample_linear(const float* in, int n_in, float* out, int n_out);
+void fmo_frames_to_s16(const float* frames, size_t n_frames, int16_t* out);
 
 /* wideband channelizer oracle (config 4; no reference counterpart): float64 shift + decimating FIR */
 void fmo_channelize_f64(const uint8_t* iq, size_t n_in, const uint8_t* hist, uint64_t n0, int D, int NN,

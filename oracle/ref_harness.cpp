@@ -25,6 +25,9 @@
 #include "fm_demod/bpsk_synchroniser.h"
 #undef private
 #include "dsp/filter_designer.h"
+#include "audio/frame.h"
+#include <limits>
+void Resample(tcb::span<const Frame<float>> buf_in, tcb::span<Frame<float>> buf_out);   // audio/resampled_pcm_player.cpp:3
 #include "rds_decoder/differential_manchester_decoder.h"
 #include "rds_decoder/rds_decoding_chain.h"
 
@@ -268,6 +271,19 @@ void fmref_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float
 void fmref_polyphase_us_f32(int L, int K, const float* b, const float* x, float* y, int N_in, int n_calls) {
     PolyphaseUpsampler<float> f(b, L, K);
     for (int c = 0; c < n_calls; c++) f.process(x + (size_t)c*N_in, y + (size_t)c*N_in*L, N_in);
+}
+
+// audio/resampled_pcm_player.cpp:37-54: the reference's own Resample(), compiled from its source file.
+void fmref_resample_linear(const float* in, int n_in, float* out, int n_out) {
+    Resample(tcb::span<const Frame<float>>((const Frame<float>*)in, (size_t)n_in),
+             tcb::span<Frame<float>>((Frame<float>*)out, (size_t)n_out));
+}
+// fm_scraper.cpp:74-78, the statement itself (Audio_Scraper needs a filesystem target, so the loop is lifted).
+void fmref_frames_to_s16(const float* frames, size_t n_frames, int16_t* out) {
+    constexpr float CONVERT_RESCALE = float(std::numeric_limits<int16_t>::max()) * 0.95f;
+    auto* data = (const Frame<float>*)frames;
+    auto* dst = (Frame<int16_t>*)out;
+    for (size_t i = 0; i < n_frames; i++) dst[i] = Frame<int16_t>(data[i]*CONVERT_RESCALE);
 }
 
 } // extern "C"
