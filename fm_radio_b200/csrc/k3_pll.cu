@@ -15,8 +15,12 @@
 //                 -> complex multiply -> atan2f -> e                         (~50 dependent ops)
 //   first cut   e -> fma, min, max -> fma, min, max -> fma -> fma -> add -> 3-op wrap -> fma -> e
 //               13 dependent ops of 4-5 cycles; measured 101 cycles per sample on B200
-//   this kernel w -> {fma.sat, fma.sat} -> sub -> {fma.sat, fma.sat} -> sub -> fma -> fma -> 3-op wrap -> w
-//               9 dependent ops, all on the FMA pipe (no FMA<->ALU pipe crossings)
+//   exact body  w -> {fma.sat, fma.sat} -> sub -> {fma.sat, fma.sat} -> sub -> fma -> fma -> 3-op wrap -> w
+//               9 dependent ops, all on the FMA pipe (no FMA<->ALU pipe crossings); 57 cycles per sample
+//   this kernel w -> {fma, fma} -> fma -> fma -> fma -> 3-op wrap -> w
+//               7 dependent ops: groups of 32 samples run with the clamps taken as inactive (exact whenever
+//               they are: clamp(x) returns x bit for bit for |x| <= 1) and are redone by the exact body from
+//               the saved state if a clamp would have acted -- never, for a locking or locked loop
 // using
 //   * theta[n] = arg(pilot[n])/2pi precomputed in parallel by K2 (arg(a*b) = arg(a)+arg(b); arg of
 //     the reference's oscillator sample is 2 pi t up to its 4e-8 polynomial error), so the phase
@@ -104,36 +108,72 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
             // L2 by now: pull the lane's 128-byte line of group i + 4G into L2 (DRAM latency under
             // load exceeds the ~1500 cycles one group of look-ahead buys; measured, see profiles/)
             if (i + 4 * G < p.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(th4 + ((i + 4 * G) >> 2)));
+            // Speculative pass: both clamps taken as inactive, which shortens the chain from 9 to 7 dependent
+            // ops (w -> {fma, fma} -> fma -> fma -> fma -> 3-op wrap).  clamp(x) = sat(x) - sat(-x) returns x
+            // itself, bit for bit, whenever |x| <= 1, so the pass is exact unless a clamp would have acted
+            // (or a NaN met fma.sat); that is tracked off the chain, and the group is then redone from the
+            // saved state by the exact body.  A locked or locking loop never clamps: |PI| stays below 0.05.
+            const float sx1 = x1, sy1 = y1, sinteg = integ, st = t, sw = w;
+            bool exact_needed = false;
 #pragma unroll
             for (int q = 0; q < G / 4; q++) {
                 const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
                 float dt[4], raw[4], pie[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    // off the chain: everything that depends only on the previous iteration's t, x1, y1
                     const float m = fmaf(x1, b0t, y1 * a0);
-                    const float a = th[j] + t;                              // |a| <= 1
-                    // IIR1 y = xn[0]*b[0] + yn[0]*a[0] + xn[1]*b[1] on the newest error
+                    const float a = th[j] + t;
                     const float lpf = fmaf(w, b1t, m);
-                    // integrator with clamp(-1, 1) = sat(x) - sat(-x)
-                    integ = fma_sat(ci, w, integ) - fma_sat(-ci, w, -integ);
+                    integ = fmaf(ci, w, integ);
                     x1 = w; y1 = lpf;
-                    // PI error and PLL_Mixer::Update's clamp, the same way
-                    const float control = fma_sat(lpf, Kp, integ) - fma_sat(-lpf, Kp, -integ);
-                    // NCO (pll_mixer.cpp:12-21), in the reference's rounding structure -- freq is
-                    // quantised to ulp(19000) = 2^-9 Hz and the loop's static phase error (1 rad per
-                    // Hz of NCO bias) follows that quantisation: t += KTs*freq; t -= round(t)
+                    const float control = fmaf(lpf, Kp, integ);
+                    exact_needed = exact_needed || !(fabsf(integ) <= 1.0f) || !(fabsf(control) <= 1.0f);
                     const float freq = fmaf(control, f_gain, f_center);
                     t = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, t));
-                    // phase detector: arg(pilot * pll) / 2pi = wrap(theta + t), straight from freq
                     w = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, a));
                     dt[j] = t;
-                    if (KEEP) { raw[j] = w * TWO_PI_F; pie[j] = fmaf(lpf, Kp, integ); }
+                    if (KEEP) { raw[j] = w * TWO_PI_F; pie[j] = control; }
                 }
                 dt4[(i >> 2) + q] = make_float4(dt[0], dt[1], dt[2], dt[3]);
                 if (KEEP) {
                     raw4[(i >> 2) + q] = make_float4(raw[0], raw[1], raw[2], raw[3]);
                     pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
+                }
+            }
+            if (exact_needed) {
+                x1 = sx1; y1 = sy1; integ = sinteg; t = st; w = sw;
+#pragma unroll 1
+                for (int q = 0; q < G / 4; q++) {
+                    const float4 c4 = th4[(i >> 2) + q];
+                    const float th[4] = { c4.x, c4.y, c4.z, c4.w };
+                    float dt[4], raw[4], pie[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        // off the chain: everything that depends only on the previous iteration's t, x1, y1
+                        const float m = fmaf(x1, b0t, y1 * a0);
+                        const float a = th[j] + t;                              // |a| <= 1
+                        // IIR1 y = xn[0]*b[0] + yn[0]*a[0] + xn[1]*b[1] on the newest error
+                        const float lpf = fmaf(w, b1t, m);
+                        // integrator with clamp(-1, 1) = sat(x) - sat(-x)
+                        integ = fma_sat(ci, w, integ) - fma_sat(-ci, w, -integ);
+                        x1 = w; y1 = lpf;
+                        // PI error and PLL_Mixer::Update's clamp, the same way
+                        const float control = fma_sat(lpf, Kp, integ) - fma_sat(-lpf, Kp, -integ);
+                        // NCO (pll_mixer.cpp:12-21), in the reference's rounding structure -- freq is
+                        // quantised to ulp(19000) = 2^-9 Hz and the loop's static phase error (1 rad per
+                        // Hz of NCO bias) follows that quantisation: t += KTs*freq; t -= round(t)
+                        const float freq = fmaf(control, f_gain, f_center);
+                        t = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, t));
+                        // phase detector: arg(pilot * pll) / 2pi = wrap(theta + t), straight from freq
+                        w = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, a));
+                        dt[j] = t;
+                        if (KEEP) { raw[j] = w * TWO_PI_F; pie[j] = fmaf(lpf, Kp, integ); }
+                    }
+                    dt4[(i >> 2) + q] = make_float4(dt[0], dt[1], dt[2], dt[3]);
+                    if (KEEP) {
+                        raw4[(i >> 2) + q] = make_float4(raw[0], raw[1], raw[2], raw[3]);
+                        pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
+                    }
                 }
             }
         }
