@@ -282,12 +282,10 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
                 }
             }
             er = fmaf(er, K1_UNSCALE, p.neg_dc); ei = fmaf(ei, K1_UNSCALE, p.neg_dc);
-            // stream start: the reference's prev_theta is 0 (fm_demod.cpp:41, zero FIR history gives atan2(0, 0));
-            // here the all-127 history sums to rounding noise instead of an exact 0, so the case is named
+            // stream start: the reference's prev_theta is 0 (fm_demod.cpp:41; its zero FIR history gives atan2(0, 0))
             th_prev_own = (tile == 0 && p.first_block) ? 0.0f : fm_atan2f(ei, er);
         }
         float prev = 0.0f;
-#pragma unroll
         if (tile == 0 && t == 0 && p.first_block) {
             // the first 16 outputs of a stream: only the taps that met real samples carry the 127 offset
 #pragma unroll

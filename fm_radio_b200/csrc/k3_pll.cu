@@ -37,8 +37,8 @@
 // The AGC gain is a positive scale and does not enter the angle; if it is not finite (all-zero
 // block: sqrt(1/0)) the reference's pilot becomes NaN and poisons the loop for good -- such a lane
 // takes the slow loop below, which keeps the reference's clamp-of-NaN behaviour.  Per-thread I/O is
-// whole 32-byte sectors (LDG.128 / STG.128 on the lane's own row), loaded a full 32-sample group
-// ahead, so memory latency never sits on the chain.
+// whole 32-byte sectors on the lane's own row; the input streams through a shared-memory ring filled by
+// cp.async seven 32-sample groups ahead, so memory latency never sits on the chain.
 #include "fm_common.cuh"
 
 namespace fm {
@@ -56,12 +56,15 @@ __device__ __forceinline__ float wrap_turn(float x) {
     return x - rintf(x);
 }
 
+constexpr int K3_RING = 8;      // groups of theta in flight per warp (8 x 4 KB of shared memory)
+
 template <bool KEEP, int WRAP>
 __global__ void __launch_bounds__(32)
 k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* __restrict__ state,
        float* __restrict__ pll_dt, float* __restrict__ dbg_raw, float* __restrict__ dbg_pi,
        const __grid_constant__ K3Params p)
 {
+    __shared__ __align__(128) float4 s_ring[K3_RING * 32 * 8];     // [slot][lane][8 chunks of 16 bytes]
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n_streams) return;
     const int S = p.n_streams;
@@ -88,26 +91,47 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
     const float f_gain = p.f_gain, f_center = p.f_center, mixer_KTs = p.mixer_KTs;
 
     if (!poisoned) {
-        // Groups of 32 samples (four 32-byte sectors per lane), loaded one whole group ahead.
+        // Groups of 32 samples = one 128-byte line per lane.  theta was written by K2 together with 2x as much
+        // fm_out_iq, so by now part of it has left the L2, and under the FIR kernels' DRAM traffic a miss costs
+        // far more than the ~1500 cycles one group of register look-ahead buys (ncu: long_scoreboard was this
+        // kernel's top stall, and it ran 1.35x slower inside the pipeline than alone).  So each lane streams
+        // its row through a ring of K3_RING groups in shared memory with cp.async, K3_RING - 1 groups
+        // (~10 000 cycles) ahead of use; chunk c of lane l sits at chunk c ^ (l & 7) of the lane's 128-byte
+        // row, so the lanes' LDS.128 are bank-conflict free.  A lane reads only what it copied itself
+        // (cp.async.wait_group orders that), so no warp-level synchronisation is involved.
         constexpr int G = 32;
+        const int lane = threadIdx.x;
+        const int n_groups = p.n / G;
+        char* ring = (char*)s_ring + lane * 128;
+        const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+        auto issue = [&](int g) {                        // copy group g into ring slot g % K3_RING (or nothing past the end)
+            if (g < n_groups) {
+                const char* src = (const char*)(th4 + (size_t)g * (G / 4));
+                const unsigned dst = ring_sa + (unsigned)(g % K3_RING) * (32 * 128);
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + (unsigned)((c ^ (lane & 7)) << 4)), "l"(src + c * 16));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto fetch = [&](int g, float4 (&dst)[G / 4]) {  // ring slot -> registers
+            const char* row = ring + (g % K3_RING) * (32 * 128);
+#pragma unroll
+            for (int c = 0; c < 8; c++) dst[c] = *(const float4*)(row + ((c ^ (lane & 7)) << 4));
+        };
+#pragma unroll
+        for (int g = 0; g < K3_RING - 1; g++) issue(g);
+        asm volatile("cp.async.wait_group %0;" :: "n"(K3_RING - 2) : "memory");      // group 0 has landed
         float4 nx[G / 4];
-#pragma unroll
-        for (int q = 0; q < G / 4; q++) nx[q] = th4[q];
-#pragma unroll
-        for (int g = 1; g < 4; g++)
-            if (g * G < p.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(th4 + ((g * G) >> 2)));
+        fetch(0, nx);
         for (int i = 0; i < p.n; i += G) {
+            const int g = i / G;
             float4 cur[G / 4];
 #pragma unroll
             for (int q = 0; q < G / 4; q++) cur[q] = nx[q];
-            if (i + G < p.n) {
-#pragma unroll
-                for (int q = 0; q < G / 4; q++) nx[q] = th4[((i + G) >> 2) + q];
-            }
-            // theta was written by K2 together with 2x as much fm_out_iq, so part of it has left the
-            // L2 by now: pull the lane's 128-byte line of group i + 4G into L2 (DRAM latency under
-            // load exceeds the ~1500 cycles one group of look-ahead buys; measured, see profiles/)
-            if (i + 4 * G < p.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(th4 + ((i + 4 * G) >> 2)));
+            issue(g + K3_RING - 1);                      // into the slot of group g - 1, read into registers one iteration ago
+            asm volatile("cp.async.wait_group %0;" :: "n"(K3_RING - 2) : "memory");  // group g + 1 has landed
+            if (g + 1 < n_groups) fetch(g + 1, nx);
             // Speculative pass: both clamps taken as inactive, which shortens the chain from 9 to 7 dependent
             // ops (w -> {fma, fma} -> fma -> fma -> fma -> 3-op wrap).  clamp(x) = sat(x) - sat(-x) returns x
             // itself, bit for bit, whenever |x| <= 1, so the pass is exact unless a clamp would have acted
