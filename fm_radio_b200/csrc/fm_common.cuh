@@ -144,6 +144,7 @@ struct K3Params {
     float Kp;                   // proportional_gain (:429)
     float f_center, f_gain, mixer_KTs;   // (:229-231)
     float agc_target, agc_beta; // dsp/agc.h:9-11
+    float integ_safe;           // filled by launch_k3: |integ| below this after a group => no clamp acted inside it
     int n;                      // B/8
     int n_streams;
     int keep;

@@ -40,6 +40,7 @@
 // whole 32-byte sectors on the lane's own row; the input streams through a shared-memory ring filled by
 // cp.async seven 32-sample groups ahead, so memory latency never sits on the chain.
 #include "fm_common.cuh"
+#include <cmath>
 
 namespace fm {
 
@@ -135,10 +136,9 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
             // Speculative pass: both clamps taken as inactive, which shortens the chain from 9 to 7 dependent
             // ops (w -> {fma, fma} -> fma -> fma -> fma -> 3-op wrap).  clamp(x) = sat(x) - sat(-x) returns x
             // itself, bit for bit, whenever |x| <= 1, so the pass is exact unless a clamp would have acted
-            // (or a NaN met fma.sat); that is tracked off the chain, and the group is then redone from the
-            // saved state by the exact body.  A locked or locking loop never clamps: |PI| stays below 0.05.
+            // (or a NaN met fma.sat); the group is then redone from the saved state by the exact body.  A locked
+            // or locking loop never clamps: |PI| stays below 0.05.
             const float sx1 = x1, sy1 = y1, sinteg = integ, st = t, sw = w;
-            bool exact_needed = false;
 #pragma unroll
             for (int q = 0; q < G / 4; q++) {
                 const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
@@ -151,7 +151,6 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
                     integ = fmaf(ci, w, integ);
                     x1 = w; y1 = lpf;
                     const float control = fmaf(lpf, Kp, integ);
-                    exact_needed = exact_needed || !(fabsf(integ) <= 1.0f) || !(fabsf(control) <= 1.0f);
                     const float freq = fmaf(control, f_gain, f_center);
                     t = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, t));
                     w = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, a));
@@ -164,7 +163,10 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
                     pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
                 }
             }
-            if (exact_needed) {
+            // |w| <= 1/2 turn bounds the low-pass output and the integrator's step, so ONE test of the integrator at
+            // the end of the group proves that neither clamp could have acted anywhere inside it (integ_safe is
+            // derived on the host from the loop's coefficients, launch_k3; NaN fails the test; <= 0 = always redo)
+            if (!(fabsf(integ) <= p.integ_safe)) {
                 x1 = sx1; y1 = sy1; integ = sinteg; t = st; w = sw;
 #pragma unroll 1
                 for (int q = 0; q < G / 4; q++) {
@@ -229,9 +231,21 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
 }
 
 cudaError_t launch_k3(const float* theta, const float* power, float* state, float* pll_dt,
-                      float* dbg_raw, float* dbg_pi, const K3Params& p, cudaStream_t st)
+                      float* dbg_raw, float* dbg_pi, const K3Params& p_in, cudaStream_t st)
 {
+    K3Params p = p_in;
     const int grid = (p.n_streams + 31) / 32;
+    {
+        // Bounds for the speculative pass.  The phase error is wrapped to |w| <= 1/2 turn, so in the kernel's
+        // units |lpf| <= (|b0| + |b1|) * pi / (1 - |a0|) and the integrator moves by at most int_KTs * pi per
+        // sample.  If |integ| <= integ_safe after a 32-sample group, then |integ| <= 1 and |Kp*lpf + integ| <= 1
+        // held at every sample of it (1e-3 of margin covers the roundings).
+        const double pi = 3.14159265358979323846;
+        const double a0 = std::fabs((double)p.lpf_a[0]);
+        const double lpf_max = a0 < 1.0 ? (std::fabs((double)p.lpf_b[0]) + std::fabs((double)p.lpf_b[1])) * pi / (1.0 - a0) : 1e30;
+        const double safe = 1.0 - std::fabs((double)p.Kp) * lpf_max - 32.0 * std::fabs((double)p.int_KTs) * pi - 1e-3;
+        p.integ_safe = safe > 0.0 ? (float)safe : 0.0f;
+    }
     if (p.keep) k3_pll<true, 0><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
     else        k3_pll<false, 0><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
     return cudaGetLastError();
