@@ -219,7 +219,7 @@ bool create_partitioned_streams(fmgpu_demod* h, int prio_hi) {
                  && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&b, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
-                 && p_cuGreenCtxStreamCreate(&e2, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
+                 && p_cuGreenCtxStreamCreate(&e2, std::getenv("FMGPU_K6_ON_FIR") ? g_rest : g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
     if (!ok) {
         for (CUstream st : { a, b, c, d, e2 }) if (st) cudaStreamDestroy((cudaStream_t)st);
         p_cuGreenCtxDestroy(g_rec); p_cuGreenCtxDestroy(g_rest);

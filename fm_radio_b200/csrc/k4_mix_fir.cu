@@ -139,7 +139,9 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         for (int a = 0; a < 5; a++) s_sig[a * K4_PLEN + K4_PLEN - 8 + t] = make_float2(0.0f, 0.0f);   // the quad a window may over-read
     }
     // ---- stage + mix: sample idx of the staged array <-> MPX sample n0 - 128 + idx ----
-    const float2 off2 = make_float2(lmr_phase[sA], lmr_phase[sB]);
+    // the L-R phase offset of the block (broadcast_fm_demod.cpp:485-488), as a rotation: (cos, sin)(2 pi off)
+    const float2 off2 = wrap2(make_float2(lmr_phase[sA], lmr_phase[sB]));
+    const float2 off_c = chebyshev_sine2(wrap2(__fadd2_rn(off2, bc2(0.25f)))), off_s = chebyshev_sine2(off2);
     const float2* xA = fm_out_iq + (size_t)sA * p.n, * xB = fm_out_iq + (size_t)sB * p.n;
     const float* dA = pll_dt + (size_t)sA * p.n, * dB = pll_dt + (size_t)sB * p.n;
     constexpr int NIT = (K4_LEN + K4_THREADS - 1) / K4_THREADS;   // 9
@@ -168,16 +170,24 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         } else {
             xr = make_float2(vxa[it].x, vxb[it].x);
             const float2 xi = make_float2(vxa[it].y, vxb[it].y);
-            {   // apply_harmonic_pll.cpp:16-23: y = x * (S(phi + 1/4 wrapped), S(phi wrapped)), phi = dt*h + off
-                const float2 ph = __ffma2_rn(vdt[it], bc2(p.harmonic_lmr), off2);
-                const float2 c = chebyshev_sine2(wrap2(__fadd2_rn(ph, bc2(0.25f)))), sn = chebyshev_sine2(wrap2(ph));
-                m2r = __ffma2_rn(xr, c, neg2(__fmul2_rn(xi, sn))); m2i = __ffma2_rn(xr, sn, __fmul2_rn(xi, c));
-            }
-            {
-                const float2 ph = __fmul2_rn(vdt[it], bc2(p.harmonic_rds));
-                const float2 c = chebyshev_sine2(wrap2(__fadd2_rn(ph, bc2(0.25f)))), sn = chebyshev_sine2(wrap2(ph));
-                m3r = __ffma2_rn(xr, c, neg2(__fmul2_rn(xi, sn))); m3i = __ffma2_rn(xr, sn, __fmul2_rn(xi, c));
-            }
+            // apply_harmonic_pll.cpp:16-23: y = x * (S(phi + 1/4 wrapped), S(phi wrapped)), phi = dt*h + off, for
+            // h = 2 (+ the L-R phase offset) and h = 3.  The reference evaluates its polynomial sine four times per
+            // sample; here the fundamental (cos, sin)(2 pi dt) is evaluated ONCE with that polynomial (dt is already
+            // wrapped to [-1/2, 1/2]; cos(2 pi t) = S(1/4 - |t|) needs no wrap) and the harmonics follow by angle
+            // addition -- 41 packed instructions per sample instead of 66 (the mixdown was 43 % of this kernel's FMA
+            // work).  The products add ~1e-7 of rounding to a unit oscillator, the size of the polynomial's own error
+            // (3.6e-8 mean, 1.5e-7 max) and of the reference's phase rounding (ulp(phi) = 6e-8 turns = 4e-7 rad).
+            const float2 t1 = vdt[it];
+            const float2 c1 = chebyshev_sine2(__fadd2_rn(bc2(0.25f), make_float2(-fabsf(t1.x), -fabsf(t1.y))));
+            const float2 s1 = chebyshev_sine2(t1);
+            const float2 c2 = __ffma2_rn(c1, c1, neg2(__fmul2_rn(s1, s1)));
+            const float2 s2 = __fmul2_rn(__fadd2_rn(s1, s1), c1);
+            const float2 c3 = __ffma2_rn(c2, c1, neg2(__fmul2_rn(s2, s1)));
+            const float2 s3 = __ffma2_rn(s2, c1, __fmul2_rn(c2, s1));
+            const float2 C2 = __ffma2_rn(c2, off_c, neg2(__fmul2_rn(s2, off_s)));     // e^{j 2 pi (2 dt + off)}
+            const float2 S2 = __ffma2_rn(s2, off_c, __fmul2_rn(c2, off_s));
+            m2r = __ffma2_rn(xr, C2, neg2(__fmul2_rn(xi, S2))); m2i = __ffma2_rn(xr, S2, __fmul2_rn(xi, C2));
+            m3r = __ffma2_rn(xr, c3, neg2(__fmul2_rn(xi, s3))); m3i = __ffma2_rn(xr, s3, __fmul2_rn(xi, c3));
         }
         const int a = a4(idx);
         s_sig[a] = xr; s_sig[K4_PLEN + a] = m2r; s_sig[2 * K4_PLEN + a] = m2i; s_sig[3 * K4_PLEN + a] = m3r; s_sig[4 * K4_PLEN + a] = m3i;
