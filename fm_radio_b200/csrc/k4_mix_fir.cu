@@ -219,23 +219,6 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         // /4 FIR: output o = 8*lane + r reads staged samples 4o + 4 + k
         if (8 * lane < n_audio)
             fir128<4, 8>(s_sig + (warp == 0 ? 0 : 2 * K4_PLEN), s_taps + (warp == 0 ? 0 : K4_NN), 32 * lane + 4, acc8);
-        if (warp == 1) {
-            // real part of L-R where the estimator looks: output o_first + 10*lane, taps ascending
-            const int o = o_first + 10 * lane;
-            if (o < n_audio) {
-                const float2* sg = s_sig + K4_PLEN;
-                const float2* tp = s_taps + K4_NN;
-#pragma unroll 4
-                for (int q = 0; q < 32; q++) {
-                    const float4 x01 = *(const float4*)(sg + a4(4 * o + 4 + 4 * q)), x23 = *(const float4*)(sg + a4(4 * o + 4 + 4 * q + 2));
-                    const float4 b01 = *(const float4*)(tp + 4 * q), b23 = *(const float4*)(tp + 4 * q + 2);
-                    sparse = __ffma2_rn(make_float2(x01.x, x01.y), make_float2(b01.x, b01.y), sparse);
-                    sparse = __ffma2_rn(make_float2(x01.z, x01.w), make_float2(b01.z, b01.w), sparse);
-                    sparse = __ffma2_rn(make_float2(x23.x, x23.y), make_float2(b23.x, b23.y), sparse);
-                    sparse = __ffma2_rn(make_float2(x23.z, x23.w), make_float2(b23.z, b23.w), sparse);
-                }
-            }
-        }
     } else if (warp == 2) {
         // /8 FIR, real then imaginary plane: output o = 4*lane + r reads staged samples 8o + 8 + k.
         // This warp owns its outputs completely: RDS samples and their AGC power partial leave from registers.
@@ -261,14 +244,31 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
             rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
             if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
         }
+    } else {
+        // warp 3 (no FIR role of its own): the 26 sparse outputs, off warp 1's critical path
+        // real part of L-R where the estimator looks: output o_first + 10*lane, taps ascending
+        const int o = o_first + 10 * lane;
+        if (o < n_audio) {
+            const float2* sg = s_sig + K4_PLEN;
+            const float2* tp = s_taps + K4_NN;
+#pragma unroll 4
+            for (int q = 0; q < 32; q++) {
+                const float4 x01 = *(const float4*)(sg + a4(4 * o + 4 + 4 * q)), x23 = *(const float4*)(sg + a4(4 * o + 4 + 4 * q + 2));
+                const float4 b01 = *(const float4*)(tp + 4 * q), b23 = *(const float4*)(tp + 4 * q + 2);
+                sparse = __ffma2_rn(make_float2(x01.x, x01.y), make_float2(b01.x, b01.y), sparse);
+                sparse = __ffma2_rn(make_float2(x01.z, x01.w), make_float2(b01.z, b01.w), sparse);
+                sparse = __ffma2_rn(make_float2(x23.x, x23.y), make_float2(b23.x, b23.y), sparse);
+                sparse = __ffma2_rn(make_float2(x23.z, x23.w), make_float2(b23.z, b23.w), sparse);
+            }
+        }
     }
     __syncthreads();                                            // planes and taps are dead from here on
     if (warp < 2) {
         float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 8 * lane;
 #pragma unroll
         for (int q = 0; q < 4; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
-        if (warp == 1) s_res[K4_RES_SPARSE + lane] = sparse;
     }
+    if (warp == 3) s_res[K4_RES_SPARSE + lane] = sparse;
     __syncthreads();
 
     // ---- MixAudio (:549-585) + phase-estimator partial sum (:496-511), 2 outputs per thread ----
