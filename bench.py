@@ -36,6 +36,11 @@ FLOP_PER_SAMPLE_CHAIN = 160.0      # SURVEY.md 8(d) headline figure
 BYTES_PER_SAMPLE_FUSED = 2.26      # 2 B u8 in + 0.25 B audio + 0.01 B symbols
 BYTES_PER_SAMPLE_K1 = 3.0          # K1 as built: 2 B u8 in + 4 B fm_demod out per 4 samples
 N_SM, FP32_LANES = 148, 128
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the roofline kernel at the default
+# workload (1024 streams x 65536 samples), from the committed `ncu --set full` capture; the algorithmic figure is
+# 3 B per IQ sample = 201 MB (134 MB of u8 in -- all of it read from DRAM -- and 67 MB of fm_demod out, of which
+# about half stays in the L2 for K2)
+NCU_K1_DRAM_BYTES = (134.8e6 + 35.4e6, "profiles/r1k_ncu_summary.md")
 # algorithmic FLOP per input IQ sample of each kernel (per-stage figures; FMA = 2)
 KERNEL_FLOP_PER_SAMPLE = {"k1_fir4_discrim": 64.0,      # a2 (a1 unpack 2.0 and a3 discriminator 1.0 not counted)
                           "k2_mpx": 16.0 + 16.25 + 3.0 + 0.6,   # a4 + a6 + a7 + a8
@@ -292,7 +297,9 @@ def run_cuda_arm(args):
             "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp32_peak,
             "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no fp32 figure; "
                            "the chain is FP32-FMA bound, not HBM or tensor bound, SURVEY.md 8d)",
-            "traffic": None,
+            "traffic": NCU_K1_DRAM_BYTES[0] if (S == STREAMS_PER_GPU and B == BLOCK) else None,
+            "traffic_source": NCU_K1_DRAM_BYTES[1] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+            "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE_K1 * S * B,
             "hbm": {"achieved": BYTES_PER_SAMPLE_K1 * S * B / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": BYTES_PER_SAMPLE_K1 * S * B / (k1_ms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},

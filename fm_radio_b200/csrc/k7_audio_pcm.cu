@@ -25,24 +25,40 @@ __device__ __forceinline__ short f32_to_s16_x86(float v) {
     return (short)(i & 0xFFFF);
 }
 
+constexpr int K7_U = 4;         // output frames per thread, loads of all four issued before the first use
+
 __global__ void __launch_bounds__(256)
 k7_audio_pcm(const float2* __restrict__ audio, const K7Entry* __restrict__ table,
              float2* __restrict__ pcm_f32, short2* __restrict__ pcm_s16, int n_in, int n_out, float s16_scale)
 {
     const int s = blockIdx.y;
     const float2* in = audio + (size_t)s * n_in;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
-        const K7Entry e = table[i];
-        const float2 f0 = __ldg(in + e.j0);
-        const float2 f1 = (e.j0 + 1 < n_in) ? __ldg(in + e.j0 + 1) : f0;
-        // buf_out[i] = f0*(1.0f-k) + f1*k, each Frame operator rounding once (frame.h:10-16, 42-49)
-        const float a = __fsub_rn(1.0f, e.k);
-        float2 o;
-        o.x = __fadd_rn(__fmul_rn(f0.x, a), __fmul_rn(f1.x, e.k));
-        o.y = __fadd_rn(__fmul_rn(f0.y, a), __fmul_rn(f1.y, e.k));
-        const size_t k = (size_t)s * n_out + i;
-        if (pcm_f32) pcm_f32[k] = o;
-        if (pcm_s16) pcm_s16[k] = make_short2(f32_to_s16_x86(__fmul_rn(o.x, s16_scale)), f32_to_s16_x86(__fmul_rn(o.y, s16_scale)));
+    for (int i0 = (blockIdx.x * blockDim.x) * K7_U + threadIdx.x; i0 < n_out; i0 += gridDim.x * blockDim.x * K7_U) {
+        K7Entry e[K7_U];
+        float2 f0[K7_U], f1[K7_U];
+#pragma unroll
+        for (int u = 0; u < K7_U; u++) {
+            const int i = i0 + u * 256;
+            e[u] = (i < n_out) ? table[i] : K7Entry{ 0, 0.0f };
+        }
+#pragma unroll
+        for (int u = 0; u < K7_U; u++) {
+            f0[u] = __ldg(in + e[u].j0);
+            f1[u] = (e[u].j0 + 1 < n_in) ? __ldg(in + e[u].j0 + 1) : f0[u];
+        }
+#pragma unroll
+        for (int u = 0; u < K7_U; u++) {
+            const int i = i0 + u * 256;
+            if (i >= n_out) continue;
+            // buf_out[i] = f0*(1.0f-k) + f1*k, each Frame operator rounding once (frame.h:10-16, 42-49)
+            const float a = __fsub_rn(1.0f, e[u].k);
+            float2 o;
+            o.x = __fadd_rn(__fmul_rn(f0[u].x, a), __fmul_rn(f1[u].x, e[u].k));
+            o.y = __fadd_rn(__fmul_rn(f0[u].y, a), __fmul_rn(f1[u].y, e[u].k));
+            const size_t k = (size_t)s * n_out + i;
+            if (pcm_f32) pcm_f32[k] = o;
+            if (pcm_s16) pcm_s16[k] = make_short2(f32_to_s16_x86(__fmul_rn(o.x, s16_scale)), f32_to_s16_x86(__fmul_rn(o.y, s16_scale)));
+        }
     }
 }
 
@@ -60,8 +76,8 @@ cudaError_t launch_k7(const float2* audio, const K7Entry* table, float2* pcm_f32
                       int n_in, int n_out, int n_streams, cudaStream_t st)
 {
     const float scale = 32767.0f * 0.95f;                // CONVERT_RESCALE, fm_scraper.cpp:74
-    const int bx = (n_out + 255) / 256;
-    k7_audio_pcm<<<dim3(bx > 16 ? 16 : bx, n_streams), 256, 0, st>>>(audio, table, pcm_f32, pcm_s16, n_in, n_out, scale);
+    const int bx = (n_out + 256 * K7_U - 1) / (256 * K7_U);
+    k7_audio_pcm<<<dim3(bx > 8 ? 8 : bx, n_streams), 256, 0, st>>>(audio, table, pcm_f32, pcm_s16, n_in, n_out, scale);
     return cudaGetLastError();
 }
 
