@@ -175,6 +175,19 @@ def run_cuda_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    if not args.no_affinity:
+        # pin this rank to the CPUs local to its GPU before any pinned host memory is allocated, so the e2e
+        # path's host buffers sit on the GPU's own NUMA node (no effect on a single-socket host)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pynvml.nvmlDeviceSetCpuAffinity(hnd)
+            numa = sorted(os.sched_getaffinity(0))
+            numa = f"{len(numa)} cpus {numa[0]}-{numa[-1]}"
+        except Exception as ex:  # noqa: BLE001
+            numa = f"unavailable ({type(ex).__name__})"
     S, B = args.streams, BLOCK
     n_in = args.input_blocks
 
@@ -330,7 +343,8 @@ def run_cuda_arm(args):
             "x_realtime": value * 1e6 / FS,
             "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "x_realtime": e2e_value * 1e6 / FS,
-                    "api": "fmgpu_enqueue_u8_host + fmgpu_fetch_outputs per block, pinned host buffers"},
+                    "api": "fmgpu_enqueue_u8_host + fmgpu_fetch_outputs per block, pinned host buffers",
+                    "cpu_affinity": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -368,6 +382,7 @@ def main():
     ap.add_argument("--input-blocks", type=int, default=24, help="distinct, CONTINUOUS input blocks per stream kept in HBM (24 = 1.5 s of signal, 3.2 GB)")
     ap.add_argument("--audio-pcm-rate", type=int, default=48000, help="audio output stage K7: resample GetAudioOut to this rate + int16 PCM (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's local CPUs")
     ap.add_argument("--clock-warmup-ms", type=float, default=500.0, help="untimed load before the W warm-up steps (clock ramp from idle)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
