@@ -52,7 +52,7 @@ struct Slot {
     int* sym_count = nullptr;      // [S]
     float2* pcm_f32 = nullptr;     // [S][pcm_n] audio at the PCM rate (K7; allocated when the stage is switched on)
     short2* pcm_s16 = nullptr;     // [S][pcm_n]
-    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_E, ev_O, ev_P;
+    cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_E, ev_O, ev_P, ev_K1;
 };
 
 struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
@@ -72,7 +72,7 @@ struct fmgpu_demod {
     fmgpu_config cfg{};
     int B = 0, S = 0, n4 = 0, n8 = 0, n32 = 0, n64 = 0, depth = 0, k4_tiles = 0;
     int device = 0;
-    cudaStream_t stH = nullptr, stA = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stE = nullptr, stO = nullptr;
+    cudaStream_t stH = nullptr, stA = nullptr, stA2 = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stE = nullptr, stO = nullptr;
     // SM partition (green contexts): the recurrence stages B, D get their own SMs
     CUgreenCtx gctx_rec = nullptr, gctx_fir = nullptr;
     int sms_rec = 0, sms_fir = 0;
@@ -214,18 +214,19 @@ bool create_partitioned_streams(fmgpu_demod* h, int prio_hi) {
     CUgreenCtx g_rec = nullptr, g_rest = nullptr;
     if (p_cuGreenCtxCreate(&g_rec, d_rec, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     if (p_cuGreenCtxCreate(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(g_rec); return false; }
-    CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr, e2 = nullptr;
+    CUstream a = nullptr, a2 = nullptr, b = nullptr, c = nullptr, d = nullptr, e2 = nullptr;
     const bool ok = p_cuGreenCtxStreamCreate(&a, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&a2, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&b, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&e2, std::getenv("FMGPU_K6_ON_FIR") ? g_rest : g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
     if (!ok) {
-        for (CUstream st : { a, b, c, d, e2 }) if (st) cudaStreamDestroy((cudaStream_t)st);
+        for (CUstream st : { a, a2, b, c, d, e2 }) if (st) cudaStreamDestroy((cudaStream_t)st);
         p_cuGreenCtxDestroy(g_rec); p_cuGreenCtxDestroy(g_rest);
         return false;
     }
-    h->stA = (cudaStream_t)a; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d; h->stE = (cudaStream_t)e2;
+    h->stA = (cudaStream_t)a; h->stA2 = (cudaStream_t)a2; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d; h->stE = (cudaStream_t)e2;
     h->gctx_rec = g_rec; h->gctx_fir = g_rest;
     h->sms_rec = (int)rec.sm.smCount; h->sms_fir = (int)rest.sm.smCount;
     return true;
@@ -257,6 +258,7 @@ int alloc_all(fmgpu_demod* h) {
         // no partition (FMGPU_NO_PARTITION, or the driver refused): plain streams; the recurrences at
         // least get the highest CTA-scheduling priority
         CU(cudaStreamCreateWithFlags(&h->stA, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->stA2, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_hi));
         CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
@@ -305,7 +307,7 @@ int alloc_all(fmgpu_demod* h) {
         CU(dalloc(&sl.rds_pw_partial, S * h->k4_tiles));
         CU(dalloc(&sl.pred_sym, S * h->n64));
         CU(dalloc(&sl.sym_count, S));
-        cudaEvent_t* evs[8] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_E, &sl.ev_O, &sl.ev_P };
+        cudaEvent_t* evs[9] = { &sl.ev_H, &sl.ev_A, &sl.ev_B, &sl.ev_C, &sl.ev_D, &sl.ev_E, &sl.ev_O, &sl.ev_P, &sl.ev_K1 };
         for (auto* ev : evs) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         HostMirror& m = h->mirrors[i];
         CU(cudaMallocHost((void**)&m.audio, S * h->n32 * sizeof(float2)));
@@ -336,7 +338,7 @@ void free_all(fmgpu_demod* h) {
     for (auto& sl : h->slots) {
         F(sl.in_u8); F(sl.fm_demod); F(sl.fm_out_iq); F(sl.theta); F(sl.power); F(sl.pll_dt); F(sl.audio); F(sl.rds);
         F(sl.est_partial); F(sl.rds_pw_partial); F(sl.pred_sym); F(sl.sym_count); F(sl.pcm_f32); F(sl.pcm_s16);
-        cudaEvent_t evs[8] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_O, sl.ev_P };
+        cudaEvent_t evs[9] = { sl.ev_H, sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_O, sl.ev_P, sl.ev_K1 };
         for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     }
     for (auto& m : h->mirrors) {
@@ -349,7 +351,7 @@ void free_all(fmgpu_demod* h) {
     F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr);
     F(d.k5.rds); F(d.k5.raw_sym); F(d.k5.pll_sym); F(d.k5.zcd); F(d.k5.dump_trig);
     F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
-    cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[8] = { h->stH, h->stA, h->stA2, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) if (st) cudaStreamDestroy(st);
     destroy_partition(h);
 }
@@ -429,11 +431,17 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.use_deemph = h->ctl_use_deemph; p.n_out = h->n8; p.keep = keep;
         fill_scan_matrices(p);
         if (prof) CU(cudaEventRecord(prof[1], h->stA));
+        // K2 runs on its own stream of the FIR partition: it is one wave of long-lived CTAs (one per stream pair,
+        // 3.9 per SM) that leaves half of the FMA pipe idle, and K1 of the NEXT block -- which only needs a free
+        // slot, not K2 -- fills those issue slots instead of queueing behind it.
+        static const bool k2_own = std::getenv("FMGPU_K2_SAME_STREAM") == nullptr;
+        cudaStream_t st2 = k2_own ? h->stA2 : h->stA;
+        if (k2_own) { CU(cudaEventRecord(sl.ev_K1, h->stA)); CU(cudaStreamWaitEvent(st2, sl.ev_K1, 0)); }
         CU(fm::launch_k2(sl.fm_demod, h->k2_hist_demod, h->k2_hist_out, h->k2_scal, sl.fm_out_iq, sl.theta, sl.power,
-                         keep ? h->dbg.pilot : nullptr, p, h->S, h->stA));
+                         keep ? h->dbg.pilot : nullptr, p, h->S, st2));
+        if (prof) CU(cudaEventRecord(prof[2], st2));
+        CU(cudaEventRecord(sl.ev_A, st2));
     }
-    if (prof) CU(cudaEventRecord(prof[2], h->stA));
-    CU(cudaEventRecord(sl.ev_A, h->stA));
 
     // ---- stage B: K3 ----
     CU(cudaStreamWaitEvent(h->stB, sl.ev_A, 0));
@@ -540,6 +548,7 @@ int fetch_slot(fmgpu_demod* h, int slot) {
 int sync_all(fmgpu_demod* h) {
     CU(cudaStreamSynchronize(h->stH));
     CU(cudaStreamSynchronize(h->stA));
+    CU(cudaStreamSynchronize(h->stA2));
     CU(cudaStreamSynchronize(h->stB));
     CU(cudaStreamSynchronize(h->stC));
     CU(cudaStreamSynchronize(h->stD));
@@ -738,7 +747,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-    cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[8] = { h->stH, h->stA, h->stA2, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) CU(cudaStreamWaitEvent(st, ev, 0));
     CU(cudaEventDestroy(ev));
     return FMGPU_OK;
@@ -746,7 +755,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
 
 int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream) {
     if (!h) return fail(FMGPU_ERR_ARG, "null handle");
-    cudaStream_t sts[7] = { h->stH, h->stA, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[8] = { h->stH, h->stA, h->stA2, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) {
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
