@@ -72,7 +72,7 @@ struct fmgpu_demod {
     fmgpu_config cfg{};
     int B = 0, S = 0, n4 = 0, n8 = 0, n32 = 0, n64 = 0, depth = 0, k4_tiles = 0;
     int device = 0;
-    cudaStream_t stH = nullptr, stA = nullptr, stA2 = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stE = nullptr, stO = nullptr;
+    cudaStream_t stH = nullptr, stA = nullptr, stA2 = nullptr, stP = nullptr, stB = nullptr, stC = nullptr, stD = nullptr, stE = nullptr, stO = nullptr;
     // SM partition (green contexts): the recurrence stages B, D get their own SMs
     CUgreenCtx gctx_rec = nullptr, gctx_fir = nullptr;
     int sms_rec = 0, sms_fir = 0;
@@ -214,19 +214,20 @@ bool create_partitioned_streams(fmgpu_demod* h, int prio_hi) {
     CUgreenCtx g_rec = nullptr, g_rest = nullptr;
     if (p_cuGreenCtxCreate(&g_rec, d_rec, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     if (p_cuGreenCtxCreate(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(g_rec); return false; }
-    CUstream a = nullptr, a2 = nullptr, b = nullptr, c = nullptr, d = nullptr, e2 = nullptr;
+    CUstream a = nullptr, a2 = nullptr, pp = nullptr, b = nullptr, c = nullptr, d = nullptr, e2 = nullptr;
     const bool ok = p_cuGreenCtxStreamCreate(&a, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&a2, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&pp, std::getenv("FMGPU_K7_ON_REC") ? g_rec : g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&b, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&e2, std::getenv("FMGPU_K6_ON_FIR") ? g_rest : g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
     if (!ok) {
-        for (CUstream st : { a, a2, b, c, d, e2 }) if (st) cudaStreamDestroy((cudaStream_t)st);
+        for (CUstream st : { a, a2, pp, b, c, d, e2 }) if (st) cudaStreamDestroy((cudaStream_t)st);
         p_cuGreenCtxDestroy(g_rec); p_cuGreenCtxDestroy(g_rest);
         return false;
     }
-    h->stA = (cudaStream_t)a; h->stA2 = (cudaStream_t)a2; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d; h->stE = (cudaStream_t)e2;
+    h->stA = (cudaStream_t)a; h->stA2 = (cudaStream_t)a2; h->stP = (cudaStream_t)pp; h->stB = (cudaStream_t)b; h->stC = (cudaStream_t)c; h->stD = (cudaStream_t)d; h->stE = (cudaStream_t)e2;
     h->gctx_rec = g_rec; h->gctx_fir = g_rest;
     h->sms_rec = (int)rec.sm.smCount; h->sms_fir = (int)rest.sm.smCount;
     return true;
@@ -259,6 +260,7 @@ int alloc_all(fmgpu_demod* h) {
         // least get the highest CTA-scheduling priority
         CU(cudaStreamCreateWithFlags(&h->stA, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->stA2, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->stP, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_hi));
         CU(cudaStreamCreateWithFlags(&h->stC, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
@@ -351,7 +353,7 @@ void free_all(fmgpu_demod* h) {
     F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr);
     F(d.k5.rds); F(d.k5.raw_sym); F(d.k5.pll_sym); F(d.k5.zcd); F(d.k5.dump_trig);
     F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
-    cudaStream_t sts[8] = { h->stH, h->stA, h->stA2, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) if (st) cudaStreamDestroy(st);
     destroy_partition(h);
 }
@@ -464,6 +466,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     CU(cudaStreamWaitEvent(h->stC, sl.ev_B, 0));
     CU(cudaStreamWaitEvent(h->stC, sl.ev_D, 0));        // K5 of the slot's previous block read sl.rds
     CU(cudaStreamWaitEvent(h->stC, sl.ev_O, 0));        // ... and the fetch read sl.audio
+    CU(cudaStreamWaitEvent(h->stC, sl.ev_P, 0));        // ... and so did K7
     {
         fm::K4Params p{};
         std::memcpy(p.taps_lpr, h->taps.lpr, sizeof(p.taps_lpr));
@@ -480,15 +483,23 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     }
     if (prof) CU(cudaEventRecord(prof[6], h->stC));
     CU(cudaEventRecord(sl.ev_C, h->stC));
-    // ---- K7 (audio output stage, off by default): after ev_C, so the RDS stages do not wait for it ----
+    // ---- K7 (audio output stage, off by default): behind ev_C on its own stream of the FIR partition, so neither
+    //      the RDS stages nor K4 of the next block wait for it.  (Measured alternative, FMGPU_K7_ON_REC: on the
+    //      recurrence partition it takes 0.068 ms instead of 0.015 and slows K5 by 10 %; step 0.32 vs 0.29 ms.) ----
     if (h->ctl_pcm_rate > 0) {
         const int rc7 = prepare_pcm(h);
         if (rc7 != FMGPU_OK) return rc7;
-        CU(fm::launch_k7(sl.audio, h->pcm_table, sl.pcm_f32, sl.pcm_s16, h->n32, h->pcm_n, h->S, h->stC));
+        CU(cudaStreamWaitEvent(h->stP, sl.ev_C, 0));
+        CU(cudaStreamWaitEvent(h->stP, sl.ev_O, 0));    // the fetch of the slot's previous block read sl.pcm_s16
+        if (prof) CU(cudaEventRecord(prof[11], h->stP));
+        CU(fm::launch_k7(sl.audio, h->pcm_table, sl.pcm_f32, sl.pcm_s16, h->n32, h->pcm_n, h->S, h->stP));
         h->launches++;
+        if (prof) CU(cudaEventRecord(prof[10], h->stP));
+        CU(cudaEventRecord(sl.ev_P, h->stP));
+    } else if (prof) {
+        CU(cudaEventRecord(prof[11], h->stC));
+        CU(cudaEventRecord(prof[10], h->stC));
     }
-    if (prof) CU(cudaEventRecord(prof[10], h->stC));
-    CU(cudaEventRecord(sl.ev_P, h->stC));
 
     // ---- stage D: K5 ----
     CU(cudaStreamWaitEvent(h->stD, sl.ev_C, 0));
@@ -549,6 +560,7 @@ int sync_all(fmgpu_demod* h) {
     CU(cudaStreamSynchronize(h->stH));
     CU(cudaStreamSynchronize(h->stA));
     CU(cudaStreamSynchronize(h->stA2));
+    CU(cudaStreamSynchronize(h->stP));
     CU(cudaStreamSynchronize(h->stB));
     CU(cudaStreamSynchronize(h->stC));
     CU(cudaStreamSynchronize(h->stD));
@@ -706,11 +718,11 @@ int fmgpu_profile_stages7(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, f
     // share the GPU with the other stages' kernels (averaged over the second half of the run).
     const bool piped = n_blocks < 0;
     const int n = piped ? -n_blocks : n_blocks;
-    constexpr int NE = 11;
+    constexpr int NE = 12;
     std::vector<cudaEvent_t> ev((size_t)NE * n);
     for (auto& e : ev) CU(cudaEventCreate(&e));
     double acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
-    const int pairs[7][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 }, { 8, 9 }, { 6, 10 } };
+    const int pairs[7][2] = { { 0, 1 }, { 1, 2 }, { 3, 4 }, { 5, 6 }, { 7, 8 }, { 8, 9 }, { 11, 10 } };
     if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
     for (int b = 0; b < n; b++) {
         const int rc = enqueue_chain(h, iq_dev, true, false, &ev[(size_t)NE * b]);
@@ -747,7 +759,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-    cudaStream_t sts[8] = { h->stH, h->stA, h->stA2, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) CU(cudaStreamWaitEvent(st, ev, 0));
     CU(cudaEventDestroy(ev));
     return FMGPU_OK;
@@ -755,7 +767,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
 
 int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream) {
     if (!h) return fail(FMGPU_ERR_ARG, "null handle");
-    cudaStream_t sts[8] = { h->stH, h->stA, h->stA2, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) {
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

@@ -25,6 +25,8 @@ for rep in range(3):
         for f in ("fmgpu_enqueue_u8_device", "fmgpu_wait_external_stream", "fmgpu_signal_external_stream"): getattr(L, f).argtypes = [vp, vp]
         h = vp()
         assert L.fmgpu_create(C.byref(_Config(B, S, 0, 0, 4)), C.byref(h)) == 0
+        L.fmgpu_set_control.argtypes = [vp, C.c_int, C.c_double]
+        if not os.environ.get('AB_NO_PCM'): L.fmgpu_set_control(h, 6, 48000.0)     # audio output stage on, as bench.py
         L.fmgpu_wait_external_stream(h, ext)
         for k in range(6): L.fmgpu_enqueue_u8_device(h, cap[k % n_in].data_ptr())
         L.fmgpu_sync(h); torch.cuda.synchronize()
@@ -33,9 +35,9 @@ for rep in range(3):
         for k in range(steps): L.fmgpu_enqueue_u8_device(h, cap[(6 + k) % n_in].data_ptr())
         L.fmgpu_signal_external_stream(h, ext); e1.record()
         L.fmgpu_sync(h); torch.cuda.synchronize()
-        ms = (C.c_float * 6)()
-        L.fmgpu_profile_stages.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_float * 6)]
-        L.fmgpu_profile_stages(h, cap[0].data_ptr(), 8, C.byref(ms))
-        print(f"{os.path.basename(path):24s} {e0.elapsed_time(e1) / steps:.4f} ms/step   serial k1..k6 ms: "
+        ms = (C.c_float * 7)()
+        L.fmgpu_profile_stages7.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_float * 7)]
+        L.fmgpu_profile_stages7(h, cap[0].data_ptr(), 8, C.byref(ms))
+        print(f"{os.path.basename(path):24s} {e0.elapsed_time(e1) / steps:.4f} ms/step   serial k1..k7 ms: "
               + " ".join(f"{x:.4f}" for x in ms), flush=True)
         L.fmgpu_destroy(h)
