@@ -166,7 +166,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 // instructions a thread issued per 16 outputs.  Every tap costs ONE FFMA2 (re and im together) whose
 // tap operand is a uniform-register scalar (SASS: FFMA2 R, R.F32x2.HI_LO, UR.F32, R.F32x2.HI_LO).
 template <int J0>   // J0 = index of the chunk's first frame relative to the thread's window (even, 0 .. 30)
-__device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], const K1Params& p) {
+__device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], float2& acc_prev, const bool warp0, const K1Params& p) {
     const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -187,6 +187,19 @@ __device__ __forceinline__ void k1u_chunk(const uint4 w, float2 (&acc)[K1_R], co
                     const float tap = p.taps_s[4 * g + m];
                     acc[r] = __ffma2_rn(x[m], make_float2(tap, tap), acc[r]);
                 }
+            }
+        }
+        // output r = -1 (the one before the thread's first): frames 0 .. 15 with tap group = frame index.  Only
+        // thread 0 of the tile needs it (its predecessor lives in another CTA) -- as a 17th accumulator of warp 0
+        // (a warp-uniform condition) it rides in the main loop's instruction stream, where the 64-deep dependent
+        // chain hides completely; it used to be a single-lane pass after the loop that kept the tile's other three
+        // warps waiting at the barrier (6 % of the kernel's warp time in ncu's source view).  Same operands in the
+        // same order as the thread that owns this output in the previous tile, so the same bits.
+        if (j < 16 && warp0) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const float tap = p.taps_s[4 * j + m];
+                acc_prev = __ffma2_rn(x[m], make_float2(tap, tap), acc_prev);
             }
         }
     }
@@ -249,41 +262,23 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
     float out[K1_R];
     float th_prev_own = 0.0f;                            // thread 0 only: angle of the output before the tile
     if (active) {
-        float2 acc[K1_R];
+        float2 acc[K1_R], acc_prev = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int r = 0; r < K1_R; r++) acc[r] = make_float2(0.0f, 0.0f);
         const uint8_t* row0 = s_tile + t * 128;
         const uint8_t* row1 = row0 + 128;
         const int k0 = (t & 7) << 4, k1 = ((t + 1) & 7) << 4;
         // window frames j = 0..15 are row t (chunk c holds frames 2c, 2c+1), j = 16..31 row t+1
-#define K1U_DO(ROWP, KEY, C, J0) k1u_chunk<J0>(*(const uint4*)((ROWP) + (((C) << 4) ^ (KEY))), acc, p)
+#define K1U_DO(ROWP, KEY, C, J0) k1u_chunk<J0>(*(const uint4*)((ROWP) + (((C) << 4) ^ (KEY))), acc, acc_prev, warp == 0, p)
         K1U_DO(row0, k0, 0, 0);  K1U_DO(row0, k0, 1, 2);  K1U_DO(row0, k0, 2, 4);  K1U_DO(row0, k0, 3, 6);
         K1U_DO(row0, k0, 4, 8);  K1U_DO(row0, k0, 5, 10); K1U_DO(row0, k0, 6, 12); K1U_DO(row0, k0, 7, 14);
         K1U_DO(row1, k1, 0, 16); K1U_DO(row1, k1, 1, 18); K1U_DO(row1, k1, 2, 20); K1U_DO(row1, k1, 3, 22);
         K1U_DO(row1, k1, 4, 24); K1U_DO(row1, k1, 5, 26); K1U_DO(row1, k1, 6, 28); K1U_DO(row1, k1, 7, 30);
 #undef K1U_DO
         if (t == 0) {
-            // output o0-1: frames 0..15 of row 0 with tap group = frame index; same summation order
-            // as the thread that owns this output in the previous tile (bit-identical result)
-            float er = 0.0f, ei = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint4 w = *(const uint4*)(s_tile + (c << 4));
-                const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-#pragma unroll
-                    for (int m = 0; m < 4; m++) {
-                        const uint32_t v = ws[2 * h + (m >> 1)];
-                        const uint32_t sel = 0x4440u | (uint32_t)((m & 1) * 2);
-                        er = fmaf(__uint_as_float(__byte_perm(v, 0u, sel)), p.taps_s[4 * (2 * c + h) + m], er);
-                        ei = fmaf(__uint_as_float(__byte_perm(v, 0u, sel + 1u)), p.taps_s[4 * (2 * c + h) + m], ei);
-                    }
-                }
-            }
-            er = fmaf(er, K1_UNSCALE, p.neg_dc); ei = fmaf(ei, K1_UNSCALE, p.neg_dc);
             // stream start: the reference's prev_theta is 0 (fm_demod.cpp:41; its zero FIR history gives atan2(0, 0))
-            th_prev_own = (tile == 0 && p.first_block) ? 0.0f : fm_atan2f(ei, er);
+            const float2 zp = k1u_finish(acc_prev, p);
+            th_prev_own = (tile == 0 && p.first_block) ? 0.0f : fm_atan2f(zp.y, zp.x);
         }
         float prev = 0.0f;
         if (tile == 0 && t == 0 && p.first_block) {
