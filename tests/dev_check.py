@@ -1,4 +1,4 @@
-"""Development check run on the GPU box: S=1 keep_intermediates vs the reference, stage by stage."""
+"""Test infrastructure (imports oracle/).  Development check run on the GPU box (python tests/dev_check.py): S=1 keep_intermediates vs the reference, stage by stage."""
 import sys, time, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
