@@ -138,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
     "fmgpu_chan_wait_external_stream", "fmgpu_chan_sync", "fmgpu_chan_stream", "fmgpu_chan_launch_count",
     "fmgpu_profile_stages7", "fmgpu_polyphase_us_create", "fmgpu_polyphase_us_process", "fmgpu_resample_linear",
-    "fmgpu_frames_to_s16",
+    "fmgpu_frames_to_s16", "fmgpu_calculate_fft", "fmgpu_get_fft",
 ]
 
 _lib = None
@@ -200,6 +200,8 @@ def lib():
     L.fmgpu_polyphase_us_process.argtypes = [vp, vp, vp, ci]
     L.fmgpu_resample_linear.argtypes = [vp, ci, vp, ci]
     L.fmgpu_frames_to_s16.argtypes = [vp, cs, vp]
+    L.fmgpu_calculate_fft.argtypes = [vp, vp, ci, ci]
+    L.fmgpu_get_fft.argtypes = [vp, ci, ci, ci, vp, C.POINTER(cs)]
     L.fmgpu_rds_create.restype = vp
     L.fmgpu_rds_destroy.argtypes = [vp]
     L.fmgpu_rds_destroy.restype = None
@@ -359,6 +361,14 @@ class FMDemod:
         n = C.c_size_t()
         _check(self.L.fmgpu_get_device_buffer(self.h, slot, int(buf), C.byref(p), C.byref(n)), "fmgpu_get_device_buffer")
         return p.value, n.value
+
+    def fft(self, buf: Buf, stream: int = 0, fftshift: bool = True) -> np.ndarray:
+        """CalculateFFT (+ InplaceFFTShift) of one stream's signal buffer of the last block, computed on the device
+        (UpdateFFTCalc, fm_demod/broadcast_fm_demod.cpp:27-40, without the dB step)."""
+        y = np.zeros(self.block_size, np.complex64)
+        n = C.c_size_t()
+        _check(self.L.fmgpu_get_fft(self.h, stream, int(buf), int(fftshift), y.ctypes.data, C.byref(n)), f"fmgpu_get_fft({buf.name})")
+        return y[:n.value].copy()
 
     def scalar(self, which: Scalar, stream: int = 0) -> float:
         v = C.c_float()
@@ -633,6 +643,14 @@ def resample_linear(frames: np.ndarray, n_out: int) -> np.ndarray:
     out = np.zeros((n_out, 2), np.float32)
     _check(lib().fmgpu_resample_linear(frames.ctypes.data, frames.shape[0], out.ctypes.data, n_out), "fmgpu_resample_linear")
     return out
+
+
+def calculate_fft(x: np.ndarray, fftshift: bool = False) -> np.ndarray:
+    """CalculateFFT (dsp/calculate_fft.cpp:43-50) [+ InplaceFFTShift, dsp/fftshift.h:21-33] on the GPU."""
+    x = np.ascontiguousarray(x, np.complex64)
+    y = np.zeros(x.size, np.complex64)
+    _check(lib().fmgpu_calculate_fft(x.ctypes.data, y.ctypes.data, x.size, int(fftshift)), "fmgpu_calculate_fft")
+    return y
 
 
 def frames_to_s16(frames: np.ndarray) -> np.ndarray:

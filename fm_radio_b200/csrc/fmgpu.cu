@@ -1135,4 +1135,46 @@ int fmgpu_frames_to_s16(const float* frames_host, size_t n_frames, int16_t* out_
 #undef CUF
 }
 
+// ---- display spectra: CalculateFFT + InplaceFFTShift (k_fft.cu) ----
+static int fft_run(const float* d_in, int in_is_real, int n, int fftshift, float* y_host) {
+    float2* w0 = nullptr; float2* w1 = nullptr; float2* res = nullptr;
+    auto done = [&](int rc) { if (w0) cudaFree(w0); if (w1) cudaFree(w1); return rc; };
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(FMGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    CUF(cudaMalloc((void**)&w0, (size_t)n * 8)); CUF(cudaMalloc((void**)&w1, (size_t)n * 8));
+    CUF(fm::launch_fft(d_in, in_is_real, w0, w1, n, fftshift, &res, 0));
+    CUF(cudaMemcpy(y_host, res, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return done(FMGPU_OK);
+#undef CUF
+}
+
+int fmgpu_calculate_fft(const float* x_host, float* y_host, int n, int fftshift) {
+    if (!x_host || !y_host) return fail(FMGPU_ERR_ARG, "calculate_fft: null argument");
+    if (n < 2 || (n & (n - 1)) != 0) return fail(FMGPU_ERR_ARG, "calculate_fft: n must be a power of two >= 2 (every block size of the chain is)");
+    float* d_in = nullptr;
+    CU(cudaMalloc((void**)&d_in, (size_t)n * 8));
+    cudaError_t e = cudaMemcpy(d_in, x_host, (size_t)n * 8, cudaMemcpyHostToDevice);
+    const int rc = e == cudaSuccess ? fft_run(d_in, 0, n, fftshift, y_host) : fail(FMGPU_ERR_CUDA, cudaGetErrorString(e));
+    cudaFree(d_in);
+    return rc;
+}
+
+int fmgpu_get_fft(fmgpu_demod* h, int stream, fmgpu_buffer buf, int fftshift, float* y_host, size_t* n_out) {
+    if (!h || !y_host) return fail(FMGPU_ERR_ARG, "get_fft: null argument");
+    if (stream < 0 || stream >= h->S) return fail(FMGPU_ERR_ARG, "get_fft: bad stream");
+    if (h->last_fetched_slot < 0) return fail(FMGPU_ERR_STATE, "get_fft: nothing processed yet");
+    BufInfo bi{}; const void* dev = nullptr;
+    if (!buf_info(h, buf, &bi, &dev, h->last_fetched_slot))
+        return fail(FMGPU_ERR_STATE, "get_fft: buffer needs keep_intermediates = 1");
+    if (buf == FMGPU_BUF_PLL_DT || buf == FMGPU_BUF_RDS_PRED_SYM || buf == FMGPU_BUF_RDS_RAW_SYM || (bi.elem != 8 && bi.elem != 4)
+        || buf == FMGPU_BUF_AUDIO_OUT || buf == FMGPU_BUF_AUDIO_PCM_F32 || buf == FMGPU_BUF_AUDIO_PCM_S16 || buf == FMGPU_BUF_RDS_SYM_COUNT)
+        return fail(FMGPU_ERR_ARG, "get_fft: not a signal buffer (complex, or real f32, of fixed length)");
+    CU(cudaSetDevice(h->device));
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    const int n = bi.per_stream;
+    if (n_out) *n_out = (size_t)n;
+    const float* d_in = (const float*)((const uint8_t*)dev + (size_t)stream * bi.elem * (size_t)n);
+    return fft_run(d_in, bi.elem == 4, n, fftshift, y_host);
+}
+
 } // extern "C"
+

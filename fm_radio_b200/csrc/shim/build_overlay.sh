@@ -26,4 +26,10 @@ $CXX -std=c++17 -O2 -w -DNDEBUG -I"$OVER" -I"$REPO/include" -o "$OUT" \
     "$OVER/rds_decoder/crc10.cpp" "$OVER/rds_decoder/rds_database_decoder_handler.cpp" \
     "$OVER/rds_decoder/rds_decoder.cpp" "$OVER/rds_decoder/rds_group_sync.cpp" "$OVER/getopt.o" \
     -L"$REPO/fm_radio_b200" -lfmgpu -Wl,-rpath,"\$ORIGIN/.." -lpthread
+# test driver of the shim's GUI-facing spectrum getters (tests/shim/spectra_check.cpp), next to the benchmark driver
+if [ -f "$REPO/tests/shim/spectra_check.cpp" ]; then
+    $CXX -std=c++17 -O2 -w -DNDEBUG -I"$OVER" -I"$REPO/include" -o "$(dirname "$OUT")/shim_spectra_check" \
+        "$REPO/tests/shim/spectra_check.cpp" "$OVER/fm_demod/broadcast_fm_demod.cpp" "$OVER/dsp/calculate_fft_mag.cpp" \
+        -L"$REPO/fm_radio_b200" -lfmgpu -Wl,-rpath,"\$ORIGIN/.." -lpthread
+fi
 echo "built $OUT"

@@ -85,10 +85,30 @@ void Broadcast_FM_Demod::AfterProcess() {
     obs_on_rds_symbols.Notify(tcb::span<const float>(rds_pred_sym_buf).first((size_t)rds_total_symbols));
 }
 
+// UpdateFFTCalc (broadcast_fm_demod.cpp:27-40) for the spectra whose source buffer exists on the device:
+// CalculateFFT + InplaceFFTShift there, Calculate_FFT_Mag::Process (the reference's class) here.
+void Broadcast_FM_Demod::UpdateSpectra(const float* baseband_cf32) {
+    fft_tmp.resize((size_t)block_size);
+    float* tmp = reinterpret_cast<float*>(fft_tmp.data());
+    if (baseband_cf32 && calc_fft_mag[0].IsAwaitingUpdate()) {                       // :413
+        die_if(fmgpu_calculate_fft(baseband_cf32, tmp, block_size, 1), "fmgpu_calculate_fft");
+        calc_fft_mag[0].Process(tcb::span<const std::complex<float>>(fft_tmp.data(), (size_t)block_size), fft_mag_bufs[0]);
+    }
+    const struct { int idx; fmgpu_buffer buf; } src[4] = { { 2, FMGPU_BUF_FM_OUT_IQ }, { 3, FMGPU_BUF_PILOT },     // :415, :459
+                                                           { 4, FMGPU_BUF_PLL }, { 7, FMGPU_BUF_RDS } };           // :460, :535
+    for (const auto& e : src) {
+        if (!calc_fft_mag[e.idx].IsAwaitingUpdate()) continue;
+        size_t n = 0;
+        if (fmgpu_get_fft(handle, 0, e.buf, 1, tmp, &n) != FMGPU_OK) continue;      // FMGPU_LEAN: the GUI buffers do not exist
+        calc_fft_mag[e.idx].Process(tcb::span<const std::complex<float>>(fft_tmp.data(), n), fft_mag_bufs[e.idx]);
+    }
+}
+
 void Broadcast_FM_Demod::Process(tcb::span<const std::complex<float>> x) {
     if (x.size() != (size_t)block_size) return;                  // broadcast_fm_demod.cpp:311-313
     LatchControls();
     die_if(fmgpu_process_cf32(handle, reinterpret_cast<const float*>(x.data()), x.size()), "fmgpu_process_cf32");
+    UpdateSpectra(reinterpret_cast<const float*>(x.data()));
     AfterProcess();
 }
 
@@ -96,6 +116,14 @@ void Broadcast_FM_Demod::ProcessU8(tcb::span<const std::complex<uint8_t>> x) {
     if (x.size() != (size_t)block_size) return;
     LatchControls();
     die_if(fmgpu_process_u8(handle, reinterpret_cast<const uint8_t*>(x.data()), x.size()), "fmgpu_process_u8");
+    if (calc_fft_mag[0].IsAwaitingUpdate()) {                    // App::Run's unpack (app.cpp:56-65), only for the display
+        std::vector<float> f(2 * (size_t)block_size);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(x.data());
+        for (size_t i = 0; i < f.size(); i++) f[i] = (float)b[i] - 127.0f;
+        UpdateSpectra(f.data());
+    } else {
+        UpdateSpectra(nullptr);
+    }
     AfterProcess();
 }
 

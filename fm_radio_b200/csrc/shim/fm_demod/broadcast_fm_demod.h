@@ -12,8 +12,11 @@
 //     kernel, saving App::Run's host-side unpack (src/app.cpp:56-65);
 //   * buffers are fetched from the device lazily, when a getter is called, into host mirrors that
 //     stay valid until the next Process (the lifetime the reference's spans have);
-//   * the 8 magnitude-spectrum getters return zero-filled buffers: spectra are display-only, need
-//     FFTW in the reference and are out of scope of this round.
+//   * magnitude spectra (display only; FFTW in the reference): UpdateFFTCalc (broadcast_fm_demod.cpp:27-40)
+//     runs when a spectrum's trigger is raised -- the DFT + FFT shift on the device (fmgpu_get_fft /
+//     fmgpu_calculate_fft), then the reference's own Calculate_FFT_Mag::Process on the host -- for the
+//     baseband, FM-out, pilot, PLL and RDS spectra.  The FM-in and the two audio spectra stay zero-filled:
+//     the fused kernels never materialise fm_in_buf or the complex decimator outputs they are taken from.
 #pragma once
 
 #include <complex>
@@ -82,6 +85,7 @@ private:
     std::vector<Frame<float>> audio_out_buf;
     std::vector<float> rds_pred_sym_buf;
     std::vector<float> fft_mag_bufs[8];
+    std::vector<std::complex<float>> fft_tmp;
     Calculate_FFT_Mag calc_fft_mag[8];
 
     // controls as last sent to the device
@@ -100,6 +104,7 @@ public:
 private:
     void LatchControls();
     void AfterProcess();
+    void UpdateSpectra(const float* baseband_cf32);
     template <typename T> tcb::span<T> Fetch(int buf);
 public:
     // 1. FM demodulation
@@ -118,7 +123,7 @@ public:
     tcb::span<std::complex<float>> GetRDSRawSymbols();
     // 5. Audio mixing
     tcb::span<Frame<float>> GetAudioOut() { return audio_out_buf; }
-    // 6. FFT (display only, zero-filled: see header comment)
+    // 6. FFT (display only: see header comment)
     tcb::span<float> GetBasebandMagnitudeSpectrum() { return fft_mag_bufs[0]; }
     tcb::span<float> GetFMInMagnitudeSpectrum() { return fft_mag_bufs[1]; }
     tcb::span<float> GetFMOutMagnitudeSpectrum() { return fft_mag_bufs[2]; }

@@ -247,6 +247,18 @@ int  fmgpu_polyphase_us_process(fmgpu_polyphase* f, const float* x_host, float* 
 int  fmgpu_resample_linear(const float* frames_in_host, int n_in, float* frames_out_host, int n_out);
 int  fmgpu_frames_to_s16(const float* frames_host, size_t n_frames, int16_t* out_host);
 
+/* ---- display spectra: the device half of UpdateFFTCalc
+ * (fm_demod/broadcast_fm_demod.cpp:27-40).  fmgpu_calculate_fft = CalculateFFT (dsp/calculate_fft.cpp:43-50; FFTW3f
+ * in the reference: the forward DFT X[k] = sum_n x[n] exp(-2 pi i n k / N), unnormalised), optionally followed by
+ * InplaceFFTShift (dsp/fftshift.h:21-33), on n complex floats in host memory; n must be a power of two (every block
+ * size of the chain is).  fmgpu_get_fft does the same on one stream's copy of a signal buffer of the last processed
+ * block where it lies on the device (complex buffers, or real f32 ones taken as complex with zero imaginary part);
+ * y_host receives *n_out complex floats.  The dB / averaging step (Calculate_FFT_Mag::Process,
+ * dsp/calculate_fft_mag.cpp:11-45) is host code in the reference and stays on the host (the shim runs the
+ * reference's own class on these results).  Off the hot path: only when a GUI window raises a trigger. */
+int fmgpu_calculate_fft(const float* x_host, float* y_host, int n, int fftshift);
+int fmgpu_get_fft(fmgpu_demod* h, int stream, fmgpu_buffer buf, int fftshift, float* y_host, size_t* n_out);
+
 /* ---- RDS bit path on the host (differential_manchester_decoder.h:25-59, rds_group_sync.cpp,
  * crc10.cpp, and the PI/PTY/PS/RT subset of rds_decoder.cpp) ---------------------------------- */
 fmgpu_rds* fmgpu_rds_create(void);

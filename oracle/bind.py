@@ -89,6 +89,11 @@ def lib(kind: str = "ref"):
         L.polyphase_us_f32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.resample_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.frames_to_s16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.fft_mag_process.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+        if kind == "port":
+            L.fft_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        else:
+            L.fftshift_inplace.argtypes = [C.c_void_p, C.c_int]
         if kind == "port":
             L.set_taps.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         _libs[kind] = L

@@ -208,6 +208,66 @@ void fmo_frames_to_s16(const float* frames, size_t n_frames, int16_t* out) {
     }
 }
 
+/* Display spectra.  CalculateFFT (dsp/calculate_fft.cpp:43-50) is FFTW3f in the reference --
+ * an external, un-vendored library (vcpkg fftw3 >= 3.3.10, toolchains/ubuntu/install_packages.sh:3); what it
+ * computes is the forward DFT X[k] = sum_n x[n] exp(-2 pi i n k / N), restated here directly in double (O(N log N)
+ * recursion-free radix-2 for powers of two, the O(N^2) sum otherwise).  PARITY UNPINNED against FFTW itself (absent
+ * here); pinned against numpy.fft in tests/test_spectra.py.  fftshift != 0 applies InplaceFFTShift
+ * (dsp/fftshift.h:21-33). */
+void fmo_fft_f64(const float* x, double* y, int n, int fftshift) {
+    const double PI = 3.14159265358979323846;
+    double* re = (double*)malloc(sizeof(double) * (size_t)n);
+    double* im = (double*)malloc(sizeof(double) * (size_t)n);
+    if ((n & (n - 1)) == 0) {
+        int bits = 0; while ((1 << bits) < n) bits++;
+        for (int i = 0; i < n; i++) {                       /* bit-reversal permutation */
+            int r = 0; for (int b = 0; b < bits; b++) if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+            re[r] = x[2*i]; im[r] = x[2*i + 1];
+        }
+        for (int len = 2; len <= n; len <<= 1) {
+            for (int i = 0; i < n; i += len) {
+                for (int k = 0; k < len/2; k++) {
+                    const double ang = -2.0 * PI * (double)k / (double)len;
+                    const double wr = cos(ang), wi = sin(ang);
+                    const int a = i + k, b = i + k + len/2;
+                    const double tr = re[b]*wr - im[b]*wi, ti = re[b]*wi + im[b]*wr;
+                    re[b] = re[a] - tr; im[b] = im[a] - ti;
+                    re[a] += tr; im[a] += ti;
+                }
+            }
+        }
+    } else {
+        for (int k = 0; k < n; k++) {
+            double sr = 0, si = 0;
+            for (int i = 0; i < n; i++) {
+                const double ang = -2.0 * PI * (double)(((long long)i * k) % n) / (double)n;
+                sr += x[2*i]*cos(ang) - x[2*i+1]*sin(ang);
+                si += x[2*i]*sin(ang) + x[2*i+1]*cos(ang);
+            }
+            re[k] = sr; im[k] = si;
+        }
+    }
+    const int M = n / 2;
+    for (int i = 0; i < n; i++) {
+        const int j = fftshift ? ((i < M) ? i + M : i - M) : i;   /* x[i] <-> x[i + M], n even in every use */
+        y[2*j] = re[i]; y[2*j + 1] = im[i];
+    }
+    free(re); free(im);
+}
+
+/* Calculate_FFT_Mag::Process (dsp/calculate_fft_mag.cpp:11-45), trigger already resolved by the caller:
+ * v = 20 log10(|x[i]| / (2N - 1)); mode 0 NORMAL y = v, 1 AVERAGE y += beta (v - y), 2 MAX_HOLD y = max(y, v). */
+void fmo_fft_mag_process(int mode, float beta, const float* x_cf32, float* y, int n) {
+    const float M = (float)(2*n - 1);
+    for (int i = 0; i < n; i++) {
+        const float a = hypotf(x_cf32[2*i], x_cf32[2*i + 1]);
+        const float v = 20.0f * log10f(a / M);
+        if (mode == 0) y[i] = v;
+        else if (mode == 1) { const float d = v - y[i]; y[i] += beta * d; }
+        else y[i] = (y[i] > v) ? y[i] : v;
+    }
+}
+
 /* dsp/polyphase_filter.h:90-185 PolyphaseUpsampler<float>: coefficient repack (:108-117) and
  * y[i*L+phase] = sum_{j<K} X[i-(K-1)+j] * bp[phase*K + j]. */
 void fmo_polyphase_us_f32(int L, int K, const float* _b, const float* x, float* y, int N_in, int n_calls) {

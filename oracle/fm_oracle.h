@@ -60,6 +60,8 @@ void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* 
 void fmo_polyphase_us_f32(int L, int K, const float* b, const float* x, float* y, int N_in, int n_calls);
 void fmo_resample_linear(const float* in, int n_in, float* out, int n_out);
 void fmo_frames_to_s16(const float* frames, size_t n_frames, int16_t* out);
+void fmo_fft_f64(const float* x_cf32, double* y_c64, int n, int fftshift);
+void fmo_fft_mag_process(int mode, float beta, const float* x_cf32, float* y, int n);
 
 /* wideband channelizer oracle (config 4; no reference counterpart): float64 shift + decimating FIR */
 void fmo_channelize_f64(const uint8_t* iq, size_t n_in, const uint8_t* hist, uint64_t n0, int D, int NN,

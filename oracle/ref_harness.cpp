@@ -26,6 +26,8 @@
 #undef private
 #include "dsp/filter_designer.h"
 #include "audio/frame.h"
+#include "dsp/calculate_fft_mag.h"
+#include "dsp/fftshift.h"
 #include <limits>
 void Resample(tcb::span<const Frame<float>> buf_in, tcb::span<Frame<float>> buf_out);   // audio/resampled_pcm_player.cpp:3
 #include "rds_decoder/differential_manchester_decoder.h"
@@ -284,6 +286,20 @@ void fmref_frames_to_s16(const float* frames, size_t n_frames, int16_t* out) {
     auto* data = (const Frame<float>*)frames;
     auto* dst = (Frame<int16_t>*)out;
     for (size_t i = 0; i < n_frames; i++) dst[i] = Frame<int16_t>(data[i]*CONVERT_RESCALE);
+}
+
+// dsp/calculate_fft_mag.cpp:11-45 and dsp/fftshift.h:21-33: the reference's own class and template.  The trigger is
+// SINGLE + raised, i.e. exactly one update per call, as the GUI drives it (gui/render_fm_demod.cpp:399).
+void fmref_fft_mag_process(int mode, float beta, const float* x_cf32, float* y, int n) {
+    Calculate_FFT_Mag calc;
+    calc.SetMode((Calculate_FFT_Mag::Mode)mode);
+    calc.GetAverageBeta() = beta;
+    calc.SetTrigger(Calculate_FFT_Mag::Trigger::SINGLE);
+    calc.RaiseSingleTrigger();
+    calc.Process(tcb::span<const std::complex<float>>((const std::complex<float>*)x_cf32, (size_t)n), tcb::span<float>(y, (size_t)n));
+}
+void fmref_fftshift_inplace(float* x_cf32, int n) {
+    InplaceFFTShift(tcb::span<std::complex<float>>((std::complex<float>*)x_cf32, (size_t)n));
 }
 
 } // extern "C"
