@@ -483,19 +483,25 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     }
     if (prof) CU(cudaEventRecord(prof[6], h->stC));
     CU(cudaEventRecord(sl.ev_C, h->stC));
-    // ---- K7 (audio output stage, off by default): behind ev_C on its own stream of the FIR partition, so neither
-    //      the RDS stages nor K4 of the next block wait for it.  (Measured alternative, FMGPU_K7_ON_REC: on the
-    //      recurrence partition it takes 0.068 ms instead of 0.015 and slows K5 by 10 %; step 0.32 vs 0.29 ms.) ----
+    // ---- K7 (audio output stage, off by default): on stage stream C behind ev_C, so the RDS stages do not wait for
+    //      it.  Measured alternatives (1024 streams, ms per step): its own stream of the FIR partition
+    //      (FMGPU_K7_OWN_STREAM) 0.291 vs 0.2805 here -- a fourth concurrent FIR-partition kernel only takes CTA slots
+    //      from K1; on the recurrence partition (FMGPU_K7_ON_REC as well) it runs 0.068 ms instead of 0.015 and slows
+    //      K5 by 10 %: 0.32. ----
     if (h->ctl_pcm_rate > 0) {
         const int rc7 = prepare_pcm(h);
         if (rc7 != FMGPU_OK) return rc7;
-        CU(cudaStreamWaitEvent(h->stP, sl.ev_C, 0));
-        CU(cudaStreamWaitEvent(h->stP, sl.ev_O, 0));    // the fetch of the slot's previous block read sl.pcm_s16
-        if (prof) CU(cudaEventRecord(prof[11], h->stP));
-        CU(fm::launch_k7(sl.audio, h->pcm_table, sl.pcm_f32, sl.pcm_s16, h->n32, h->pcm_n, h->S, h->stP));
+        static const bool k7_own = std::getenv("FMGPU_K7_OWN_STREAM") != nullptr;
+        cudaStream_t st7 = k7_own ? h->stP : h->stC;
+        if (k7_own) {
+            CU(cudaStreamWaitEvent(st7, sl.ev_C, 0));
+            CU(cudaStreamWaitEvent(st7, sl.ev_O, 0));   // the fetch of the slot's previous block read sl.pcm_s16
+        }
+        if (prof) CU(cudaEventRecord(prof[11], st7));
+        CU(fm::launch_k7(sl.audio, h->pcm_table, sl.pcm_f32, sl.pcm_s16, h->n32, h->pcm_n, h->S, st7));
         h->launches++;
-        if (prof) CU(cudaEventRecord(prof[10], h->stP));
-        CU(cudaEventRecord(sl.ev_P, h->stP));
+        if (prof) CU(cudaEventRecord(prof[10], st7));
+        CU(cudaEventRecord(sl.ev_P, st7));
     } else if (prof) {
         CU(cudaEventRecord(prof[11], h->stC));
         CU(cudaEventRecord(prof[10], h->stC));
