@@ -46,6 +46,7 @@ class Buf(enum.IntEnum):
     BPSK_INT_DUMP_FILTER = 21
     AUDIO_PCM_F32 = 22
     AUDIO_PCM_S16 = 23
+    FM_IN = 24
 
 
 _BUF_DTYPE = {
@@ -58,7 +59,7 @@ _BUF_DTYPE = {
     Buf.BPSK_TED_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_TED_PI_PHASE_ERROR: (np.float32, 1),
     Buf.BPSK_PLL_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_PLL_PI_PHASE_ERROR: (np.float32, 1),
     Buf.BPSK_INT_DUMP_FILTER: (np.complex64, 1),
-    Buf.AUDIO_PCM_F32: (np.float32, 2), Buf.AUDIO_PCM_S16: (np.int16, 2),
+    Buf.AUDIO_PCM_F32: (np.float32, 2), Buf.AUDIO_PCM_S16: (np.int16, 2), Buf.FM_IN: (np.complex64, 1),
 }
 
 

@@ -120,6 +120,7 @@ struct K1Params {
     int parity;                 // history ping-pong: read [parity], write [parity^1]
     int n_streams;
     int first_block;            // no block before this one: the discriminator's previous angle is 0
+    float2* dbg_fm_in;          // keep_intermediates: [S][n_out] FIR outputs before the discriminator (GUI spectrum), else null
 };
 
 struct K2Params {

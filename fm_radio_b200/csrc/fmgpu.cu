@@ -57,7 +57,7 @@ struct Slot {
 
 struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
     float2* pilot = nullptr; float2* pll = nullptr; float* pll_raw = nullptr; float* pll_pi = nullptr;
-    float* lpr = nullptr; float* lmr = nullptr;
+    float* lpr = nullptr; float* lmr = nullptr; float2* fm_in = nullptr;
     fm::K5Debug k5{};
 };
 
@@ -321,7 +321,7 @@ int alloc_all(fmgpu_demod* h) {
         DebugBufs& d = h->dbg;
         CU(dalloc(&d.pilot, S * h->n8)); CU(dalloc(&d.pll, S * h->n8));
         CU(dalloc(&d.pll_raw, S * h->n8)); CU(dalloc(&d.pll_pi, S * h->n8));
-        CU(dalloc(&d.lpr, S * h->n32)); CU(dalloc(&d.lmr, S * h->n32));
+        CU(dalloc(&d.lpr, S * h->n32)); CU(dalloc(&d.lmr, S * h->n32)); CU(dalloc(&d.fm_in, S * h->n4));
         CU(dalloc(&d.k5.rds, S * h->n64)); CU(dalloc(&d.k5.raw_sym, S * h->n64)); CU(dalloc(&d.k5.pll_sym, S * h->n64));
         CU(dalloc(&d.k5.zcd, S * h->n64)); CU(dalloc(&d.k5.dump_trig, S * h->n64));
         CU(dalloc(&d.k5.ted_raw, S * h->n64)); CU(dalloc(&d.k5.ted_pi, S * h->n64));
@@ -350,7 +350,7 @@ void free_all(fmgpu_demod* h) {
         if (m.pcm_s16) cudaFreeHost(m.pcm_s16);
     }
     DebugBufs& d = h->dbg;
-    F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr);
+    F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr); F(d.fm_in);
     F(d.k5.rds); F(d.k5.raw_sym); F(d.k5.pll_sym); F(d.k5.zcd); F(d.k5.dump_trig);
     F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
     cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
@@ -420,7 +420,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         const float Wd = 75e3f * 2.0f * 3.14159265358979323846f;
         const float Ts = 1.0f / 256000.0f;
         p.discrim_gain = 1.0f / (Wd * Ts) * 0.5f;
-        p.n_out = h->n4; p.parity = parity; p.n_streams = h->S; p.first_block = (h->step == 0);
+        p.n_out = h->n4; p.parity = parity; p.n_streams = h->S; p.first_block = (h->step == 0); p.dbg_fm_in = keep ? h->dbg.fm_in : nullptr;
         if (prof) CU(cudaEventRecord(prof[0], h->stA));
         CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
     }
@@ -807,6 +807,7 @@ static bool buf_info(const fmgpu_demod* h, fmgpu_buffer b, BufInfo* bi, const vo
     case FMGPU_BUF_PLL_LPF_PHASE_ERROR: *bi = { 4, h->n8 }; *dev = d.pll_pi; return true;
     case FMGPU_BUF_AUDIO_LPR: *bi = { 4, h->n32 }; *dev = d.lpr; return true;
     case FMGPU_BUF_AUDIO_LMR: *bi = { 4, h->n32 }; *dev = d.lmr; return true;
+    case FMGPU_BUF_FM_IN: *bi = { 8, h->n4 }; *dev = d.fm_in; return true;
     case FMGPU_BUF_RDS: *bi = { 8, h->n64 }; *dev = d.k5.rds; return true;
     case FMGPU_BUF_RDS_RAW_SYM: *bi = { 8, h->n64 }; *dev = d.k5.raw_sym; return true;
     case FMGPU_BUF_BPSK_PLL_SYM: *bi = { 8, h->n64 }; *dev = d.k5.pll_sym; return true;

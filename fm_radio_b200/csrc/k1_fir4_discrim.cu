@@ -112,6 +112,11 @@ k1_fir4_discrim(const void* __restrict__ iq, const float2* __restrict__ hist_in,
         }
     }
 
+    if (p.dbg_fm_in) {
+        float2* d2 = p.dbg_fm_in + (size_t)s * p.n_out + o0 + t * K1_R;
+#pragma unroll
+        for (int r = 0; r < K1_R; r++) d2[r] = make_float2(ar[r + 1], ai[r + 1]);
+    }
     // ---- discriminator epilogue (fm_demod.cpp:36-44) ----
     float prev = fm_atan2f(ai[0], ar[0]);
     float out[K1_R];
@@ -289,6 +294,11 @@ k1_fir4_discrim_u8(const uint8_t* __restrict__ iq, const float2* __restrict__ hi
         } else {
 #pragma unroll
             for (int r = 0; r < K1_R; r++) acc[r] = k1u_finish(acc[r], p);
+        }
+        if (p.dbg_fm_in) {                               // GUI mode only: fm_in_buf for the FM-in spectrum
+            float4* d4 = (float4*)(p.dbg_fm_in + (size_t)s * p.n_out + o0 + t * K1_R);
+#pragma unroll
+            for (int r = 0; r < K1_R; r += 2) d4[r >> 1] = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
         }
 #pragma unroll
         for (int r = 0; r < K1_R; r += 2) {

@@ -15,8 +15,8 @@
 //   * magnitude spectra (display only; FFTW in the reference): UpdateFFTCalc (broadcast_fm_demod.cpp:27-40)
 //     runs when a spectrum's trigger is raised -- the DFT + FFT shift on the device (fmgpu_get_fft /
 //     fmgpu_calculate_fft), then the reference's own Calculate_FFT_Mag::Process on the host -- for the
-//     baseband, FM-out, pilot, PLL and RDS spectra.  The FM-in and the two audio spectra stay zero-filled:
-//     the fused kernels never materialise fm_in_buf or the complex decimator outputs they are taken from.
+//     baseband, FM-in, FM-out, pilot, PLL and RDS spectra.  The two audio spectra stay zero-filled: the fused
+//     kernel never materialises the complex decimator outputs (temp_audio_buf) they are taken from.
 #pragma once
 
 #include <complex>

@@ -125,6 +125,9 @@ typedef enum fmgpu_buffer {
     /* audio output stage K7 (needs FMGPU_CTL_AUDIO_PCM_RATE_HZ > 0), M = (int)((rate / 32000.f) * (B/32)) */
     FMGPU_BUF_AUDIO_PCM_F32,        /* Frame<float>[M]: Resample() of GetAudioOut (audio/resampled_pcm_player.cpp:37-54) */
     FMGPU_BUF_AUDIO_PCM_S16,        /* Frame<int16_t>[M]: the same frames as Audio_Scraper writes them (fm_scraper.cpp:74-78); pinned mirror */
+    FMGPU_BUF_FM_IN,                /* fm_in_buf cf32[B/4]: output of filt_poly_ds_lpf_fm_in (private in the reference; feeds its
+                                       FM-in spectrum, broadcast_fm_demod.cpp:414).  keep_intermediates only: the fused kernel
+                                       otherwise never stores it */
     FMGPU_BUF__COUNT
 } fmgpu_buffer;
 

@@ -89,7 +89,7 @@ def test_gpu_spectra_of_the_chain_buffers():
     g = fm.FMDemod(H.B, 2, keep_intermediates=True)
     for k in range(50):
         g.process_u8(np.stack([iq[2 * H.B * k:2 * H.B * (k + 1)], iq[2 * H.B * (k + 1):2 * H.B * (k + 2)]]))
-    for buf in (Buf.FM_OUT_IQ, Buf.PILOT, Buf.PLL, Buf.RDS, Buf.AUDIO_LPR, Buf.FM_DEMOD):
+    for buf in (Buf.FM_IN, Buf.FM_OUT_IQ, Buf.PILOT, Buf.PLL, Buf.RDS, Buf.AUDIO_LPR, Buf.FM_DEMOD):
         for s in (0, 1):
             x = g.get(buf, s)
             ref = _port_fft(x.astype(np.complex64), True)
@@ -115,8 +115,8 @@ def test_gpu_spectra_of_the_chain_buffers():
 @pytest.mark.gpu
 def test_shim_spectrum_getters_driven_like_the_gui(tmp_path):
     """The header-compatible Broadcast_FM_Demod shim with every spectrum's trigger raised before each block, as the
-    reference's GUI does: the five spectra whose source exists on the device are live, the pilot / PLL lines sit at
-    19 kHz and the RDS spectrum inside +-2.4 kHz; FM-in and the two audio spectra stay zero-filled (documented)."""
+    reference's GUI does: the six spectra whose source exists on the device are live, the pilot / PLL lines sit at
+    19 kHz and the RDS spectrum inside +-2.4 kHz; the two audio spectra stay zero-filled (documented)."""
     import subprocess
     exe = os.path.join(H.ROOT, "fm_radio_b200", "build", "shim_spectra_check")
     if not os.path.exists(exe):
@@ -132,10 +132,38 @@ def test_shim_spectrum_getters_driven_like_the_gui(tmp_path):
         n = int(rows[name]["n"])
         return (int(rows[name]["argmax"]) - n // 2) * fs / n
 
-    for name in ("fm_in", "audio_lpr", "audio_lmr"):
+    for name in ("audio_lpr", "audio_lmr"):
         assert float(rows[name]["max"]) == 0.0 and float(rows[name]["min"]) == 0.0
+    # FM-in: the 256 kS/s FM signal (+-75 kHz deviation) fills the middle of the band, the edges are filtered away
+    assert int(rows["fm_in"]["n"]) == H.B // 4 and abs(freq("fm_in", 256000.0)) <= 90000.0
+    assert float(rows["fm_in"]["max"]) > float(rows["fm_in"]["min"]) + 20
     assert int(rows["baseband"]["n"]) == H.B and float(rows["baseband"]["max"]) > float(rows["baseband"]["min"]) + 20
     assert abs(abs(freq("pilot", 128000.0)) - 19000.0) <= 40.0
     assert abs(abs(freq("pll", 128000.0)) - 19000.0) <= 40.0
     assert abs(freq("rds", 16000.0)) <= 2400.0
     assert abs(freq("fm_out", 128000.0)) <= 60000.0 and float(rows["fm_out"]["max"]) > float(rows["fm_out"]["min"]) + 20
+
+
+@pytest.mark.gpu
+def test_gpu_fm_in_buffer_matches_the_checker():
+    """fm_in_buf (the decimator output before the discriminator; private in the reference, source of its FM-in
+    spectrum) from both entry points against the restatement: feed-forward tolerance."""
+    import fm_radio_b200 as fm
+    from fm_radio_b200 import Buf
+    iq = H.capture("seed0")
+    chk = bind.CpuDemod(H.B, "port")
+    a, b = fm.FMDemod(H.B, 1, keep_intermediates=True), fm.FMDemod(H.B, 1, keep_intermediates=True)
+    for k in range(3):
+        blk = iq[2 * H.B * k:2 * H.B * (k + 1)]
+        chk.process_u8(blk)
+        a.process_u8(blk)
+        b.process_cf32((blk.astype(np.float32) - 127.0).view(np.complex64))
+        ref = chk.get("fm_in")
+        rms = np.sqrt(np.mean(np.abs(ref) ** 2))
+        assert np.abs(a.get(Buf.FM_IN) - ref).max() <= 1e-4 * rms
+        assert np.abs(b.get(Buf.FM_IN) - ref).max() <= 1e-4 * rms
+    lean = fm.FMDemod(H.B, 1)
+    lean.process_u8(iq[:2 * H.B])
+    with pytest.raises(fm.FMGPUError):
+        lean.get(Buf.FM_IN)
+    a.close(); b.close(); lean.close()
