@@ -47,6 +47,8 @@ class Buf(enum.IntEnum):
     AUDIO_PCM_F32 = 22
     AUDIO_PCM_S16 = 23
     FM_IN = 24
+    AUDIO_LPR_IQ = 25
+    AUDIO_LMR_IQ = 26
 
 
 _BUF_DTYPE = {
@@ -60,6 +62,7 @@ _BUF_DTYPE = {
     Buf.BPSK_PLL_RAW_PHASE_ERROR: (np.float32, 1), Buf.BPSK_PLL_PI_PHASE_ERROR: (np.float32, 1),
     Buf.BPSK_INT_DUMP_FILTER: (np.complex64, 1),
     Buf.AUDIO_PCM_F32: (np.float32, 2), Buf.AUDIO_PCM_S16: (np.int16, 2), Buf.FM_IN: (np.complex64, 1),
+    Buf.AUDIO_LPR_IQ: (np.complex64, 1), Buf.AUDIO_LMR_IQ: (np.complex64, 1),
 }
 
 

@@ -227,6 +227,8 @@ size_t k6_state_bytes();
 // debug-only finalisation of the GUI buffers: pilot *= gain, pll = (S(t+1/4), S(t))
 cudaError_t launch_fft(const float* in, int in_is_real, float2* work0, float2* work1, int n, int fftshift,
                        float2** result, cudaStream_t st);
+cudaError_t launch_kdbg_audio_iq(const float2* fm_out_iq, const float* pll_dt, const float2* hist_iq, const float2* hist_m2,
+                                 const float* lmr_phase_used, float2* lpr_iq, float2* lmr_iq, const K4Params& p, cudaStream_t st);
 cudaError_t launch_kdbg(float2* pilot, const float* pll_state, const float* pll_dt, float2* pll_out,
                         int n, int n_streams, cudaStream_t st);
 // stand-alone polyphase decimator (dsp/polyphase_filter.h:41-64) for the dsp API surface

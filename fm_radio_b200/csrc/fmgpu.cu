@@ -58,6 +58,7 @@ struct Slot {
 struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
     float2* pilot = nullptr; float2* pll = nullptr; float* pll_raw = nullptr; float* pll_pi = nullptr;
     float* lpr = nullptr; float* lmr = nullptr; float2* fm_in = nullptr;
+    float2* lpr_iq = nullptr; float2* lmr_iq = nullptr; float2* hist_iq = nullptr; float* lmr_phase_used = nullptr;   // GUI audio spectra
     fm::K5Debug k5{};
 };
 
@@ -322,6 +323,7 @@ int alloc_all(fmgpu_demod* h) {
         CU(dalloc(&d.pilot, S * h->n8)); CU(dalloc(&d.pll, S * h->n8));
         CU(dalloc(&d.pll_raw, S * h->n8)); CU(dalloc(&d.pll_pi, S * h->n8));
         CU(dalloc(&d.lpr, S * h->n32)); CU(dalloc(&d.lmr, S * h->n32)); CU(dalloc(&d.fm_in, S * h->n4));
+        CU(dalloc(&d.lpr_iq, S * h->n32)); CU(dalloc(&d.lmr_iq, S * h->n32)); CU(dalloc(&d.hist_iq, S * fm::K4_NN)); CU(dalloc(&d.lmr_phase_used, S));
         CU(dalloc(&d.k5.rds, S * h->n64)); CU(dalloc(&d.k5.raw_sym, S * h->n64)); CU(dalloc(&d.k5.pll_sym, S * h->n64));
         CU(dalloc(&d.k5.zcd, S * h->n64)); CU(dalloc(&d.k5.dump_trig, S * h->n64));
         CU(dalloc(&d.k5.ted_raw, S * h->n64)); CU(dalloc(&d.k5.ted_pi, S * h->n64));
@@ -350,7 +352,7 @@ void free_all(fmgpu_demod* h) {
         if (m.pcm_s16) cudaFreeHost(m.pcm_s16);
     }
     DebugBufs& d = h->dbg;
-    F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr); F(d.fm_in);
+    F(d.pilot); F(d.pll); F(d.pll_raw); F(d.pll_pi); F(d.lpr); F(d.lmr); F(d.fm_in); F(d.lpr_iq); F(d.lmr_iq); F(d.hist_iq); F(d.lmr_phase_used);
     F(d.k5.rds); F(d.k5.raw_sym); F(d.k5.pll_sym); F(d.k5.zcd); F(d.k5.dump_trig);
     F(d.k5.ted_raw); F(d.k5.ted_pi); F(d.k5.pll_raw); F(d.k5.pll_pi); F(d.k5.dump_filter);
     cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
@@ -475,11 +477,21 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.harmonic_lmr = 38000.0f / 19000.0f; p.harmonic_rds = 57000.0f / 19000.0f;
         p.stereo_mix = h->ctl_stereo_mix; p.audio_out_mode = h->ctl_audio_out;
         p.n = h->n8; p.n_tiles = h->k4_tiles; p.parity = parity; p.n_streams = h->S; p.keep = keep;
+        if (keep) CU(cudaMemcpyAsync(h->dbg.lmr_phase_used, h->lmr_phase, (size_t)h->S * sizeof(float), cudaMemcpyDeviceToDevice, h->stC));
         if (prof) CU(cudaEventRecord(prof[5], h->stC));
         CU(fm::launch_k4(sl.fm_out_iq, sl.pll_dt, h->k4_hist_x[parity], h->k4_hist_m2[parity], h->k4_hist_m3[parity],
                          h->k4_hist_x[parity ^ 1], h->k4_hist_m2[parity ^ 1], h->k4_hist_m3[parity ^ 1],
                          h->lmr_phase, sl.audio, sl.rds, sl.est_partial, sl.rds_pw_partial,
                          h->dbg.lpr, h->dbg.lmr, p, h->stC));
+        if (keep) {
+            // GUI mode: the complex decimator outputs behind the two audio spectra, then this block's last 128
+            // fm_out_iq samples as the next block's history (before ev_C lets K2 overwrite the slot)
+            CU(fm::launch_kdbg_audio_iq(sl.fm_out_iq, sl.pll_dt, h->dbg.hist_iq, h->k4_hist_m2[parity], h->dbg.lmr_phase_used,
+                                        h->dbg.lpr_iq, h->dbg.lmr_iq, p, h->stC));
+            CU(cudaMemcpy2DAsync(h->dbg.hist_iq, fm::K4_NN * sizeof(float2), sl.fm_out_iq + (h->n8 - fm::K4_NN), (size_t)h->n8 * sizeof(float2),
+                                 fm::K4_NN * sizeof(float2), (size_t)h->S, cudaMemcpyDeviceToDevice, h->stC));
+            h->launches++;
+        }
     }
     if (prof) CU(cudaEventRecord(prof[6], h->stC));
     CU(cudaEventRecord(sl.ev_C, h->stC));
@@ -808,6 +820,8 @@ static bool buf_info(const fmgpu_demod* h, fmgpu_buffer b, BufInfo* bi, const vo
     case FMGPU_BUF_AUDIO_LPR: *bi = { 4, h->n32 }; *dev = d.lpr; return true;
     case FMGPU_BUF_AUDIO_LMR: *bi = { 4, h->n32 }; *dev = d.lmr; return true;
     case FMGPU_BUF_FM_IN: *bi = { 8, h->n4 }; *dev = d.fm_in; return true;
+    case FMGPU_BUF_AUDIO_LPR_IQ: *bi = { 8, h->n32 }; *dev = d.lpr_iq; return true;
+    case FMGPU_BUF_AUDIO_LMR_IQ: *bi = { 8, h->n32 }; *dev = d.lmr_iq; return true;
     case FMGPU_BUF_RDS: *bi = { 8, h->n64 }; *dev = d.k5.rds; return true;
     case FMGPU_BUF_RDS_RAW_SYM: *bi = { 8, h->n64 }; *dev = d.k5.raw_sym; return true;
     case FMGPU_BUF_BPSK_PLL_SYM: *bi = { 8, h->n64 }; *dev = d.k5.pll_sym; return true;

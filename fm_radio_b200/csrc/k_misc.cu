@@ -32,6 +32,55 @@ cudaError_t launch_kdbg(float2* pilot, const float* pll_state, const float* pll_
     return cudaGetLastError();
 }
 
+// GUI mode only: the COMPLEX outputs of the two audio decimators, temp_audio_buf as the reference has it after
+// broadcast_fm_demod.cpp:475 (L+R: filt_poly_ds_lpf_audio_lpr on fm_out_iq) and :490 (L-R: filt_poly_ds_lpf_audio_lmr
+// on the 38 kHz mixdown), the sources of its two audio spectra (:481, :523).  The fused K4 keeps only what the audio
+// needs of them (the real part of the first, the imaginary part of the second), so for the display they are
+// recomputed here, one output per thread, straight from the definitions: y[o] = sum_k b[k] v(4 (o + 1) - 128 + k),
+// v(n < 0) from the carried histories; the mixdown is the reference's formula (apply_harmonic_pll.cpp:16-23).
+__global__ void kdbg_audio_iq(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_dt,
+                              const float2* __restrict__ hist_iq, const float2* __restrict__ hist_m2,
+                              const float* __restrict__ lmr_phase_used, float2* __restrict__ lpr_iq,
+                              float2* __restrict__ lmr_iq, const __grid_constant__ K4Params p)
+{
+    const int s = blockIdx.y;
+    const int n_out = p.n >> 2;
+    const float off = lmr_phase_used[s];
+    const float2* x = fm_out_iq + (size_t)s * p.n;
+    const float* dt = pll_dt + (size_t)s * p.n;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += gridDim.x * blockDim.x) {
+        float ar = 0.0f, ai = 0.0f, br = 0.0f, bi = 0.0f;
+        for (int k = 0; k < K4_NN; k++) {
+            const int n = 4 * (o + 1) - K4_NN + k;
+            float2 v, m;
+            if (n < 0) {
+                v = hist_iq[(size_t)s * K4_NN + K4_NN + n];
+                m = hist_m2[(size_t)s * K4_NN + K4_NN + n];
+            } else {
+                v = x[n];
+                float ph = fmaf(dt[n], p.harmonic_lmr, off);
+                float pc = ph + 0.25f;
+                pc -= rintf(pc); ph -= rintf(ph);
+                const float c = chebyshev_sine(pc), sn = chebyshev_sine(ph);
+                m = make_float2(v.x * c - v.y * sn, v.x * sn + v.y * c);
+            }
+            ar = fmaf(v.x, p.taps_lpr[k], ar); ai = fmaf(v.y, p.taps_lpr[k], ai);
+            br = fmaf(m.x, p.taps_lmr[k], br); bi = fmaf(m.y, p.taps_lmr[k], bi);
+        }
+        lpr_iq[(size_t)s * n_out + o] = make_float2(ar, ai);
+        lmr_iq[(size_t)s * n_out + o] = make_float2(br, bi);
+    }
+}
+
+cudaError_t launch_kdbg_audio_iq(const float2* fm_out_iq, const float* pll_dt, const float2* hist_iq, const float2* hist_m2,
+                                 const float* lmr_phase_used, float2* lpr_iq, float2* lmr_iq, const K4Params& p, cudaStream_t st)
+{
+    const int n_out = p.n >> 2;
+    const dim3 grid((n_out + 127) / 128 > 32 ? 32 : (n_out + 127) / 128, p.n_streams);
+    kdbg_audio_iq<<<grid, 128, 0, st>>>(fm_out_iq, pll_dt, hist_iq, hist_m2, lmr_phase_used, lpr_iq, lmr_iq, p);
+    return cudaGetLastError();
+}
+
 // y[i] = sum_k b[k] * ext[(i+1)*M + k], ext = (NN history samples) ++ (n_out*M new samples).
 // Generic M / NN, one output per thread, taps broadcast from shared memory.
 template <bool CPLX>

@@ -94,8 +94,9 @@ void Broadcast_FM_Demod::UpdateSpectra(const float* baseband_cf32) {
         die_if(fmgpu_calculate_fft(baseband_cf32, tmp, block_size, 1), "fmgpu_calculate_fft");
         calc_fft_mag[0].Process(tcb::span<const std::complex<float>>(fft_tmp.data(), (size_t)block_size), fft_mag_bufs[0]);
     }
-    const struct { int idx; fmgpu_buffer buf; } src[5] = { { 1, FMGPU_BUF_FM_IN }, { 2, FMGPU_BUF_FM_OUT_IQ },     // :414, :415
+    const struct { int idx; fmgpu_buffer buf; } src[7] = { { 1, FMGPU_BUF_FM_IN }, { 2, FMGPU_BUF_FM_OUT_IQ },     // :414, :415
                                                            { 3, FMGPU_BUF_PILOT }, { 4, FMGPU_BUF_PLL },           // :459, :460
+                                                           { 5, FMGPU_BUF_AUDIO_LPR_IQ }, { 6, FMGPU_BUF_AUDIO_LMR_IQ },   // :481, :523
                                                            { 7, FMGPU_BUF_RDS } };                                 // :535
     for (const auto& e : src) {
         if (!calc_fft_mag[e.idx].IsAwaitingUpdate()) continue;

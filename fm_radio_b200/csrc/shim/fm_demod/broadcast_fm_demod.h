@@ -15,8 +15,8 @@
 //   * magnitude spectra (display only; FFTW in the reference): UpdateFFTCalc (broadcast_fm_demod.cpp:27-40)
 //     runs when a spectrum's trigger is raised -- the DFT + FFT shift on the device (fmgpu_get_fft /
 //     fmgpu_calculate_fft), then the reference's own Calculate_FFT_Mag::Process on the host -- for the
-//     baseband, FM-in, FM-out, pilot, PLL and RDS spectra.  The two audio spectra stay zero-filled: the fused
-//     kernel never materialises the complex decimator outputs (temp_audio_buf) they are taken from.
+//     all eight spectra.  (GUI mode only: fm_in_buf and the complex decimator outputs behind the FM-in and
+//     audio spectra are extra stores / a small extra kernel that lean mode, FMGPU_LEAN=1, does not run.)
 #pragma once
 
 #include <complex>

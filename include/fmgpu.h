@@ -128,6 +128,10 @@ typedef enum fmgpu_buffer {
     FMGPU_BUF_FM_IN,                /* fm_in_buf cf32[B/4]: output of filt_poly_ds_lpf_fm_in (private in the reference; feeds its
                                        FM-in spectrum, broadcast_fm_demod.cpp:414).  keep_intermediates only: the fused kernel
                                        otherwise never stores it */
+    FMGPU_BUF_AUDIO_LPR_IQ,         /* temp_audio_buf after the L+R decimator, cf32[B/32] (broadcast_fm_demod.cpp:475; its real part is
+                                       GetLPRAudioOutput) -- source of the L+R spectrum (:481).  keep_intermediates only */
+    FMGPU_BUF_AUDIO_LMR_IQ,         /* temp_audio_buf after the L-R decimator, cf32[B/32] (:490; its imaginary part is
+                                       GetLMRAudioOutput) -- source of the L-R spectrum (:523).  keep_intermediates only */
     FMGPU_BUF__COUNT
 } fmgpu_buffer;
 

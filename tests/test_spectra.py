@@ -115,8 +115,8 @@ def test_gpu_spectra_of_the_chain_buffers():
 @pytest.mark.gpu
 def test_shim_spectrum_getters_driven_like_the_gui(tmp_path):
     """The header-compatible Broadcast_FM_Demod shim with every spectrum's trigger raised before each block, as the
-    reference's GUI does: the six spectra whose source exists on the device are live, the pilot / PLL lines sit at
-    19 kHz and the RDS spectrum inside +-2.4 kHz; the two audio spectra stay zero-filled (documented)."""
+    reference's GUI does: all eight spectra are live, the pilot / PLL lines sit at 19 kHz, the RDS spectrum inside
+    +-2.4 kHz, the audio spectra below 15 kHz."""
     import subprocess
     exe = os.path.join(H.ROOT, "fm_radio_b200", "build", "shim_spectra_check")
     if not os.path.exists(exe):
@@ -132,8 +132,11 @@ def test_shim_spectrum_getters_driven_like_the_gui(tmp_path):
         n = int(rows[name]["n"])
         return (int(rows[name]["argmax"]) - n // 2) * fs / n
 
+    # the audio spectra (32 kHz complex decimator outputs): program material below 15 kHz, L+R strongest near its 1 / 1.7 kHz tones
     for name in ("audio_lpr", "audio_lmr"):
-        assert float(rows[name]["max"]) == 0.0 and float(rows[name]["min"]) == 0.0
+        assert int(rows[name]["n"]) == H.B // 32 and abs(freq(name, 32000.0)) <= 15000.0
+        assert float(rows[name]["max"]) > float(rows[name]["min"]) + 20
+    assert abs(freq("audio_lpr", 32000.0)) <= 5500.0
     # FM-in: the 256 kS/s FM signal (+-75 kHz deviation) fills the middle of the band, the edges are filtered away
     assert int(rows["fm_in"]["n"]) == H.B // 4 and abs(freq("fm_in", 256000.0)) <= 90000.0
     assert float(rows["fm_in"]["max"]) > float(rows["fm_in"]["min"]) + 20
@@ -167,3 +170,31 @@ def test_gpu_fm_in_buffer_matches_the_checker():
     with pytest.raises(fm.FMGPUError):
         lean.get(Buf.FM_IN)
     a.close(); b.close(); lean.close()
+
+
+@pytest.mark.gpu
+def test_gpu_complex_audio_decimator_outputs():
+    """temp_audio_buf of the reference (broadcast_fm_demod.cpp:475, 490), recomputed in GUI mode for the audio spectra:
+    its real (L+R) / imaginary (L-R) part must be the audio the fused kernel produced, and the part the fused kernel
+    never computes must equal a float64 FIR of the same signal with the same taps, across block boundaries."""
+    import fm_radio_b200 as fm
+    from fm_radio_b200 import Buf, Filter
+    iq = H.capture("seed0")
+    g = fm.FMDemod(H.B, 2, keep_intermediates=True)
+    b_lpr, _ = g.download_taps(Filter.AUDIO_LPR)
+    hist = [np.zeros(128, np.complex128), np.zeros(128, np.complex128)]
+    for k in range(52):
+        g.process_u8(np.stack([iq[2 * H.B * k:2 * H.B * (k + 1)], iq[2 * H.B * (k + 3):2 * H.B * (k + 4)]]))
+        for s in (0, 1):
+            x = g.get(Buf.FM_OUT_IQ, s).astype(np.complex128)
+            ext = np.concatenate([hist[s], x])
+            hist[s] = x[-128:]
+            if k in (0, 1, 51):
+                lpr_iq, lmr_iq = g.get(Buf.AUDIO_LPR_IQ, s), g.get(Buf.AUDIO_LMR_IQ, s)
+                lpr, lmr = g.get(Buf.AUDIO_LPR, s), g.get(Buf.AUDIO_LMR, s)
+                rms = max(np.sqrt(np.mean(lpr ** 2)), 1e-3)
+                assert np.abs(lpr_iq.real - lpr).max() <= 1e-5 * rms, (k, s)
+                assert np.abs(lmr_iq.imag - lmr).max() <= 1e-5 * max(np.sqrt(np.mean(lmr ** 2)), 1e-3) + 1e-6, (k, s)
+                want = np.array([np.dot(b_lpr.astype(np.float64), ext[4 * (o + 1):4 * (o + 1) + 128]) for o in range(H.B // 32)])
+                assert np.abs(lpr_iq - want).max() <= 1e-5 * max(np.sqrt(np.mean(np.abs(want) ** 2)), 1e-3), (k, s)
+    g.close()
