@@ -73,6 +73,30 @@ def test_restatement_matches_live_reference():
     assert np.array_equal(_port_s16(x), s)
 
 
+def test_wav_container_matches_the_reference_layout(tmp_path):
+    """fm_scraper.cpp:107-160: 44-byte PCM header (stereo, 16 bit), size fields rewritten after every write; readable
+    by the standard library; reference_sizes=True reproduces the reference's frame-count-in-a-byte-field quirk."""
+    import wave
+    from fm_radio_b200.wav import WavWriter, wav_header
+    assert len(wav_header(32000, 0)) == 44
+    pcm = _port_s16(GOLD["s16_in"])
+    path = tmp_path / "a.wav"
+    with WavWriter(str(path), 48000) as w:
+        w.write(pcm[:1000]); w.write(pcm[1000:])
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data"
+    assert int.from_bytes(raw[40:44], "little") == pcm.size * 2 and int.from_bytes(raw[4:8], "little") == 36 + pcm.size * 2
+    assert int.from_bytes(raw[24:28], "little") == 48000 and int.from_bytes(raw[28:32], "little") == 48000 * 4
+    assert raw[44:] == pcm.astype("<i2").tobytes()
+    with wave.open(str(path)) as r:
+        assert (r.getnchannels(), r.getsampwidth(), r.getframerate(), r.getnframes()) == (2, 2, 48000, pcm.shape[0])
+    ref = tmp_path / "b.wav"
+    with WavWriter(str(ref), 32000, reference_sizes=True) as w:
+        w.write(pcm)
+    raw = open(ref, "rb").read()
+    assert int.from_bytes(raw[40:44], "little") == pcm.shape[0] and raw[44:] == pcm.astype("<i2").tobytes()
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU
 # ------------------------------------------------------------------------------------------------
