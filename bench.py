@@ -40,7 +40,7 @@ N_SM, FP32_LANES = 148, 128
 # workload (1024 streams x 65536 samples), from the committed `ncu --set full` capture; the algorithmic figure is
 # 3 B per IQ sample = 201 MB (134 MB of u8 in -- all of it read from DRAM -- and 67 MB of fm_demod out, of which
 # about half stays in the L2 for K2)
-NCU_K1_DRAM_BYTES = (134.8e6 + 35.4e6, "profiles/r1k_ncu_summary.md")
+NCU_K1_DRAM_BYTES = (134.8e6 + 35.4e6, "profiles/r1l_ncu_summary.md")
 # algorithmic FLOP per input IQ sample of each kernel (per-stage figures; FMA = 2)
 KERNEL_FLOP_PER_SAMPLE = {"k1_fir4_discrim": 64.0,      # a2 (a1 unpack 2.0 and a3 discriminator 1.0 not counted)
                           "k2_mpx": 16.0 + 16.25 + 3.0 + 0.6,   # a4 + a6 + a7 + a8
