@@ -9,8 +9,8 @@
 // Two kernels:
 //   k1_fir4_discrim_u8   the production path (rtl-sdr bytes).  FP32-FMA-pipe bound, 64 FLOP per
 //                        input IQ sample; design notes at the kernel.
-//   k1_fir4_discrim<..>  first version, kept for the cf32 entry point (Process(span<cf32>), one
-//                        stream, GUI use) where the input is 4x larger and speed is irrelevant.
+//   k1_fir4_discrim_cf32 first version (fp32 staging, scalar FFMA), kept for the cf32 entry point
+//                        (Process(span<cf32>), one stream, GUI use) where the input is 4x larger and speed is irrelevant.
 // The previous block's last 64 samples are the only state (ping-pong buffers, because the CTA
 // that reads the history is not the CTA that writes it); the discriminator's prev_theta is
 // recomputed from that history instead of being stored.
@@ -18,20 +18,13 @@
 
 namespace fm {
 
-__device__ __forceinline__ float u8_to_f32_m127(uint32_t w, int byte) {
-    // (2^23 + u8) built by PRMT into the mantissa of 0x4B000000, then one exact FADD.
-    const uint32_t sel = 0x7440u | (uint32_t)byte;
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388735.0f;
-}
-
 __device__ __forceinline__ float wrap_phase(float x) {          // fm_demod.cpp:6-10, as two selects
     const float lo = x - 2.0f * PI_F, hi = x + 2.0f * PI_F;
     return (x >= PI_F) ? lo : ((x <= -PI_F) ? hi : x);
 }
 
-template <bool U8>
 __global__ void __launch_bounds__(K1_THREADS, 3)
-k1_fir4_discrim(const void* __restrict__ iq, const float2* __restrict__ hist_in,
+k1_fir4_discrim_cf32(const float2* __restrict__ iq, const float2* __restrict__ hist_in,
                 float2* __restrict__ hist_out, float* __restrict__ fm_demod,
                 const __grid_constant__ K1Params p)
 {
@@ -52,31 +45,12 @@ k1_fir4_discrim(const void* __restrict__ iq, const float2* __restrict__ hist_in,
         float* d = smem + (f >> 4) * K1_SEG + (f & 15) * 8 + (t & 3) * 2;
         d[0] = v.x; d[1] = v.y;
     }
-    if (U8) {
-        // 16 bytes = 8 IQ samples = 2 frames per thread per iteration
-        const uint8_t* src = (const uint8_t*)iq + ((size_t)s * n_in + (size_t)(o0 - 16) * K1_M) * 2;
-        for (int pp = (f_first >> 1) + t; pp < (n_frames >> 1); pp += K1_THREADS) {
-            const uint4 w = __ldg((const uint4*)(src + (size_t)pp * 16));
-            const int f = pp * 2;
-            float* d = smem + (f >> 4) * K1_SEG + (f & 15) * 8;     // f even: both frames in one segment
-            float4 v;
-            v.x = u8_to_f32_m127(w.x, 0); v.y = u8_to_f32_m127(w.x, 1); v.z = u8_to_f32_m127(w.x, 2); v.w = u8_to_f32_m127(w.x, 3);
-            *(float4*)(d + 0) = v;
-            v.x = u8_to_f32_m127(w.y, 0); v.y = u8_to_f32_m127(w.y, 1); v.z = u8_to_f32_m127(w.y, 2); v.w = u8_to_f32_m127(w.y, 3);
-            *(float4*)(d + 4) = v;
-            v.x = u8_to_f32_m127(w.z, 0); v.y = u8_to_f32_m127(w.z, 1); v.z = u8_to_f32_m127(w.z, 2); v.w = u8_to_f32_m127(w.z, 3);
-            *(float4*)(d + 8) = v;
-            v.x = u8_to_f32_m127(w.w, 0); v.y = u8_to_f32_m127(w.w, 1); v.z = u8_to_f32_m127(w.w, 2); v.w = u8_to_f32_m127(w.w, 3);
-            *(float4*)(d + 12) = v;
-        }
-    } else {
-        // 16 bytes = 2 IQ samples = half a frame
-        const float4* src = (const float4*)((const float2*)iq + (size_t)s * n_in + (ptrdiff_t)(o0 - 16) * K1_M);
-        for (int hf = f_first * 2 + t; hf < n_frames * 2; hf += K1_THREADS) {
-            const float4 v = __ldg(src + hf);
-            const int f = hf >> 1;
-            *(float4*)(smem + (f >> 4) * K1_SEG + (f & 15) * 8 + (hf & 1) * 4) = v;
-        }
+    // 16 bytes = 2 IQ samples = half a frame
+    const float4* src = (const float4*)(iq + (size_t)s * n_in + (ptrdiff_t)(o0 - 16) * K1_M);
+    for (int hf = f_first * 2 + t; hf < n_frames * 2; hf += K1_THREADS) {
+        const float4 v = __ldg(src + hf);
+        const int f = hf >> 1;
+        *(float4*)(smem + (f >> 4) * K1_SEG + (f & 15) * 8 + (hf & 1) * 4) = v;
     }
     __syncthreads();
 
@@ -331,15 +305,13 @@ cudaError_t launch_k1(bool u8, const void* iq, const float2* hist_in, float2* hi
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k1_fir4_discrim<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k1_fir4_discrim<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k1_fir4_discrim_cf32, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const dim3 grid((p.n_out + K1_TILE - 1) / K1_TILE, p.n_streams);
     if (u8) k1_fir4_discrim_u8<<<grid, K1_THREADS, 0, st>>>((const uint8_t*)iq, hist_in, hist_out, fm_demod, p);
-    else    k1_fir4_discrim<false><<<grid, K1_THREADS, K1_SMEM_BYTES, st>>>(iq, hist_in, hist_out, fm_demod, p);
+    else    k1_fir4_discrim_cf32<<<grid, K1_THREADS, K1_SMEM_BYTES, st>>>((const float2*)iq, hist_in, hist_out, fm_demod, p);
     return cudaGetLastError();
 }
 
