@@ -415,3 +415,36 @@ def test_reference_driver_runs_unchanged_on_the_shim(tmp_path):
     assert sum("[group]" in ln for ln in want) >= 40
     assert log_of(gpu_drv) == want
     assert log_of(gpu_drv, {"FMGPU_LEAN": "1"}) == want
+
+
+@pytest.mark.parametrize("S", [33, 37])
+def test_ragged_batch_sizes_are_batch_invariant(S):
+    """Batch sizes that leave a partial warp in the one-thread-per-stream kernels (K3, K5, K6) and an odd last
+    stream pair in the two-streams-per-CTA kernels (K2, K4): every stream's audio, PCM and symbols must equal, bit
+    for bit, what a single-stream handle produces from the same bytes."""
+    iq = H.capture("seed0", n_blocks=70)
+    nblk, n_src = 5, 3
+    srcs = [iq[2 * H.B * 7 * j:2 * H.B * (7 * j + nblk)] for j in range(n_src)]       # three different stretches of signal
+    singles = []
+    for j in range(n_src):
+        g1 = fm.FMDemod(H.B, 1)
+        g1.set_control(Control.AUDIO_PCM_RATE_HZ, 48000)
+        outs = []
+        for k in range(nblk):
+            g1.process_u8(srcs[j][2 * H.B * k:2 * H.B * (k + 1)])
+            outs.append((g1.get(Buf.AUDIO_OUT), g1.get(Buf.AUDIO_PCM_S16), g1.get(Buf.RDS_PRED_SYM)))
+        singles.append(outs)
+        g1.close()
+    g = fm.FMDemod(H.B, S)
+    g.set_control(Control.AUDIO_PCM_RATE_HZ, 48000)
+    for k in range(nblk):
+        g.process_u8(np.stack([srcs[s % n_src][2 * H.B * k:2 * H.B * (k + 1)] for s in range(S)]))
+        for s in (0, 1, 2, 30, 31, 32, S - 2, S - 1):
+            a, pcm, sym = singles[s % n_src][k]
+            assert np.array_equal(g.get(Buf.AUDIO_OUT, s), a), (k, s)
+            assert np.array_equal(g.get(Buf.AUDIO_PCM_S16, s), pcm), (k, s)
+            assert np.array_equal(g.get(Buf.RDS_PRED_SYM, s), sym), (k, s)
+    g.rds_fetch()
+    for s in range(n_src, S):
+        assert g.rds_counts(s) == g.rds_counts(s % n_src)
+    g.close()
