@@ -62,12 +62,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """The timed region starts here: rows sampled before this call are not reported."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", os.environ.get("BENCH_SMI_MS", "25")], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -81,10 +85,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows
+        sm = sorted(float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -219,6 +224,10 @@ def run_cuda_arm(args):
     # clock ramp: a box that has just been handed out idles at 120 MHz and takes ~0.3 s of load to reach
     # its boost clock (measured: the first 48 steps after idle ran 1.45x slower), so besides the W warm-up
     # steps the GPU is kept busy with untimed blocks for args.clock_warmup_ms before anything is timed
+    # nvidia-smi is started here, before the clock ramp, so that its start-up (NVML attach) is over when the timed
+    # region begins; only rows sampled after mark() are reported
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     t_w = time.perf_counter()
     n_ramp = 0
     while (time.perf_counter() - t_w) * 1e3 < args.clock_warmup_ms:
@@ -229,9 +238,10 @@ def run_cuda_arm(args):
     for k in range(args.warmup):
         demod.enqueue_u8_device(cap[k % n_in])
     barrier()
+    if args.clock_warmup_ms < 300.0:
+        time.sleep(0.3)                                  # nvidia-smi's start-up must be over
     launches0 = demod.launch_count
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     demod.wait_external_stream(ext)

@@ -613,6 +613,20 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
     cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return fail(FMGPU_ERR_CUDA, "fmgpu_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    // Measured on this pool (driver 580.159, tools/bisect_bench.py): the FIRST handle whose green contexts are created in
+    // a process runs its FIR partition 6-7 % slower than every later one (0.300 vs 0.281 ms per step at 1024 streams),
+    // for as long as it lives.  Scratch green contexts with streams and a kernel launch do not change that; a complete
+    // handle that is created and destroyed, however small and without processing anything, does.  The cause is not
+    // identified; until it is, the first create of a process builds and drops a minimal handle first (a few ms).
+    static bool primed = false;
+    if (!primed && !std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME")) {
+        primed = true;
+        fmgpu_config sc{};
+        sc.block_size = 1024; sc.n_streams = 1; sc.device = dev; sc.pipeline_depth = 1;
+        fmgpu_demod* scratch = nullptr;
+        if (fmgpu_create(&sc, &scratch) == FMGPU_OK) fmgpu_destroy(scratch);
+        CU(cudaSetDevice(dev));
+    }
     auto* h = new fmgpu_demod();
     h->cfg = *cfg; h->cfg.device = dev;
     h->device = dev;

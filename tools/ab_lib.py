@@ -28,7 +28,7 @@ for rep in range(3):
         L.fmgpu_set_control.argtypes = [vp, C.c_int, C.c_double]
         if not os.environ.get('AB_NO_PCM'): L.fmgpu_set_control(h, 6, 48000.0)     # audio output stage on, as bench.py
         L.fmgpu_wait_external_stream(h, ext)
-        for k in range(6): L.fmgpu_enqueue_u8_device(h, cap[k % n_in].data_ptr())
+        for k in range(int(os.environ.get('AB_WARM', '6'))): L.fmgpu_enqueue_u8_device(h, cap[k % n_in].data_ptr())
         L.fmgpu_sync(h); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); L.fmgpu_wait_external_stream(h, ext)
