@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -618,9 +619,8 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
     // for as long as it lives.  Scratch green contexts with streams and a kernel launch do not change that; a complete
     // handle that is created and destroyed, however small and without processing anything, does.  The cause is not
     // identified; until it is, the first create of a process builds and drops a minimal handle first (a few ms).
-    static bool primed = false;
-    if (!primed && !std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME")) {
-        primed = true;
+    static std::atomic<bool> primed{false};
+    if (!std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME") && !primed.exchange(true)) {
         fmgpu_config sc{};
         sc.block_size = 1024; sc.n_streams = 1; sc.device = dev; sc.pipeline_depth = 1;
         fmgpu_demod* scratch = nullptr;
