@@ -618,9 +618,9 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
     // a process runs its FIR partition 6-7 % slower than every later one (0.300 vs 0.281 ms per step at 1024 streams),
     // for as long as it lives.  Scratch green contexts with streams and a kernel launch do not change that; a complete
     // handle that is created and destroyed, however small and without processing anything, does.  The cause is not
-    // identified; until it is, the first create of a process builds and drops a minimal handle first (a few ms).
-    static std::atomic<bool> primed{false};
-    if (!std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME") && !primed.exchange(true)) {
+    // identified; until it is, the first create of a process on a device builds and drops a minimal handle first (a few ms).
+    static std::atomic<bool> primed[64];                    // per device ordinal (zero-initialised)
+    if (!std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME") && dev < 64 && !primed[dev].exchange(true)) {
         fmgpu_config sc{};
         sc.block_size = 1024; sc.n_streams = 1; sc.device = dev; sc.pipeline_depth = 1;
         fmgpu_demod* scratch = nullptr;
