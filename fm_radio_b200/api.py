@@ -142,7 +142,7 @@ EXPORTED_SYMBOLS = [
     "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
     "fmgpu_chan_wait_external_stream", "fmgpu_chan_sync", "fmgpu_chan_stream", "fmgpu_chan_launch_count",
     "fmgpu_profile_stages7", "fmgpu_polyphase_us_create", "fmgpu_polyphase_us_process", "fmgpu_resample_linear",
-    "fmgpu_frames_to_s16", "fmgpu_calculate_fft", "fmgpu_get_fft",
+    "fmgpu_frames_to_s16", "fmgpu_calculate_fft", "fmgpu_get_fft", "fmgpu_set_option",
 ]
 
 _lib = None
@@ -218,6 +218,7 @@ def lib():
     L.fmgpu_rds_get_db.argtypes = [vp, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
     L.fmgpu_rds_get_db.restype = None
     L.fmgpu_get_partition.argtypes = [vp, C.POINTER(ci * 2)]
+    L.fmgpu_set_option.argtypes = [vp, C.c_char_p, ci]
     L.fmgpu_rds_device_fetch.argtypes = [vp]
     L.fmgpu_rds_device_counts.argtypes = [vp, ci, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(ci * 2)]
     L.fmgpu_rds_device_get_groups.argtypes = [vp, ci, C.c_ulonglong, C.POINTER(RDSGroup), ci]
@@ -412,6 +413,10 @@ class FMDemod:
         if not self.pcm_rate:
             del out["k7_audio_pcm"]
         return out
+
+    def set_option(self, name: str, value: int) -> None:
+        """Implementation switches for A/B measurements: "k1_fp32", "k5_literal" (include/fmgpu.h)."""
+        _check(self.L.fmgpu_set_option(self.h, name.encode(), int(value)), "fmgpu_set_option")
 
     def partition(self):
         """(SMs reserved for the recurrence stages, SMs of the FIR stages); (0, 0) = not partitioned."""

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfmgpu.so")
-CU_SOURCES = ["fmgpu.cu", "k1_fir4_discrim.cu", "k2_mpx.cu", "k3_pll.cu", "k4_mix_fir.cu", "k5_bpsk.cu", "k6_rds.cu", "k7_audio_pcm.cu", "k_fft.cu", "k_misc.cu", "chan.cu"]
+CU_SOURCES = ["fmgpu.cu", "k1_fir4_discrim.cu", "k1_toeplitz_i8.cu", "k2_mpx.cu", "k3_pll.cu", "k4_mix_fir.cu", "k5_bpsk.cu", "k6_rds.cu", "k7_audio_pcm.cu", "k_fft.cu", "k_misc.cu", "chan.cu"]
 CPP_SOURCES = ["filter_designer.cpp", "rds_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 
 namespace fm {
 
@@ -179,6 +180,7 @@ struct K5Params {
     int n_tiles_k4;             // number of power partials per stream
     int n_streams;
     int keep;
+    int literal;                // 1: the reference's per-sample loop instead of the symbol-wise loop (same bits; A/B aid)
 };
 
 // indices into the [field][stream] SoA state arrays of the per-stream recurrences
@@ -196,6 +198,23 @@ struct K5Debug {
     float2* rds; float2* raw_sym; float2* pll_sym; uint8_t* zcd; uint8_t* dump_trig;
     float* ted_raw; float* ted_pi; float* pll_raw; float* pll_pi; float2* dump_filter;
 };
+
+struct K1TParams {
+    const int8_t* bimg;        // [2 chunks][96 rows][128 B]: G digit planes, shared-memory (swizzled) image
+    const int* ptab;           // [32 lanes][6]: dp4a operands of the output before a tile (re, im per plane)
+    int off[3];       // 127 * sum of the plane's digits
+    float w[3];       // plane weights 65536 / S, 256 / S, 1 / S
+    float discrim_gain;
+    int n_rows;                // 128-byte rows per stream per block = block_size / 64
+    int tiles_per_stream, n_tiles, n_streams;
+    int base_offset;           // descriptor base-offset field of the row-shifted chunk (0: swizzle by absolute address)
+    float2* dbg_fm_in;         // keep_intermediates: [S][n_out] FIR outputs before the discriminator, else null
+};
+
+// K1 on the tensor cores (k1_toeplitz_i8.cu).  variant 0: tile staged twice, 1: one buffer + row-shifted descriptor
+void k1t_build_tables(const float* taps, std::vector<int8_t>& bimg, std::vector<int>& ptab, int off[3], float w[3]);
+cudaError_t launch_k1t(const uint8_t* iq, const uint8_t* hist_in, uint8_t* hist_out, float2* hist_f32_out, float* fm_demod,
+                       const K1TParams& p, int variant, int n_ctas, cudaStream_t st);
 
 // launchers (one per .cu file)
 cudaError_t launch_k1(bool u8, const void* iq, const float2* hist_in, float2* hist_out, float* fm_demod,

@@ -24,6 +24,7 @@
 
 extern "C" const void* fmgpu_rds_tables_(size_t* bytes);     // rds_host.cpp
 
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -78,11 +79,19 @@ struct fmgpu_demod {
     // SM partition (green contexts): the recurrence stages B, D get their own SMs
     CUgreenCtx gctx_rec = nullptr, gctx_fir = nullptr;
     int sms_rec = 0, sms_fir = 0;
+    int n_sm_fir = 148;            // SMs that run the FIR stages (the FIR partition, or the whole device)
     std::vector<Slot> slots;
     std::vector<HostMirror> mirrors;
     DebugBufs dbg;
     // per-stream state
     float2* k1_hist[2] = { nullptr, nullptr };
+    // K1 on the tensor cores (k1_toeplitz_i8.cu): byte history (ping-pong), G image, dp4a table, digit-plane constants
+    uint8_t* k1t_hist[2] = { nullptr, nullptr };
+    int8_t* k1t_bimg = nullptr; int* k1t_ptab = nullptr;
+    float k1t_taps[64] = { 0 }; bool k1t_ready = false, use_k1t = true;
+    int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
+    int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
+    bool k5_literal = false;
     float* k2_hist_demod = nullptr; float* k2_hist_out = nullptr; float* k2_scal = nullptr;
     float* pll_state = nullptr;
     float* k4_hist_x[2] = { nullptr, nullptr };
@@ -268,6 +277,19 @@ int alloc_all(fmgpu_demod* h) {
         CU(cudaStreamCreateWithPriority(&h->stD, cudaStreamNonBlocking, prio_hi));
         CU(cudaStreamCreateWithPriority(&h->stE, cudaStreamNonBlocking, prio_hi));
     }
+    h->use_k1t = std::getenv("FMGPU_K1_FP32") == nullptr;
+    h->k5_literal = std::getenv("FMGPU_K5_LITERAL") != nullptr;
+    {
+        int n_sm = 148;
+        CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+        h->n_sm_fir = h->sms_fir > 0 ? h->sms_fir : n_sm;
+    }
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMalloc((void**)&h->k1t_hist[i], S * 128));
+        CU(cudaMemset(h->k1t_hist[i], 127, S * 128));       // a new stream: zero FIR history <-> bytes 127
+    }
+    CU(cudaMalloc((void**)&h->k1t_bimg, 2 * 96 * 128));
+    CU(cudaMalloc((void**)&h->k1t_ptab, 32 * 6 * sizeof(int)));
     for (int i = 0; i < 2; i++) {
         CU(dalloc(&h->k1_hist[i], S * fm::K1_HIST));
         CU(dalloc(&h->k4_hist_x[i], S * fm::K4_NN));
@@ -337,6 +359,8 @@ int alloc_all(fmgpu_demod* h) {
 void free_all(fmgpu_demod* h) {
     cudaDeviceSynchronize();
     auto F = [](void* p) { if (p) cudaFree(p); };
+    for (int i = 0; i < 2; i++) { F(h->k1t_hist[i]); }
+    F(h->k1t_bimg); F(h->k1t_ptab);
     for (int i = 0; i < 2; i++) { F(h->k1_hist[i]); F(h->k4_hist_x[i]); F(h->k4_hist_m2[i]); F(h->k4_hist_m3[i]); }
     F(h->k2_hist_demod); F(h->k2_hist_out); F(h->k2_scal); F(h->pll_state); F(h->bpsk_state); F(h->lmr_phase); F(h->in_f32);
     F(h->rds_state); F(h->rds_glog); F(h->rds_blog); F(h->rds_tables); F(h->pcm_table);
@@ -395,6 +419,11 @@ int prepare_pcm(fmgpu_demod* h) {
 
 // Enqueue the chain for one block whose input is already ordered on stA (or signalled by ev_H).
 int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cudaEvent_t* prof = nullptr) {
+    // K1's FIR history is kept as bytes by the u8 kernels (exact) and as floats by the cf32 kernel; the u8 kernels also
+    // write the float copy, so cf32 may follow u8, but arbitrary floats cannot become bytes again
+    if (u8 && h->last_input_kind == 2)
+        return fail(FMGPU_ERR_STATE, "enqueue: a u8 block cannot follow a cf32 block on the same handle (the FIR history would be truncated to bytes)");
+    h->last_input_kind = u8 ? 1 : 2;
     update_filters(h);
     const int slot = (int)(h->step % (unsigned long long)h->depth);
     const int parity = (int)(h->step & 1ull);
@@ -425,7 +454,28 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.discrim_gain = 1.0f / (Wd * Ts) * 0.5f;
         p.n_out = h->n4; p.parity = parity; p.n_streams = h->S; p.first_block = (h->step == 0); p.dbg_fm_in = keep ? h->dbg.fm_in : nullptr;
         if (prof) CU(cudaEventRecord(prof[0], h->stA));
-        CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
+        if (u8 && h->use_k1t) {
+            // tensor-core path: the G image follows the fm_in taps (fmgpu_upload_taps may change them)
+            if (!h->k1t_ready || std::memcmp(h->k1t_taps, h->taps.fm_in, sizeof(h->k1t_taps)) != 0) {
+                std::vector<int8_t> bimg; std::vector<int> ptab;
+                fm::k1t_build_tables(h->taps.fm_in, bimg, ptab, h->k1t_off, h->k1t_w);
+                CU(cudaStreamSynchronize(h->stA));
+                CU(cudaMemcpy(h->k1t_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(h->k1t_ptab, ptab.data(), ptab.size() * sizeof(int), cudaMemcpyHostToDevice));
+                std::memcpy(h->k1t_taps, h->taps.fm_in, sizeof(h->k1t_taps));
+                h->k1t_ready = true;
+            }
+            fm::K1TParams t{};
+            t.bimg = h->k1t_bimg; t.ptab = h->k1t_ptab;
+            for (int i = 0; i < 3; i++) { t.off[i] = h->k1t_off[i]; t.w[i] = h->k1t_w[i]; }
+            t.discrim_gain = p.discrim_gain;
+            t.n_rows = h->B / 64; t.tiles_per_stream = (t.n_rows + 127) / 128; t.n_tiles = t.tiles_per_stream * h->S; t.n_streams = h->S;
+            t.base_offset = 0; t.dbg_fm_in = p.dbg_fm_in;
+            CU(fm::launch_k1t((const uint8_t*)iq_dev, h->k1t_hist[parity], h->k1t_hist[parity ^ 1], h->k1_hist[parity ^ 1], sl.fm_demod,
+                              t, 1, 2 * h->n_sm_fir, h->stA));
+        } else {
+            CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
+        }
     }
     {
         fm::K2Params p{};
@@ -539,7 +589,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.int_ted_KTs = 10.0f * Ts * k; p.int_pll_KTs = 10.0f * Ts * k;
         p.ted_Kp = 0.3f; p.pll_Kp = 0.3f;
         p.agc_target = 0.5f; p.agc_beta = 0.2f;
-        p.n = h->n64; p.n_tiles_k4 = h->k4_tiles; p.n_streams = h->S; p.keep = keep;
+        p.n = h->n64; p.n_tiles_k4 = h->k4_tiles; p.n_streams = h->S; p.keep = keep; p.literal = h->k5_literal ? 1 : 0;
         if (prof) CU(cudaEventRecord(prof[7], h->stD));
         CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, h->stD));
     }
@@ -621,10 +671,38 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
     // identified; until it is, the first create of a process on a device builds and drops a minimal handle first (a few ms).
     static std::atomic<bool> primed[64];                    // per device ordinal (zero-initialised)
     if (!std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME") && dev < 64 && !primed[dev].exchange(true)) {
-        fmgpu_config sc{};
-        sc.block_size = 1024; sc.n_streams = 1; sc.device = dev; sc.pipeline_depth = 1;
-        fmgpu_demod* scratch = nullptr;
-        if (fmgpu_create(&sc, &scratch) == FMGPU_OK) fmgpu_destroy(scratch);
+        // FMGPU_PRIME_MODE (measurement aid for the bisection in DESIGN.md section 9): which part of the scratch handle matters
+        const char* pm = std::getenv("FMGPU_PRIME_MODE");
+        const std::string mode = pm ? pm : "full";
+        if (mode == "gctx" || mode == "gctx_launch") {      // green contexts + stage streams only (+ one kernel on each partition)
+            fmgpu_demod tmp{};
+            tmp.device = dev;
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (create_partitioned_streams(&tmp, hi)) {
+                if (mode == "gctx_launch") {
+                    void* st8 = nullptr;
+                    if (cudaMalloc(&st8, 64 * fm::k6_state_bytes()) == cudaSuccess) {
+                        fm::launch_k6_init(st8, 64, tmp.stD);
+                        fm::launch_k6_init(st8, 64, tmp.stA);
+                        cudaStreamSynchronize(tmp.stD); cudaStreamSynchronize(tmp.stA);
+                        cudaFree(st8);
+                    }
+                }
+                cudaStream_t sts[7] = { tmp.stA, tmp.stA2, tmp.stP, tmp.stB, tmp.stC, tmp.stD, tmp.stE };
+                for (auto st : sts) if (st) cudaStreamDestroy(st);
+                destroy_partition(&tmp);
+            }
+        } else if (mode == "alloc") {                       // device + pinned allocations only
+            void* d = nullptr; void* hp = nullptr;
+            if (cudaMalloc(&d, 64 << 20) == cudaSuccess) { cudaMemset(d, 0, 64 << 20); cudaDeviceSynchronize(); cudaFree(d); }
+            if (cudaMallocHost(&hp, 1 << 20) == cudaSuccess) cudaFreeHost(hp);
+        } else if (mode != "none") {
+            fmgpu_config sc{};
+            sc.block_size = 1024; sc.n_streams = 1; sc.device = dev; sc.pipeline_depth = 1;
+            fmgpu_demod* scratch = nullptr;
+            if (fmgpu_create(&sc, &scratch) == FMGPU_OK && mode != "nodestroy") fmgpu_destroy(scratch);
+        }
         CU(cudaSetDevice(dev));
     }
     auto* h = new fmgpu_demod();
@@ -981,6 +1059,20 @@ int fmgpu_get_config(fmgpu_demod* h, fmgpu_config* out) {
 }
 
 long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
+
+// Implementation switches for A/B measurements and cross-checks (the defaults are the production path):
+//   "k1_fp32"     1: the u8 FIR + discriminator on the FP32 FMA pipe (k1_fir4_discrim_u8) instead of the tensor cores
+//   "k5_literal"  1: the BPSK synchroniser's per-sample loop instead of the symbol-wise loop (identical bits)
+int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
+    if (!h || !name) return fail(FMGPU_ERR_ARG, "set_option: null argument");
+    const std::string n = name;
+    if (n == "k1_fp32") {
+        if (h->step != 0 && h->use_k1t != (value == 0)) return fail(FMGPU_ERR_STATE, "set_option: k1_fp32 must be chosen before the first block");
+        h->use_k1t = value == 0;
+    } else if (n == "k5_literal") h->k5_literal = value != 0;
+    else return fail(FMGPU_ERR_ARG, "set_option: unknown option");
+    return FMGPU_OK;
+}
 
 int fmgpu_get_partition(fmgpu_demod* h, int sms[2]) {
     if (!h || !sms) return fail(FMGPU_ERR_ARG, "get_partition: null argument");

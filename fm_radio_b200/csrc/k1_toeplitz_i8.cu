@@ -1,0 +1,305 @@
+// K1 on the tensor cores: u8 IQ -> 64-tap /4 polyphase FIR -> polar discriminator -> fm_demod.
+//
+// Replaces the same reference code as k1_fir4_discrim.cu (file:line under /root/reference/src):
+//   App::Run u8 -> cf32 unpack, (float)u8 - 127.0f           app.cpp:56-65
+//   PolyphaseDownsampler<cf32>::process, M=4 K=16 NN=64      dsp/polyphase_filter.h:41-64,197-201
+//   FM_Demod::Process, atan2 + wrapped first difference      fm_demod/fm_demod.cpp:30-45
+//
+// The FIR is the ONE stage of the chain whose input is integer (rtl-sdr bytes), and a decimating FIR over a byte
+// stream is a block-Toeplitz contraction whose A operand is the raw capture itself:
+//
+//   row R of a stream = its bytes [128 R, 128 R + 128) = 64 IQ samples = the NEW input of outputs 16 R .. 16 R + 15
+//   A[R, kappa]  = byte 128 (R - 1) + kappa,  kappa < 256        (rows R - 1 and R back to back: overlapping windows)
+//   G[kappa, (j, c)] = b[(kappa - 8 j - 8) >> 1]  if (kappa & 1) == c and 0 <= kappa - 8 j - 8 < 128, else 0
+//   Y[R, (j, c)] = sum_kappa A[R, kappa] G[kappa, (j, c)]  = re (c = 0) / im (c = 1) of output 16 R + j before "- 127"
+//
+// i.e. M = 128 rows (2048 outputs) x N = 32 columns x K = 256 bytes per tile, with G = the 64 taps laid out as a
+// banded (Toeplitz) matrix.  Half of G is structural zeros, and the taps need three signed base-256 digit planes
+// (24-bit fixed point, |error| <= 2^-26: as exact as the fp32 taps) -- 12x the algorithmic MACs -- but
+// tcgen05.mma kind::i8 does 8192 MAC/clk/SM against the FMA pipe's 128 lanes: 8 MMAs of M128 N96 K32 = 384
+// clocks per tile where the FFMA2 kernel spends ~4700.  The accumulators are int32 in tensor memory, so the
+// sums are EXACT; "- 127" leaves as the integer constant 127 * sum(digits) per plane, and a silent capture
+// (all bytes 127) gives exact zeros like the reference's (float)u8 - 127.0f (atan2(0, 0) = 0, and the all-127
+// block that turns the reference's AGC into NaN for good).  The planes are recombined in fp32 by two FFMA2.
+// With the FIR off the FMA pipe the kernel is bound by HBM (2 B in + 1 B out per IQ sample).
+//
+// Shared memory holds the tile ONCE (129 rows of 128 bytes, 128-byte swizzle, cp.async 16-byte copies): the
+// K-chunk kappa < 128 of A is rows 0..127 of that buffer, the chunk kappa >= 128 is THE SAME buffer one row
+// later (descriptor start address + 128 bytes; the swizzle is a function of the absolute shared-memory address,
+// so the shifted view stays consistent).  The FIR history of a stream is its previous block's last row (128
+// bytes; a new stream starts from bytes 127 = the reference's zero history).
+//
+// One persistent CTA (128 threads = 128 TMEM lanes = 128 rows) walks tiles round-robin, software pipelined:
+//   iteration i:  wait for tile i's bytes | thread 0 issues tile i's 8 MMAs into TMEM buffer i & 1
+//                 | cp.async of tile i + 1 | epilogue of tile i - 1 from TMEM buffer (i - 1) & 1
+// so loads, MMAs and the discriminator epilogue of three consecutive tiles overlap; two CTAs per SM.
+// Epilogue per thread = one row = 16 outputs: tcgen05.ld, integer offset + magic-number int->float (exact),
+// plane recombination, minimax atan2 (fm_common.cuh), wrapped first difference, 4 x STG.128.
+// The angle of the output before a thread's first comes from the neighbouring lane / warp; for the tile's first
+// row it is the last output of the previous row, which depends on buffer row 0 only: warp 1 computes its exact
+// integer sums with dp4a (same digits, same recombination => the same bits as the tile that owns that output).
+#include "fm_common.cuh"
+#include "tcgen05.cuh"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace fm {
+
+constexpr int K1T_ROWS = 128;                        // A rows per tile = TMEM lanes = threads
+constexpr int K1T_NCOL = 32;                         // 16 outputs x (re, im)
+constexpr int K1T_PLANES = 3;
+constexpr int K1T_N = K1T_NCOL * K1T_PLANES;         // 96 accumulator columns
+constexpr int K1T_ABUF = 17 * 1024;                  // 129 rows x 128 B, padded to the 1024-byte swizzle atom
+constexpr int K1T_BCHUNK = K1T_N * 128;              // 12 KB: one 128-byte K chunk of G
+constexpr int K1T_BBYTES = 2 * K1T_BCHUNK;
+constexpr int K1T_TMEM_COLS = 256;                   // 2 accumulator buffers of 128 columns (96 used)
+constexpr float K1T_MAGIC = 12582912.0f;             // 1.5 * 2^23: as_float(0x4B400000 + v) == MAGIC + v for |v| < 2^22
+constexpr int K1T_SMEM = K1T_BBYTES + 2 * K1T_ABUF + 1024;
+constexpr int K1T_SMEM_DUAL = K1T_SMEM + 2 * K1T_ROWS * 128;
+
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a_u8x4, int b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ float k1t_wrap_phase(float x) {       // fm_demod.cpp:6-10, as two selects
+    const float lo = x - 2.0f * PI_F, hi = x + 2.0f * PI_F;
+    return (x >= PI_F) ? lo : ((x <= -PI_F) ? hi : x);
+}
+
+// exact plane sums (integers) -> sum_k b[k] (u - 127): the same instruction sequence everywhere it is used
+__device__ __forceinline__ float2 k1t_combine(uint32_t r0, uint32_t i0, uint32_t r1, uint32_t i1, uint32_t r2, uint32_t i2,
+                                              const uint32_t (&K)[3], const float2 (&W)[3]) {
+    const float2 nm = make_float2(-K1T_MAGIC, -K1T_MAGIC);
+    const float2 f0 = __fadd2_rn(make_float2(__uint_as_float(r0 + K[0]), __uint_as_float(i0 + K[0])), nm);
+    const float2 f1 = __fadd2_rn(make_float2(__uint_as_float(r1 + K[1]), __uint_as_float(i1 + K[1])), nm);
+    const float2 f2 = __fadd2_rn(make_float2(__uint_as_float(r2 + K[2]), __uint_as_float(i2 + K[2])), nm);
+    return __ffma2_rn(f0, W[0], __ffma2_rn(f1, W[1], __fmul2_rn(f2, W[2])));
+}
+
+template <bool DUAL>
+__global__ void __launch_bounds__(K1T_ROWS, 2)
+k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_in, uint8_t* __restrict__ hist_out,
+               float2* __restrict__ hist_f32_out, float* __restrict__ fm_demod, const __grid_constant__ K1TParams p)
+{
+    extern __shared__ uint8_t k1t_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)k1t_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;
+    uint8_t* sA = sB + K1T_BBYTES;                   // [2][K1T_ABUF]
+    uint8_t* sA2 = sA + 2 * K1T_ABUF;                // DUAL only: [2][128 rows] = the tile's rows 1..128 staged a second time
+    __shared__ __align__(8) uint64_t bar_acc[2];     // the MMAs of the tile in TMEM buffer b have completed
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_theta[2][4];                  // last angle of each warp's rows
+    __shared__ float s_thprev[2];                    // angle of the output before the tile
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < K1T_BBYTES / 16; i += K1T_ROWS) ((uint4*)sB)[i] = __ldg((const uint4*)p.bimg + i);
+    if (tid == 0) { tc::mbar_init(&bar_acc[0], 1); tc::mbar_init(&bar_acc[1], 1); tc::mbar_init_fence(); }
+    if (warp == 0) tc::tmem_alloc(&s_tmem, K1T_TMEM_COLS);
+    int pw[6] = { 0, 0, 0, 0, 0, 0 };
+    if (warp == 1) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) pw[q] = p.ptab[lane * 6 + q];
+    }
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t sA_addr = tc::smem_u32(sA), sA2_addr = tc::smem_u32(sA2), sB_addr = tc::smem_u32(sB);
+    const size_t stream_bytes = (size_t)p.n_rows * 128;
+    const uint32_t Kc[3] = { 0x4B400000u - (uint32_t)p.off[0], 0x4B400000u - (uint32_t)p.off[1], 0x4B400000u - (uint32_t)p.off[2] };
+    const float2 Wc[3] = { make_float2(p.w[0], p.w[0]), make_float2(p.w[1], p.w[1]), make_float2(p.w[2], p.w[2]) };
+    constexpr uint32_t IDESC = tc::idesc_i8_u8s8(K1T_ROWS, K1T_N);
+
+    // buffer row q of a tile <-> data row row0 - 1 + q of its stream (q = 0: the halo = previous row / history)
+    auto stage = [&](int tile, int buf) {
+        const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
+        const int n_valid = min(K1T_ROWS, p.n_rows - row0);
+        const uint8_t* src = iq + (size_t)s * stream_bytes + (ptrdiff_t)(row0 - 1) * 128;
+        const uint8_t* hsrc = hist_in + (size_t)s * 128;
+        uint8_t* dst = sA + buf * K1T_ABUF;
+        uint8_t* dst2 = sA2 + buf * (K1T_ROWS * 128);
+        for (int ci = tid; ci < (n_valid + 1) * 8; ci += K1T_ROWS) {
+            const int q = ci >> 3, c = ci & 7;
+            const uint8_t* g = (row0 == 0 && q == 0) ? hsrc + c * 16 : src + (size_t)ci * 16;
+            tc::cp_async16(dst + q * 128 + ((c ^ (q & 7)) << 4), g);
+            if (DUAL && q >= 1) tc::cp_async16(dst2 + (q - 1) * 128 + ((c ^ ((q - 1) & 7)) << 4), g);
+        }
+        tc::cp_async_commit();
+    };
+
+    // everything of a tile that reads its bytes from shared memory (before the buffer is recycled)
+    auto pre_epilogue = [&](int tile, int buf) {
+        const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
+        const int n_valid = min(K1T_ROWS, p.n_rows - row0);
+        const uint8_t* A = sA + buf * K1T_ABUF;
+        if (warp == 1) {
+            // the output before the tile = output 15 of buffer row 0: all 64 taps on that row's 128 bytes
+            const uint32_t w4 = *(const uint32_t*)(A + 4 * lane);                // row 0: swizzle key 0
+            int a[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) a[q] = __reduce_add_sync(0xffffffffu, dp4a_u8s8(w4, pw[q], 0));
+            if (lane == 0) {
+                const float2 z = k1t_combine((uint32_t)a[0], (uint32_t)a[1], (uint32_t)a[2], (uint32_t)a[3], (uint32_t)a[4], (uint32_t)a[5], Kc, Wc);
+                s_thprev[buf] = fm_atan2f(z.y, z.x);
+            }
+        } else if (row0 + n_valid == p.n_rows) {
+            // history for the next block: the stream's last row, as bytes (this kernel) and as floats (cf32 kernel)
+            const uint8_t* row = A + n_valid * 128;
+            const int key = n_valid & 7;
+            if (warp == 0 && lane < 8)
+                *(uint4*)(hist_out + (size_t)s * 128 + lane * 16) = *(const uint4*)(row + ((lane ^ key) << 4));
+            if (warp >= 2) {
+                const int t0 = (warp - 2) * 32 + lane;                           // 64 samples
+                const uint8_t* b = row + (((t0 >> 3) ^ key) << 4) + (t0 & 7) * 2;
+                hist_f32_out[(size_t)s * K1_HIST + t0] = make_float2((float)b[0] - 127.0f, (float)b[1] - 127.0f);
+            }
+        }
+    };
+
+    auto epilogue = [&](int tile, int buf, int par) {
+        const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
+        const int n_valid = min(K1T_ROWS, p.n_rows - row0);
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128);
+        float out[16];
+        float prev = 0.0f;
+        const size_t o_base = (size_t)s * p.n_rows * 16 + (size_t)(row0 + tid) * 16;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t a0[16], a1[16], a2[16];
+            tc::tmem_ld16(lane_addr + 0 * K1T_NCOL + 16 * h, a0);
+            tc::tmem_ld16(lane_addr + 1 * K1T_NCOL + 16 * h, a1);
+            tc::tmem_ld16(lane_addr + 2 * K1T_NCOL + 16 * h, a2);
+            tc::tmem_ld_wait();
+            float2 z[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) z[j] = k1t_combine(a0[2 * j], a0[2 * j + 1], a1[2 * j], a1[2 * j + 1], a2[2 * j], a2[2 * j + 1], Kc, Wc);
+            if (p.dbg_fm_in && tid < n_valid) {
+                float4* d4 = (float4*)(p.dbg_fm_in + o_base + 8 * h);
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) d4[j >> 1] = make_float4(z[j].x, z[j].y, z[j + 1].x, z[j + 1].y);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const float2 th = fm_atan2f_x2(z[j].y, z[j].x, z[j + 1].y, z[j + 1].x);
+                out[8 * h + j] = (h == 0 && j == 0) ? th.x : th.x - prev;        // out[0] is fixed up below
+                out[8 * h + j + 1] = th.y - th.x;
+                prev = th.y;
+            }
+        }
+        tc::fence_before();                                                      // this thread's TMEM reads are done
+        // angle of the output before this thread's first one: previous lane / previous warp / dp4a path
+        float th_before = __shfl_up_sync(0xffffffffu, prev, 1);
+        if (lane == 31) s_theta[par][warp] = prev;
+        __syncthreads();
+        if (lane == 0) th_before = (warp == 0) ? s_thprev[buf] : s_theta[par][warp - 1];
+        if (tid >= n_valid) return;
+        out[0] -= th_before;
+#pragma unroll
+        for (int r = 0; r < 16; r++) out[r] = k1t_wrap_phase(out[r]) * p.discrim_gain;
+        float4* dst = (float4*)(fm_demod + o_base);
+#pragma unroll
+        for (int q = 0; q < 4; q++) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    };
+
+    int it = 0, prev_tile = -1;
+    if ((int)blockIdx.x < p.n_tiles) stage(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
+        const int buf = it & 1;
+        tc::cp_async_wait<0>();
+        tc::fence_async_smem();
+        __syncthreads();                             // tile's bytes are in place; everyone has left iteration it - 1
+        if (tid == 0) {
+            tc::fence_after();
+            const uint32_t a_base = sA_addr + buf * K1T_ABUF, a2_base = sA2_addr + buf * (K1T_ROWS * 128);
+#pragma unroll
+            for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const uint64_t a_desc = DUAL ? tc::smem_desc_sw128((kc ? a2_base : a_base) + ks * 32)
+                                                 : tc::smem_desc_sw128(a_base + kc * 128 + ks * 32, kc ? (uint32_t)p.base_offset : 0u);
+                    const uint64_t b_desc = tc::smem_desc_sw128(sB_addr + kc * K1T_BCHUNK + ks * 32);
+                    tc::mma_i8(tmem + (uint32_t)(buf * 128), a_desc, b_desc, IDESC, (kc | ks) != 0 ? 1u : 0u);
+                }
+            tc::commit(&bar_acc[buf]);
+        }
+        pre_epilogue(tile, buf);
+        if (it >= 1) {
+            tc::mbar_wait(&bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));   // tile it - 1: accumulators complete, its bytes dead
+            tc::fence_after();
+        }
+        const int next = tile + gridDim.x;
+        if (next < p.n_tiles) stage(next, buf ^ 1);
+        if (it >= 1) epilogue(prev_tile, buf ^ 1, it & 1);
+        prev_tile = tile;
+    }
+    if (it >= 1) {
+        tc::mbar_wait(&bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+        tc::fence_after();
+        epilogue(prev_tile, (it - 1) & 1, it & 1);
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, K1T_TMEM_COLS);
+}
+
+// ---- host side: digit planes of the taps -> shared-memory image of G, dp4a table, constants ----
+void k1t_build_tables(const float* taps, std::vector<int8_t>& bimg, std::vector<int>& ptab, int off[3], float w[3])
+{
+    double gmax = 0.0;
+    for (int k = 0; k < K1_NN; k++) gmax = std::max(gmax, (double)std::fabs(taps[k]));
+    if (!(gmax > 0.0)) gmax = 1.0;
+    // three balanced base-256 digits of round(b * 2^e), |value| < 127 * 65536
+    const int e = (int)std::floor(std::log2(8.29e6 / gmax));
+    const double S = std::ldexp(1.0, e);
+    w[0] = (float)(65536.0 / S); w[1] = (float)(256.0 / S); w[2] = (float)(1.0 / S);
+    int d[K1_NN][3];
+    for (int k = 0; k < K1_NN; k++) {
+        long long v = std::llround((double)taps[k] * S);
+        d[k][2] = (int)(int8_t)(v & 0xff); v = (v - d[k][2]) >> 8;
+        d[k][1] = (int)(int8_t)(v & 0xff); v = (v - d[k][1]) >> 8;
+        d[k][0] = (int)v;
+    }
+    for (int pl = 0; pl < 3; pl++) { off[pl] = 0; for (int k = 0; k < K1_NN; k++) off[pl] += 127 * d[k][pl]; }
+    bimg.assign(K1T_BBYTES, 0);
+    for (int kappa = 0; kappa < 256; kappa++)
+        for (int col = 0; col < K1T_NCOL; col++) {
+            const int j = col >> 1, c = col & 1, rel = kappa - 8 * j - 8;
+            if ((kappa & 1) != c || rel < 0 || rel >= 128) continue;
+            const int k = rel >> 1, kc = kappa >> 7, kk = kappa & 127;
+            for (int pl = 0; pl < 3; pl++) {
+                const int n = pl * K1T_NCOL + col;
+                bimg[(size_t)kc * K1T_BCHUNK + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((kk >> 4) ^ (n & 7)) << 4) + (kk & 15)] = (int8_t)d[k][pl];
+            }
+        }
+    ptab.assign(32 * 6, 0);
+    for (int l = 0; l < 32; l++)
+        for (int pl = 0; pl < 3; pl++) {
+            const uint32_t lo = (uint32_t)(uint8_t)(int8_t)d[2 * l][pl], hi = (uint32_t)(uint8_t)(int8_t)d[2 * l + 1][pl];
+            ptab[l * 6 + 2 * pl + 0] = (int)(lo | (hi << 16));               // bytes (I, Q, I, Q) x (d, 0, d', 0)
+            ptab[l * 6 + 2 * pl + 1] = (int)((lo << 8) | (hi << 24));        //                   x (0, d, 0, d')
+        }
+}
+
+cudaError_t launch_k1t(const uint8_t* iq, const uint8_t* hist_in, uint8_t* hist_out, float2* hist_f32_out, float* fm_demod,
+                       const K1TParams& p, int variant, int n_ctas, cudaStream_t st)
+{
+    cudaError_t e;
+    const int grid = std::max(1, std::min(p.n_tiles, n_ctas));
+    if (variant == 0) {
+        e = cudaFuncSetAttribute(k1_toeplitz_i8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM_DUAL);
+        if (e != cudaSuccess) return e;
+        k1_toeplitz_i8<true><<<grid, K1T_ROWS, K1T_SMEM_DUAL, st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
+    } else {
+        e = cudaFuncSetAttribute(k1_toeplitz_i8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM);
+        if (e != cudaSuccess) return e;
+        k1_toeplitz_i8<false><<<grid, K1T_ROWS, K1T_SMEM, st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace fm

@@ -8,34 +8,67 @@
 //     Trigger_Cooldown::on_trigger                            fm_demod/trigger_cooldown.cpp:4-13
 //     TED_Clock::get_timing_error / update                    fm_demod/ted_clock.cpp:18-44
 //   imag extraction of the dumped symbols                     broadcast_fm_demod.cpp:542-546
-// One thread per stream (same reasoning as K3; this loop is 8x shorter and data dependent, so it is
-// kept in the reference's exact operation order).  The block's RDS power arrives as per-tile
-// partial sums from K4 and is reduced here in a fixed order.
+//
+// One thread per stream, one warp per CTA (same reasoning as K3: the loop is non-linear, so the parallelism is
+// across streams and the time of a batch is n_samples x the latency of the dependent chain).  The arithmetic lives
+// in k5_core.h; this file is the warp loop around it.  First version: the reference's per-sample order, ~390
+// cycles per sample (libm atan2f, two roundf and two serial polynomial sines on the chain of EVERY sample,
+// because in a warp some lane dumps a symbol at almost every sample).  This version walks SYMBOL by symbol
+// (k5_symbol_step): every lane advances to its own next dump, so the dump work (atan2 -> carrier error) is done
+// once per symbol for all 32 lanes together, the carrier loop + rotation of the symbol's samples runs as one batch
+// with instruction-level parallelism, and only the timing loop's ~12-op chain remains per sample.  Lanes therefore
+// sit at different samples of their rows; loads are per-lane 8-byte reads of lines prefetched into the L1.
+// Bit-identical to the per-sample loop (k5_sample; checked on the host by tests/test_k5_core_cpu.py and on the
+// device by FMGPU_K5_LITERAL=1 in tests/test_gpu_parity.py).
 #include "fm_common.cuh"
+#include "k5_core.h"
+#include <cstdlib>
 
 namespace fm {
 
-template <bool KEEP>
+constexpr int K5_NB = 7;        // samples per batch: a locked clock dumps every 6 or 7 samples (16000 / 2375 = 6.74)
+
+struct K5Fetch {
+    const float2* row;
+    __device__ __forceinline__ K5Sample operator()(int i) const { const float2 v = __ldg(row + i); return K5Sample{ v.x, v.y }; }
+};
+
+struct K5LiveDebug {            // keep_intermediates: the display arrays of bpsk_synchroniser.cpp:175-182
+    static constexpr bool kLive = true;
+    K5Debug d; size_t o;
+    __device__ __forceinline__ void sample(int i, float x_re, float x_im, float iq_re, float iq_im, bool is_zcd, bool is_ted,
+                                           float ted_raw, float ted_pi, float pll_raw, float pll_pi, float dump_re, float dump_im) const {
+        d.rds[o + i] = make_float2(x_re, x_im);
+        d.pll_sym[o + i] = make_float2(iq_re, iq_im);
+        d.zcd[o + i] = is_zcd ? 1 : 0;
+        d.dump_trig[o + i] = is_ted ? 1 : 0;
+        d.ted_raw[o + i] = ted_raw;
+        d.ted_pi[o + i] = ted_pi;
+        d.pll_raw[o + i] = pll_raw;
+        d.pll_pi[o + i] = pll_pi;
+        d.dump_filter[o + i] = make_float2(dump_re, dump_im);
+    }
+};
+
+template <bool KEEP, bool LITERAL>
 __global__ void __launch_bounds__(32)
 k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_partial,
         float* __restrict__ state, float* __restrict__ pred_sym, int* __restrict__ sym_count,
-        float2* __restrict__ dbg_rds, float2* __restrict__ dbg_raw_sym, float2* __restrict__ dbg_pll_sym,
-        uint8_t* __restrict__ dbg_zcd, uint8_t* __restrict__ dbg_dump_trig,
-        float* __restrict__ dbg_ted_raw, float* __restrict__ dbg_ted_pi,
-        float* __restrict__ dbg_pll_raw, float* __restrict__ dbg_pll_pi, float2* __restrict__ dbg_dump_filter,
-        const __grid_constant__ K5Params p)
+        const K5Debug dbgp, const __grid_constant__ K5Params p)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n_streams) return;
+    const int s_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s_raw < p.n_streams;
+    const int s = valid ? s_raw : p.n_streams - 1;
     const int S = p.n_streams;
 #define ST(f) state[(size_t)(f) * S + s]
-    float lp_x1 = ST(BP_LPF_PLL_X1), lp_y1 = ST(BP_LPF_PLL_Y1), int_pll = ST(BP_INT_PLL);
-    float mix_t = ST(BP_MIX_T), pll_prev = ST(BP_PLL_PREV_ERR);
-    float zcd_xn = ST(BP_ZCD_XN);
-    int cooldown = (int)ST(BP_COOLDOWN);
-    float ted_yn = ST(BP_TED_YN), ted_phase_error = ST(BP_TED_PHASE_ERR), ted_prev = ST(BP_TED_PREV_ERR);
-    float lt_x1 = ST(BP_LPF_TED_X1), lt_y1 = ST(BP_LPF_TED_Y1), int_ted = ST(BP_INT_TED);
-    float dump_re = ST(BP_DUMP_RE), dump_im = ST(BP_DUMP_IM);
+    K5Lane L;
+    L.lp_x1 = ST(BP_LPF_PLL_X1); L.lp_y1 = ST(BP_LPF_PLL_Y1); L.int_pll = ST(BP_INT_PLL);
+    L.mix_t = ST(BP_MIX_T); L.pll_prev = ST(BP_PLL_PREV_ERR);
+    L.zcd_xn = ST(BP_ZCD_XN);
+    L.cooldown = (int)ST(BP_COOLDOWN);
+    L.ted_yn = ST(BP_TED_YN); L.ted_phase_error = ST(BP_TED_PHASE_ERR); L.ted_prev = ST(BP_TED_PREV_ERR);
+    L.lt_x1 = ST(BP_LPF_TED_X1); L.lt_y1 = ST(BP_LPF_TED_Y1); L.int_ted = ST(BP_INT_TED);
+    L.dump_re = ST(BP_DUMP_RE); L.dump_im = ST(BP_DUMP_IM);
     float gain = ST(BP_AGC_GAIN);
 
     // agc.h:12-19
@@ -44,113 +77,72 @@ k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_p
     const float avg_power = pw / (float)p.n;
     const float target_gain = sqrtf(p.agc_target / avg_power);
     gain = gain + p.agc_beta * (target_gain - gain);
+    L.gain = gain;
 
-    const float4* x4 = (const float4*)(rds_in + (size_t)s * p.n);
+    K5Coef c;
+    c.pll_b0 = p.pll_b[0]; c.pll_b1 = p.pll_b[1]; c.pll_a0 = p.pll_a[0]; c.int_pll_KTs = p.int_pll_KTs; c.pll_Kp = p.pll_Kp;
+    c.mixer_fgain = p.mixer_fgain; c.mixer_KTs = p.mixer_KTs;
+    c.ted_b0 = p.ted_b[0]; c.ted_b1 = p.ted_b[1]; c.ted_a0 = p.ted_a[0]; c.int_ted_KTs = p.int_ted_KTs; c.ted_Kp = p.ted_Kp;
+    c.dump_KTs = p.dump_KTs; c.ted_fgain = p.ted_fgain; c.ted_fcenter = p.ted_fcenter; c.ted_KTs = p.ted_KTs;
+    c.cooldown_N = p.cooldown_N;
+
     const size_t o = (size_t)s * p.n;
+    const int n = p.n;
+    const K5Fetch fetch{ rds_in + o };
     int total = 0;
-    // 8 samples (two 32-byte sectors) per lane are loaded one group ahead of their use, so the
-    // global-load latency never sits on the recurrence
-    float4 nx[4] = { x4[0], x4[1], x4[2], x4[3] };
-    for (int i0 = 0; i0 < p.n; i0 += 8) {
-    const float4 cur[4] = { nx[0], nx[1], nx[2], nx[3] };
-    if (i0 + 8 < p.n) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) nx[q] = x4[(i0 >> 1) + 4 + q];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int i = i0 + j;
-        float2 xi = (j & 1) ? make_float2(cur[j >> 1].z, cur[j >> 1].w) : make_float2(cur[j >> 1].x, cur[j >> 1].y);
-        xi.x *= gain; xi.y *= gain;
-        // PI controller of the carrier PLL (:106-113)
-        const float pll_lpf = fmaf(pll_prev, p.pll_b[1], fmaf(lp_x1, p.pll_b[0], lp_y1 * p.pll_a[0]));
-        lp_x1 = pll_prev; lp_y1 = pll_lpf;
-        int_pll = clampf(fmaf(p.int_pll_KTs, pll_prev, int_pll), -1.0f, 1.0f);
-        const float PI_pll_error = fmaf(pll_lpf, p.pll_Kp, int_pll);
-        // PLL_Mixer::Update, f_center = 0
-        const float control = clampf(PI_pll_error, -1.0f, 1.0f);
-        const float freq = 0.0f + control * p.mixer_fgain;
-        float tt = fmaf(p.mixer_KTs, freq, mix_t);
-        tt = tt - roundf(tt);
-        mix_t = tt;
-        float dc = tt + 0.25f;
-        dc = dc - roundf(dc);
-        const float c = chebyshev_sine(dc), sn = chebyshev_sine(tt);
-        const float iq_re = xi.x * c - xi.y * sn;
-        const float iq_im = xi.x * sn + xi.y * c;
-        // zero crossing on Q with cooldown (:127-132)
-        bool is_zcd = (iq_im * zcd_xn) < 0.0f;
-        zcd_xn = iq_im;
-        if (is_zcd && cooldown == 0) { cooldown = p.cooldown_N; }
-        else { if (cooldown > 0) cooldown--; is_zcd = false; }
-        if (is_zcd) {
-            float err = 2.0f * ted_yn;
-            if (err > 1.0f) err = err - 2.0f;
-            ted_prev = err;
-        }
-        // TED PI controller (:134-143)
-        const float ted_lpf = fmaf(ted_prev, p.ted_b[1], fmaf(lt_x1, p.ted_b[0], lt_y1 * p.ted_a[0]));
-        lt_x1 = ted_prev; lt_y1 = ted_lpf;
-        int_ted = clampf(fmaf(p.int_ted_KTs, ted_prev, int_ted), -1.0f, 1.0f);
-        const float PI_ted_error = fmaf(p.ted_Kp, ted_lpf, int_ted);
-        ted_phase_error = -PI_ted_error;
-        // integrate and dump (:146)
-        dump_re = fmaf(p.dump_KTs, iq_re, dump_re);
-        dump_im = fmaf(p.dump_KTs, iq_im, dump_im);
-        // TED_Clock::update (ted_clock.cpp:31-44)
-        bool is_ted;
-        {
-            const float ctl = clampf(ted_phase_error, -1.0f, 1.0f);
-            const float f = fmaf(ctl, p.ted_fgain, p.ted_fcenter);
-            const float v = fmaf(p.ted_KTs, f, ted_yn);
-            ted_yn = v;
-            const float offset = p.ted_KTs * f / 2.0f;
-            is_ted = !(v < (1.0f - offset));
-            if (is_ted) ted_yn = 0.0f;
-        }
-        if (is_ted) {
-            const float sym_re = dump_re, sym_im = dump_im;
-            dump_re = 0.0f; dump_im = 0.0f;
-            const float sym_phase = atan2f(sym_im, sym_re);
-            const float est = (sym_phase > 0.0f) ? (PI_F / 2.0f - sym_phase) : (-PI_F / 2.0f - sym_phase);
-            pll_prev = est / (PI_F / 2.0f);
-            pred_sym[o + total] = sym_im;
-            if (KEEP) dbg_raw_sym[o + total] = make_float2(sym_re, sym_im);
-            total++;
-        }
-        if (KEEP) {
-            dbg_rds[o + i] = xi;
-            dbg_pll_sym[o + i] = make_float2(iq_re, iq_im);
-            dbg_zcd[o + i] = is_zcd ? 1 : 0;
-            dbg_dump_trig[o + i] = is_ted ? 1 : 0;
-            dbg_ted_raw[o + i] = ted_prev;
-            dbg_ted_pi[o + i] = PI_ted_error;
-            dbg_pll_raw[o + i] = pll_prev;
-            dbg_pll_pi[o + i] = PI_pll_error;
-            dbg_dump_filter[o + i] = make_float2(dump_re, dump_im);
+    K5LiveDebug live{ dbgp, o };
+    K5NoDebug none;
+    if (LITERAL) {
+        if (valid)
+            for (int i = 0; i < n; i++) {
+                const K5Sample x = fetch(i);
+                float sr = 0.0f, si = 0.0f;
+                const bool d = KEEP ? k5_sample(c, L, i, x.x_re, x.x_im, sr, si, live) : k5_sample(c, L, i, x.x_re, x.x_im, sr, si, none);
+                if (d) {
+                    pred_sym[o + total] = si;
+                    if (KEEP) dbgp.raw_sym[o + total] = make_float2(sr, si);
+                    total++;
+                }
+            }
+    } else {
+        int pos = valid ? 0 : n;
+        while (__any_sync(0xffffffffu, pos < n)) {
+            // the line 2-3 symbols ahead of this lane -> L1 (the row was written by K4 and sits in the L2)
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(fetch.row + min(pos + 24, n - 1)));
+            float sr = 0.0f, si = 0.0f;
+            const bool d = KEEP ? k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, live)
+                                : k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, none);
+            if (d) {
+                pred_sym[o + total] = si;
+                if (KEEP) dbgp.raw_sym[o + total] = make_float2(sr, si);
+                total++;
+            }
         }
     }
-    }
+    if (!valid) return;
     sym_count[s] = total;
-    ST(BP_LPF_PLL_X1) = lp_x1; ST(BP_LPF_PLL_Y1) = lp_y1; ST(BP_INT_PLL) = int_pll;
-    ST(BP_MIX_T) = mix_t; ST(BP_PLL_PREV_ERR) = pll_prev; ST(BP_ZCD_XN) = zcd_xn;
-    ST(BP_COOLDOWN) = (float)cooldown;
-    ST(BP_TED_YN) = ted_yn; ST(BP_TED_PHASE_ERR) = ted_phase_error; ST(BP_TED_PREV_ERR) = ted_prev;
-    ST(BP_LPF_TED_X1) = lt_x1; ST(BP_LPF_TED_Y1) = lt_y1; ST(BP_INT_TED) = int_ted;
-    ST(BP_DUMP_RE) = dump_re; ST(BP_DUMP_IM) = dump_im; ST(BP_AGC_GAIN) = gain;
+    ST(BP_LPF_PLL_X1) = L.lp_x1; ST(BP_LPF_PLL_Y1) = L.lp_y1; ST(BP_INT_PLL) = L.int_pll;
+    ST(BP_MIX_T) = L.mix_t; ST(BP_PLL_PREV_ERR) = L.pll_prev; ST(BP_ZCD_XN) = L.zcd_xn;
+    ST(BP_COOLDOWN) = (float)L.cooldown;
+    ST(BP_TED_YN) = L.ted_yn; ST(BP_TED_PHASE_ERR) = L.ted_phase_error; ST(BP_TED_PREV_ERR) = L.ted_prev;
+    ST(BP_LPF_TED_X1) = L.lt_x1; ST(BP_LPF_TED_Y1) = L.lt_y1; ST(BP_INT_TED) = L.int_ted;
+    ST(BP_DUMP_RE) = L.dump_re; ST(BP_DUMP_IM) = L.dump_im; ST(BP_AGC_GAIN) = gain;
 #undef ST
 }
 
 cudaError_t launch_k5(const float2* rds_in, const float* rds_power_partial, float* state, float* pred_sym,
                       int* sym_count, const K5Debug& d, const K5Params& p, cudaStream_t st)
 {
+    const bool literal = p.literal != 0;                 // A/B aid (fmgpu_set_option "k5_literal"): the per-sample loop
     const int grid = (p.n_streams + 31) / 32;
-    if (p.keep)
-        k5_bpsk<true><<<grid, 32, 0, st>>>(rds_in, rds_power_partial, state, pred_sym, sym_count, d.rds, d.raw_sym,
-            d.pll_sym, d.zcd, d.dump_trig, d.ted_raw, d.ted_pi, d.pll_raw, d.pll_pi, d.dump_filter, p);
-    else
-        k5_bpsk<false><<<grid, 32, 0, st>>>(rds_in, rds_power_partial, state, pred_sym, sym_count, nullptr, nullptr,
-            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, p);
+    const K5Debug nd{};
+    if (p.keep) {
+        if (literal) k5_bpsk<true, true><<<grid, 32, 0, st>>>(rds_in, rds_power_partial, state, pred_sym, sym_count, d, p);
+        else         k5_bpsk<true, false><<<grid, 32, 0, st>>>(rds_in, rds_power_partial, state, pred_sym, sym_count, d, p);
+    } else {
+        if (literal) k5_bpsk<false, true><<<grid, 32, 0, st>>>(rds_in, rds_power_partial, state, pred_sym, sym_count, nd, p);
+        else         k5_bpsk<false, false><<<grid, 32, 0, st>>>(rds_in, rds_power_partial, state, pred_sym, sym_count, nd, p);
+    }
     return cudaGetLastError();
 }
 

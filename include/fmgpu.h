@@ -203,6 +203,13 @@ int fmgpu_profile_stages7(fmgpu_demod* h, const uint8_t* iq_dev, int n_blocks, f
  * synchroniser, RDS bit path), sms[1] = SMs of the FIR stages; {0, 0} when the device is not
  * partitioned (FMGPU_NO_PARTITION=1 in the environment, or the driver has no green contexts). */
 int fmgpu_get_partition(fmgpu_demod* h, int sms[2]);
+/* Implementation switches for A/B measurements and parity cross-checks (no reference counterpart; the
+ * defaults are the production path).  name = "k1_fp32": value 1 runs the u8 FIR + discriminator
+ * (app.cpp:56-65, dsp/polyphase_filter.h:41-64, fm_demod/fm_demod.cpp:30-45) on the FP32 FMA pipe instead of
+ * the tensor cores (choose before the first block); name = "k5_literal": value 1 runs the BPSK synchroniser
+ * (fm_demod/bpsk_synchroniser.cpp:94-186) sample by sample in the reference's order instead of symbol by symbol
+ * (identical bits). */
+int fmgpu_set_option(fmgpu_demod* h, const char* name, int value);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long fmgpu_launch_count(fmgpu_demod* h);
 

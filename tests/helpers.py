@@ -63,3 +63,14 @@ def copy_taps(src: "bind.CpuDemod", dst_set):
     for name in REF_TAP_NAMES:
         b, a = src.taps(name)
         dst_set(name, b, a[:len(b)] if name in IIR_NAMES else None)
+
+
+def oracle_stream_job(args):
+    """Process-pool worker (spawned, no CUDA): synthesise stream `s` of config 3 (for_stream(s)), run a CPU checker
+    over it and return (capture bytes, groups, rds bytes, db).  kind = "port" | "ref"."""
+    s, n_blocks, block_size, kind = args
+    cap = synth.synth_u8_numpy(block_size * n_blocks, synth.StreamParams.for_stream(s))
+    chk = bind.CpuDemod(block_size, kind)
+    for k in range(n_blocks):
+        chk.process_u8(cap[2 * block_size * k:2 * block_size * (k + 1)])
+    return cap, chk.groups(), chk.rds_bytes(), chk.db()

@@ -1,0 +1,193 @@
+"""GPU suite, part 2 (-m gpu): the tensor-core K1 against the FP32 K1, the symbol-wise K5 against the per-sample K5,
+and parity on the BASELINE.json configurations as stated (config 1's full 10 s capture, config 2's largest block
+sizes, a sample of config 3's 1024 stream recipes for 10 s each).  Tolerances as in tests/test_gpu_parity.py."""
+from concurrent.futures import ProcessPoolExecutor
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+import fm_radio_b200 as fm
+from fm_radio_b200 import Buf, synth
+from oracle import bind
+from tests import helpers as H
+from tests.test_gpu_parity import FEED_FORWARD, FEEDBACK, TAP_IDS, _assert_fb, _assert_ff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("bs", [1024, 4096, 65536])
+def test_k1_tensor_core_path_matches_fp32_path_and_checker(bs):
+    """k1_toeplitz_i8 (tcgen05 kind::i8, exact integer sums) and k1_fir4_discrim_u8 (FFMA2) are the same FIR +
+    discriminator: both within the feed-forward tolerance of the checker, within rounding noise of each other, and
+    a silent block gives exact zeros in both."""
+    iq = H.capture("seed0")
+    nblk = {1024: 96, 4096: 24, 65536: 4}[bs]
+    t = fm.FMDemod(bs, 1, keep_intermediates=True)
+    f = fm.FMDemod(bs, 1, keep_intermediates=True)
+    f.set_option("k1_fp32", 1)
+    chk = bind.CpuDemod(bs, "port")
+    for k in range(nblk):
+        blk = iq[2 * bs * k:2 * bs * (k + 1)]
+        chk.process_u8(blk); t.process_u8(blk); f.process_u8(blk)
+        ref_in, ref_d = chk.get("fm_in"), chk.get("fm_demod")
+        rms_in, rms_d = np.sqrt(np.mean(np.abs(ref_in) ** 2)), np.sqrt(np.mean(ref_d ** 2))
+        for g in (t, f):
+            assert np.abs(g.get(Buf.FM_IN) - ref_in).max() <= 1e-4 * rms_in, (k, g is t)
+            assert np.abs(g.get(Buf.FM_DEMOD) - ref_d).max() <= 1e-4 * max(rms_d, 1e-3), (k, g is t)
+        assert np.abs(t.get(Buf.FM_IN) - f.get(Buf.FM_IN)).max() <= 2e-5 * rms_in
+        assert np.abs(t.get(Buf.FM_DEMOD) - f.get(Buf.FM_DEMOD)).max() <= 2e-5 * max(rms_d, 1e-3)
+    z = np.full(2 * bs, 127, np.uint8)
+    for g in (t, f):
+        g.process_u8(z); g.process_u8(z)                   # the second block's history is silent too
+        assert np.all(g.get(Buf.FM_IN) == 0) and np.all(g.get(Buf.FM_DEMOD) == 0)
+    t.close(); f.close()
+
+
+def test_k1_tensor_core_path_new_stream_and_taps_upload():
+    """First block of a stream (zero FIR history = bytes 127) and re-designed fm_in taps (the G image is rebuilt)."""
+    iq = H.capture("stream7")
+    t = fm.FMDemod(H.B, 2, keep_intermediates=True)
+    chk = [bind.CpuDemod(H.B, "port") for _ in range(2)]
+    b = fm.create_fir_lpf(64, 0.2)
+    for k in range(3):
+        blk = np.stack([iq[2 * H.B * k:2 * H.B * (k + 1)], iq[2 * H.B * (k + 5):2 * H.B * (k + 6)]])
+        if k == 1:
+            t.upload_taps(fm.Filter.FM_IN, b)
+            for c in chk:
+                c.set_taps("fm_in", b, None)
+        t.process_u8(blk)
+        for s in range(2):
+            chk[s].process_u8(blk[s])
+            _assert_ff(t.get(Buf.FM_IN, s), chk[s].get("fm_in"), (k, s, "fm_in"))
+            _assert_ff(t.get(Buf.FM_DEMOD, s), chk[s].get("fm_demod"), (k, s, "fm_demod"))
+    t.close()
+
+
+def test_u8_block_after_cf32_block_is_refused():
+    g = fm.FMDemod(H.B, 1)
+    iq = H.capture("seed0")
+    g.process_u8(iq[:2 * H.B])
+    g.process_cf32((iq[2 * H.B:4 * H.B].astype(np.float32) - 127.0).view(np.complex64))       # cf32 after u8: fine
+    with pytest.raises(fm.FMGPUError):
+        g.process_u8(iq[4 * H.B:6 * H.B])
+    g.close()
+
+
+def test_k5_symbolwise_loop_equals_per_sample_loop_on_the_device():
+    """The symbol-wise BPSK synchroniser (production) and the per-sample loop (reference order) give identical bits:
+    symbols, counts and every display signal, through acquisition and lock."""
+    iq = H.capture("seed0")
+    a = fm.FMDemod(H.B, 3, keep_intermediates=True)
+    b = fm.FMDemod(H.B, 3, keep_intermediates=True)
+    b.set_option("k5_literal", 1)
+    bufs = (Buf.RDS_PRED_SYM, Buf.RDS_RAW_SYM, Buf.RDS, Buf.BPSK_PLL_SYM, Buf.BPSK_ZCD, Buf.BPSK_INT_DUMP_TRIGGER,
+            Buf.BPSK_TED_RAW_PHASE_ERROR, Buf.BPSK_TED_PI_PHASE_ERROR, Buf.BPSK_PLL_RAW_PHASE_ERROR,
+            Buf.BPSK_PLL_PI_PHASE_ERROR, Buf.BPSK_INT_DUMP_FILTER)
+    for k in range(60):
+        blk = np.stack([iq[2 * H.B * k:2 * H.B * (k + 1)], iq[2 * H.B * (k + 3):2 * H.B * (k + 4)], iq[2 * H.B * (k + 7):2 * H.B * (k + 8)]])
+        a.process_u8(blk); b.process_u8(blk)
+        for s in range(3):
+            for buf in bufs:
+                assert np.array_equal(a.get(buf, s), b.get(buf, s), equal_nan=True), (k, s, buf)
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("kind", H.cpu_checker_kinds())
+def test_config1_full_10s_capture(kind):
+    """BASELINE config 1 as stated: the whole 10 s capture (156 blocks of 65536) against the checker -- every group,
+    validity flag and block type, the packed bytes, PI / PS / RT, and the audio after lock."""
+    n_blocks = 156
+    iq = H.capture("seed0", n_blocks)
+    chk = bind.CpuDemod(H.B, kind)
+    g = fm.FMDemod(H.B, 1, keep_intermediates=True)
+    dec = fm.RDSDecoder()
+    worst_audio = 0.0
+    for k in range(n_blocks):
+        blk = iq[2 * H.B * k:2 * H.B * (k + 1)]
+        chk.process_u8(blk)
+        if k == 0:
+            H.copy_taps(chk, lambda name, b, a: g.upload_taps(TAP_IDS[name], b, a))
+        g.process_u8(blk)
+        dec.push_symbols(g.get(Buf.RDS_PRED_SYM))
+        _assert_ff(g.get(Buf.FM_DEMOD), chk.get("fm_demod"), (k, "fm_demod"))
+        if k >= H.LOCK_BLOCK:
+            _assert_fb(g.get(Buf.AUDIO_OUT), chk.get("audio_out"), (k, "audio_out"))
+            assert H.wrap_turn_diff(g.get(Buf.PLL_DT), chk.get("pll_dt")).max() <= 1e-4, k
+            worst_audio = max(worst_audio, float(np.abs(g.get(Buf.AUDIO_OUT) - chk.get("audio_out")).max()))
+    for a, b in zip(dec.groups(), chk.groups()):
+        assert np.array_equal(a, b)
+    assert dec.rds_bytes() == chk.rds_bytes()
+    assert dec.db() == chk.db()
+    assert len(dec.groups()[0]) >= 100                    # ~111 groups in 10 s
+    print(f"config 1 vs {kind}: {len(dec.groups()[0])} groups, worst audio_out error after lock {worst_audio:.2e}")
+    g.close()
+
+
+@pytest.mark.parametrize("bs", [262144, 1048576])
+def test_config2_largest_block_sizes_match_checker(bs):
+    """BASELINE config 2's largest block sizes for >= 2 s of signal: feed-forward stages every block, loops after
+    lock, RDS groups bit-exact with the checker run at the same block size."""
+    n_blocks = max(2, int(np.ceil(4.2 * 1_024_000 / bs)))          # >= 4.2 s: lock (3.07 s) + at least one block after it
+    iq = H.capture("seed0", (n_blocks * bs) // H.B)
+    chk = bind.CpuDemod(bs, "port")
+    g = fm.FMDemod(bs, 1, keep_intermediates=True)
+    dec = fm.RDSDecoder()
+    for k in range(n_blocks):
+        blk = iq[2 * bs * k:2 * bs * (k + 1)]
+        chk.process_u8(blk); g.process_u8(blk)
+        dec.push_symbols(g.get(Buf.RDS_PRED_SYM))
+        for name, buf in FEED_FORWARD:
+            _assert_ff(g.get(buf), chk.get(name), (k, name))
+        if k * bs >= H.LOCK_BLOCK * H.B:
+            for name, buf in FEEDBACK:
+                _assert_fb(g.get(buf), chk.get(name), (k, name))
+            assert H.wrap_turn_diff(g.get(Buf.PLL_DT), chk.get("pll_dt")).max() <= 1e-4, k
+    for a, b in zip(dec.groups(), chk.groups()):
+        assert np.array_equal(a, b)
+    assert dec.rds_bytes() == chk.rds_bytes()
+    assert len(dec.groups()[0]) >= 20
+    g.close()
+
+
+def test_config3_sample_of_the_1024_stream_recipes_for_10s():
+    """SURVEY.md 8(d) config 3's criterion -- "every stream's group list == the oracle's for that seed" -- on 64 of the
+    1024 stream recipes (every 16th: SNR 30-50 dB, carrier offset +-2 kHz, own PI / PS / RT), 10 s each, decoded ON
+    THE DEVICE (K6) in one batch.  The checker legs run in a process pool."""
+    import torch
+    ids = list(range(0, 1024, 16))
+    n_blocks = 156
+    ctx = mp.get_context("spawn")
+    with ProcessPoolExecutor(max_workers=min(len(ids), os.cpu_count() or 1), mp_context=ctx) as ex:
+        jobs = list(ex.map(H.oracle_stream_job, [(s, n_blocks, H.B, "port") for s in ids]))
+    S = len(ids)
+    g = fm.FMDemod(H.B, S, pipeline_depth=3)
+    g.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    got = [[np.zeros((0, 4), np.uint16), np.zeros((0, 4), np.uint8), np.zeros((0, 4), np.uint8)] for _ in range(S)]
+    got_bytes = [b"" for _ in range(S)]
+    keep = []
+    for k in range(n_blocks):
+        blk = torch.from_numpy(np.stack([j[0][2 * H.B * k:2 * H.B * (k + 1)] for j in jobs])).cuda()
+        keep.append(blk)
+        if len(keep) > 4:
+            g.sync(); keep = keep[-4:]
+        g.enqueue_u8_device(blk)
+        if (k + 1) % 12 == 0 or k == n_blocks - 1:
+            g.rds_fetch()
+            for i in range(S):
+                d, v, t = g.rds_groups(i, first=len(got[i][0]))
+                got[i] = [np.concatenate([a, b]) for a, b in zip(got[i], (d, v, t))]
+                got_bytes[i] += g.rds_bytes(i, first=len(got_bytes[i]))
+    n_groups = []
+    for i, s in enumerate(ids):
+        _cap, groups, rds_bytes, db = jobs[i]
+        for a, b in zip(got[i], groups):
+            assert np.array_equal(a, b), s
+        assert got_bytes[i] == rds_bytes, s
+        assert g.rds_db(i) == db, s
+        assert db["pi"] == 0x1000 + s
+        n_groups.append(len(groups[0]))
+    assert min(n_groups) >= 80, n_groups
+    print(f"config 3 sample: {S} streams x 10 s, groups per stream {min(n_groups)}..{max(n_groups)}, all equal to the checker's")
+    g.close()
