@@ -142,7 +142,7 @@ EXPORTED_SYMBOLS = [
     "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
     "fmgpu_chan_wait_external_stream", "fmgpu_chan_sync", "fmgpu_chan_stream", "fmgpu_chan_launch_count",
     "fmgpu_profile_stages7", "fmgpu_polyphase_us_create", "fmgpu_polyphase_us_process", "fmgpu_resample_linear",
-    "fmgpu_frames_to_s16", "fmgpu_calculate_fft", "fmgpu_get_fft", "fmgpu_set_option",
+    "fmgpu_frames_to_s16", "fmgpu_calculate_fft", "fmgpu_get_fft", "fmgpu_set_option", "fmgpu_set_fetch_mask",
 ]
 
 _lib = None
@@ -219,6 +219,7 @@ def lib():
     L.fmgpu_rds_get_db.restype = None
     L.fmgpu_get_partition.argtypes = [vp, C.POINTER(ci * 2)]
     L.fmgpu_set_option.argtypes = [vp, C.c_char_p, ci]
+    L.fmgpu_set_fetch_mask.argtypes = [vp, C.c_uint]
     L.fmgpu_rds_device_fetch.argtypes = [vp]
     L.fmgpu_rds_device_counts.argtypes = [vp, ci, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(ci * 2)]
     L.fmgpu_rds_device_get_groups.argtypes = [vp, ci, C.c_ulonglong, C.POINTER(RDSGroup), ci]
@@ -329,10 +330,13 @@ class FMDemod:
         self.blocks_enqueued += 1
         return slot
 
-    def enqueue_cf32_device(self, iq_dev, after_stream: int = 0) -> int:
-        """Queues one block of complex64 [n_streams, block_size] device input (the channelizer's output)."""
+    def enqueue_cf32_device(self, iq_dev, after_stream=None) -> int:
+        """Queues one block of complex64 [n_streams, block_size] device input (the channelizer's output).
+        after_stream: handle of the CUDA stream whose queued work produces iq_dev; None = nothing to wait for.
+        Handle 0 (the legacy default stream) is passed to the C-ABI as cudaStreamLegacy, because there NULL means "none"."""
         slot = self.blocks_enqueued % self.depth
-        _check(self.L.fmgpu_enqueue_cf32_device(self.h, _ptr(iq_dev), after_stream or None), "fmgpu_enqueue_cf32_device")
+        st = None if after_stream is None else (int(after_stream) or 1)
+        _check(self.L.fmgpu_enqueue_cf32_device(self.h, _ptr(iq_dev), st), "fmgpu_enqueue_cf32_device")
         self.blocks_enqueued += 1
         return slot
 
@@ -413,6 +417,12 @@ class FMDemod:
         if not self.pcm_rate:
             del out["k7_audio_pcm"]
         return out
+
+    FETCH_AUDIO_F32, FETCH_PCM_S16, FETCH_RDS_SYMBOLS, FETCH_ALL = 1, 2, 4, 7
+
+    def set_fetch_mask(self, mask: int) -> None:
+        """Which outputs fetch_outputs copies to the host (include/fmgpu.h FMGPU_FETCH_*); counts always travel."""
+        _check(self.L.fmgpu_set_fetch_mask(self.h, int(mask)), "fmgpu_set_fetch_mask")
 
     def set_option(self, name: str, value: int) -> None:
         """Implementation switches for A/B measurements: "k1_fp32", "k5_literal" (include/fmgpu.h)."""

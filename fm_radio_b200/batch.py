@@ -98,20 +98,28 @@ class WidebandReceiver:
                                                               device=device, mode=mode,
                                                               ring_depth=getattr(self.demod, "depth", 0))
 
-    def feed(self, iq_block, producer_stream: int = 0) -> int:
-        """One wideband block (device u8 tensor / pointer of 2 * block_in bytes), asynchronous."""
-        if producer_stream:
-            self.chan.wait_external_stream(producer_stream)
+    def feed(self, iq_block, producer_stream=None) -> int:
+        """One wideband block (device u8 tensor / pointer of 2 * block_in bytes), asynchronous.  producer_stream:
+        handle of the CUDA stream whose queued work produces iq_block -- 0 is a valid handle (the legacy default
+        stream); None means "no producer to wait for" (the block is already complete)."""
+        if producer_stream is not None:
+            self.chan.wait_external_stream(int(producer_stream))
         return self.chan.feed(self.demod, iq_block)
 
     def broadcast_and_feed(self, iq_block, src: int = 0, group=None) -> int:
-        """iq_block: torch.uint8 tensor of 2 * block_in bytes, valid on rank `src`, overwritten elsewhere."""
+        """iq_block: torch.uint8 tensor of 2 * block_in bytes, valid on rank `src`, overwritten elsewhere.  The
+        channelizer copies the block into its own staging buffer on its own stream; the caller's current stream is
+        made to wait for that copy, so the next broadcast into iq_block cannot overtake it."""
         import torch
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.broadcast(iq_block, src=src, group=group)
-        stream = torch.cuda.current_stream().cuda_stream if iq_block.is_cuda else 0
-        return self.feed(iq_block, stream)
+        if not iq_block.is_cuda:
+            return self.feed(iq_block, None)
+        cur = torch.cuda.current_stream()
+        rc = self.feed(iq_block, cur.cuda_stream)
+        cur.wait_stream(torch.cuda.ExternalStream(self.chan.stream))
+        return rc
 
     def results(self):
         """[(channel id, PI, PS, RT, n_groups)] of this rank's channels, decoded on the device (K6)."""

@@ -403,7 +403,7 @@ int chan_run(fmgpu_chan* h, int slot) {
 }
 
 void chan_free(fmgpu_chan* h) {
-    cudaDeviceSynchronize();
+    if (h->st) cudaStreamSynchronize(h->st);
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(h->d_stage); F(h->d_g); F(h->d_meta32); F(h->d_bimg); F(h->d_offs); F(h->d_meta);
     for (auto p : h->d_out) F(p);
@@ -553,6 +553,7 @@ int fmgpu_chan_sync(fmgpu_chan* h) {
 
 int fmgpu_chan_wait_external_stream(fmgpu_chan* h, void* cuda_stream) {
     if (!h) return fmgpu_set_last_error_(FMGPU_ERR_ARG, "chan_wait_external_stream: null handle");
+    CHK(cudaSetDevice(h->device));
     cudaEvent_t ev;
     CHK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CHK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));

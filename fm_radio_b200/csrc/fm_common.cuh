@@ -207,14 +207,15 @@ struct K1TParams {
     float discrim_gain;
     int n_rows;                // 128-byte rows per stream per block = block_size / 64
     int tiles_per_stream, n_tiles, n_streams;
-    int base_offset;           // descriptor base-offset field of the row-shifted chunk (0: swizzle by absolute address)
+    const float* theta_in;     // [S] the discriminator's prev_theta carried from the previous block (fm_demod.cpp:41-44)
+    float* theta_out;          // [S] ... for the next block (ping-pong with theta_in)
     float2* dbg_fm_in;         // keep_intermediates: [S][n_out] FIR outputs before the discriminator, else null
 };
 
-// K1 on the tensor cores (k1_toeplitz_i8.cu).  variant 0: tile staged twice, 1: one buffer + row-shifted descriptor
+// K1 on the tensor cores (k1_toeplitz_i8.cu)
 void k1t_build_tables(const float* taps, std::vector<int8_t>& bimg, std::vector<int>& ptab, int off[3], float w[3]);
 cudaError_t launch_k1t(const uint8_t* iq, const uint8_t* hist_in, uint8_t* hist_out, float2* hist_f32_out, float* fm_demod,
-                       const K1TParams& p, int variant, int n_ctas, cudaStream_t st);
+                       const K1TParams& p, int n_ctas, cudaStream_t st);
 
 // launchers (one per .cu file)
 cudaError_t launch_k1(bool u8, const void* iq, const float2* hist_in, float2* hist_out, float* fm_demod,

@@ -87,11 +87,13 @@ struct fmgpu_demod {
     float2* k1_hist[2] = { nullptr, nullptr };
     // K1 on the tensor cores (k1_toeplitz_i8.cu): byte history (ping-pong), G image, dp4a table, digit-plane constants
     uint8_t* k1t_hist[2] = { nullptr, nullptr };
+    float* k1t_theta[2] = { nullptr, nullptr };
     int8_t* k1t_bimg = nullptr; int* k1t_ptab = nullptr;
     float k1t_taps[64] = { 0 }; bool k1t_ready = false, use_k1t = true;
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
     bool k5_literal = false;
+    unsigned fetch_mask = FMGPU_FETCH_ALL, last_fetch_mask = 0;
     float* k2_hist_demod = nullptr; float* k2_hist_out = nullptr; float* k2_scal = nullptr;
     float* pll_state = nullptr;
     float* k4_hist_x[2] = { nullptr, nullptr };
@@ -287,6 +289,7 @@ int alloc_all(fmgpu_demod* h) {
     for (int i = 0; i < 2; i++) {
         CU(cudaMalloc((void**)&h->k1t_hist[i], S * 128));
         CU(cudaMemset(h->k1t_hist[i], 127, S * 128));       // a new stream: zero FIR history <-> bytes 127
+        CU(dalloc(&h->k1t_theta[i], S));
     }
     CU(cudaMalloc((void**)&h->k1t_bimg, 2 * 96 * 128));
     CU(cudaMalloc((void**)&h->k1t_ptab, 32 * 6 * sizeof(int)));
@@ -357,9 +360,13 @@ int alloc_all(fmgpu_demod* h) {
 }
 
 void free_all(fmgpu_demod* h) {
-    cudaDeviceSynchronize();
+    // only this handle's streams are drained: other handles and streams of the device keep running
+    {
+        cudaStream_t sts0[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
+        for (auto st : sts0) if (st) cudaStreamSynchronize(st);
+    }
     auto F = [](void* p) { if (p) cudaFree(p); };
-    for (int i = 0; i < 2; i++) { F(h->k1t_hist[i]); }
+    for (int i = 0; i < 2; i++) { F(h->k1t_hist[i]); F(h->k1t_theta[i]); }
     F(h->k1t_bimg); F(h->k1t_ptab);
     for (int i = 0; i < 2; i++) { F(h->k1_hist[i]); F(h->k4_hist_x[i]); F(h->k4_hist_m2[i]); F(h->k4_hist_m3[i]); }
     F(h->k2_hist_demod); F(h->k2_hist_out); F(h->k2_scal); F(h->pll_state); F(h->bpsk_state); F(h->lmr_phase); F(h->in_f32);
@@ -408,6 +415,7 @@ int prepare_pcm(fmgpu_demod* h) {
     }
     std::vector<fm::K7Entry> tab((size_t)M);
     fm::k7_build_table(h->n32, M, tab.data());
+    if (M > 0 && tab.back().j0 >= h->n32) return fail(FMGPU_ERR_ARG, "audio PCM rate: Resample()'s read position leaves the block (the reference would read out of bounds)");
     if (h->pcm_table) cudaFree(h->pcm_table);
     h->pcm_table = nullptr;
     CU(cudaMalloc((void**)&h->pcm_table, sizeof(fm::K7Entry) * (size_t)M));
@@ -470,9 +478,9 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
             for (int i = 0; i < 3; i++) { t.off[i] = h->k1t_off[i]; t.w[i] = h->k1t_w[i]; }
             t.discrim_gain = p.discrim_gain;
             t.n_rows = h->B / 64; t.tiles_per_stream = (t.n_rows + 127) / 128; t.n_tiles = t.tiles_per_stream * h->S; t.n_streams = h->S;
-            t.base_offset = 0; t.dbg_fm_in = p.dbg_fm_in;
+            t.theta_in = h->k1t_theta[parity]; t.theta_out = h->k1t_theta[parity ^ 1]; t.dbg_fm_in = p.dbg_fm_in;
             CU(fm::launch_k1t((const uint8_t*)iq_dev, h->k1t_hist[parity], h->k1t_hist[parity ^ 1], h->k1_hist[parity ^ 1], sl.fm_demod,
-                              t, 1, 2 * h->n_sm_fir, h->stA));
+                              t, 2 * h->n_sm_fir, h->stA));
         } else {
             CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
         }
@@ -612,16 +620,26 @@ int fetch_slot(fmgpu_demod* h, int slot) {
     Slot& sl = h->slots[slot];
     HostMirror& m = h->mirrors[slot];
     const size_t S = h->S;
+    const unsigned mask = h->fetch_mask;
     CU(cudaStreamWaitEvent(h->stO, sl.ev_D, 0));
-    CU(cudaMemcpyAsync(m.audio, sl.audio, S * h->n32 * sizeof(float2), cudaMemcpyDeviceToHost, h->stO));
-    CU(cudaMemcpyAsync(m.pred_sym, sl.pred_sym, S * h->n64 * sizeof(float), cudaMemcpyDeviceToHost, h->stO));
+    if (mask & FMGPU_FETCH_AUDIO_F32)
+        CU(cudaMemcpyAsync(m.audio, sl.audio, S * h->n32 * sizeof(float2), cudaMemcpyDeviceToHost, h->stO));
+    if (mask & FMGPU_FETCH_RDS_SYMBOLS) {
+        // only the part of each stream's row that can hold symbols: the timing clock runs at <= f_center + f_gain =
+        // 3500 Hz (ted_clock.cpp:31-44), i.e. at most n64 * 3500 / 16000 + 1 dumps per block (~152 at lock)
+        const size_t cap = std::min<size_t>((size_t)h->n64, (size_t)h->n64 * 7 / 32 + 2);
+        CU(cudaMemcpy2DAsync(m.pred_sym, (size_t)h->n64 * sizeof(float), sl.pred_sym, (size_t)h->n64 * sizeof(float),
+                             cap * sizeof(float), S, cudaMemcpyDeviceToHost, h->stO));
+    }
     CU(cudaMemcpyAsync(m.sym_count, sl.sym_count, S * sizeof(int), cudaMemcpyDeviceToHost, h->stO));
-    if (h->pcm_rate_built > 0 && h->ctl_pcm_rate == h->pcm_rate_built) {
+    const bool pcm_on = h->pcm_rate_built > 0 && h->ctl_pcm_rate == h->pcm_rate_built;
+    if (pcm_on && (mask & FMGPU_FETCH_PCM_S16)) {
         CU(cudaStreamWaitEvent(h->stO, sl.ev_P, 0));
         CU(cudaMemcpyAsync(m.pcm_s16, sl.pcm_s16, S * h->pcm_n * sizeof(short2), cudaMemcpyDeviceToHost, h->stO));
     }
     CU(cudaEventRecord(sl.ev_O, h->stO));
     h->last_fetched_slot = slot;
+    h->last_fetch_mask = mask;
     return FMGPU_OK;
 }
 
@@ -653,6 +671,7 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
     const int B = cfg->block_size;
     if (B < 1024 || (B & (B - 1)) != 0) return fail(FMGPU_ERR_ARG, "fmgpu_create: block_size must be a power of two >= 1024");
     if (cfg->n_streams < 1) return fail(FMGPU_ERR_ARG, "fmgpu_create: n_streams must be >= 1");
+    if (cfg->n_streams > 65535) return fail(FMGPU_ERR_ARG, "fmgpu_create: n_streams must be <= 65535 per handle (streams ride in gridDim.y)");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -785,7 +804,8 @@ int fmgpu_enqueue_u8_device(fmgpu_demod* h, const uint8_t* iq_dev) {
 }
 
 // cf32 input already on the device (the channelizer's output): K1's cf32 variant reads it in place.
-// after_stream (may be NULL): CUDA stream whose queued work produces iq_dev.
+// after_stream: CUDA stream whose queued work produces iq_dev; NULL = nothing to wait for (for the legacy
+// default stream pass cudaStreamLegacy, not 0).
 int fmgpu_enqueue_cf32_device(fmgpu_demod* h, const float* iq_dev, void* after_stream) {
     if (!h || !iq_dev) return fail(FMGPU_ERR_ARG, "enqueue: null argument");
     CU(cudaSetDevice(h->device));
@@ -864,8 +884,16 @@ int fmgpu_fetch_outputs(fmgpu_demod* h, int slot) {
     return fetch_slot(h, slot);
 }
 
+int fmgpu_set_fetch_mask(fmgpu_demod* h, unsigned mask) {
+    if (!h) return fail(FMGPU_ERR_ARG, "set_fetch_mask: null handle");
+    if (mask & ~(unsigned)FMGPU_FETCH_ALL) return fail(FMGPU_ERR_ARG, "set_fetch_mask: unknown bits");
+    h->fetch_mask = mask;
+    return FMGPU_OK;
+}
+
 int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
     if (!h) return fail(FMGPU_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
@@ -877,6 +905,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
 
 int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream) {
     if (!h) return fail(FMGPU_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
     cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
     for (auto st : sts) {
         cudaEvent_t ev;
@@ -936,11 +965,16 @@ int fmgpu_get_buffer(fmgpu_demod* h, int stream, fmgpu_buffer buf, const void** 
     HostMirror& m = h->mirrors[slot];
     const int count = m.sym_count[stream];
     switch (buf) {
-    case FMGPU_BUF_AUDIO_OUT: *host_ptr = m.audio + (size_t)stream * h->n32; *n_elems = h->n32; return FMGPU_OK;
-    case FMGPU_BUF_RDS_PRED_SYM: *host_ptr = m.pred_sym + (size_t)stream * h->n64; *n_elems = (size_t)count; return FMGPU_OK;
+    case FMGPU_BUF_AUDIO_OUT:
+        if (!(h->last_fetch_mask & FMGPU_FETCH_AUDIO_F32)) return fail(FMGPU_ERR_STATE, "get_buffer: the last fetch left the f32 audio on the device (fmgpu_set_fetch_mask)");
+        *host_ptr = m.audio + (size_t)stream * h->n32; *n_elems = h->n32; return FMGPU_OK;
+    case FMGPU_BUF_RDS_PRED_SYM:
+        if (!(h->last_fetch_mask & FMGPU_FETCH_RDS_SYMBOLS)) return fail(FMGPU_ERR_STATE, "get_buffer: the last fetch left the RDS symbols on the device (fmgpu_set_fetch_mask)");
+        *host_ptr = m.pred_sym + (size_t)stream * h->n64; *n_elems = (size_t)count; return FMGPU_OK;
     case FMGPU_BUF_RDS_SYM_COUNT: *host_ptr = m.sym_count + stream; *n_elems = 1; return FMGPU_OK;
     case FMGPU_BUF_AUDIO_PCM_S16:
         if (!m.pcm_s16 || h->pcm_rate_built <= 0) return fail(FMGPU_ERR_STATE, "get_buffer: the audio output stage is off (FMGPU_CTL_AUDIO_PCM_RATE_HZ)");
+        if (!(h->last_fetch_mask & FMGPU_FETCH_PCM_S16)) return fail(FMGPU_ERR_STATE, "get_buffer: the last fetch left the int16 PCM on the device (fmgpu_set_fetch_mask)");
         *host_ptr = m.pcm_s16 + (size_t)stream * h->pcm_n; *n_elems = (size_t)h->pcm_n; return FMGPU_OK;
     default: break;
     }

@@ -15,6 +15,7 @@
 // that reads the history is not the CTA that writes it); the discriminator's prev_theta is
 // recomputed from that history instead of being stored.
 #include "fm_common.cuh"
+#include <atomic>
 
 namespace fm {
 
@@ -303,11 +304,14 @@ constexpr int K1_SMEM_BYTES = (K1_THREADS + 1) * K1_SEG * (int)sizeof(float);
 cudaError_t launch_k1(bool u8, const void* iq, const float2* hist_in, float2* hist_out, float* fm_demod,
                       const K1Params& p, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: one flag per ordinal (a handle may live on any device of the process)
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(k1_fir4_discrim_cf32, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const dim3 grid((p.n_out + K1_TILE - 1) / K1_TILE, p.n_streams);
     if (u8) k1_fir4_discrim_u8<<<grid, K1_THREADS, 0, st>>>((const uint8_t*)iq, hist_in, hist_out, fm_demod, p);

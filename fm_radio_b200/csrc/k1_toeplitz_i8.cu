@@ -29,45 +29,44 @@
 // so the shifted view stays consistent).  The FIR history of a stream is its previous block's last row (128
 // bytes; a new stream starts from bytes 127 = the reference's zero history).
 //
-// One persistent CTA (128 threads = 128 TMEM lanes = 128 rows) walks tiles round-robin, software pipelined:
+// One persistent CTA (256 threads; 128 TMEM lanes = 128 rows, two warpgroups taking outputs 0..7 and 8..15 of
+// every row) walks tiles round-robin through a ring of four tile buffers, software pipelined:
 //   iteration i:  wait for tile i's bytes | thread 0 issues tile i's 8 MMAs into TMEM buffer i & 1
-//                 | cp.async of tile i + 1 | epilogue of tile i - 1 from TMEM buffer (i - 1) & 1
-// so loads, MMAs and the discriminator epilogue of three consecutive tiles overlap; two CTAs per SM.
-// Epilogue per thread = one row = 16 outputs: tcgen05.ld, integer offset + magic-number int->float (exact),
-// plane recombination, minimax atan2 (fm_common.cuh), wrapped first difference, 4 x STG.128.
-// The angle of the output before a thread's first comes from the neighbouring lane / warp; for the tile's first
-// row it is the last output of the previous row, which depends on buffer row 0 only: warp 1 computes its exact
-// integer sums with dp4a (same digits, same recombination => the same bits as the tile that owns that output).
+//                 | cp.async of tile i + 3 | epilogue of tile i - 1 from TMEM buffer (i - 1) & 1
+// so up to three tiles of loads (the kernel is HBM-latency bound with fewer: 0.078 ms with one tile ahead), the
+// MMAs and the discriminator epilogue of consecutive tiles overlap; two CTAs per SM.
+// Epilogue per thread = half a row = 8 outputs: tcgen05.ld, integer offset + magic-number int->float (exact),
+// plane recombination, minimax atan2 (fm_common.cuh), wrapped first difference, 2 x STG.128.
+// The angle of the output before a thread's first comes through shared memory (same row's other half / previous
+// row); for the tile's first row it is the last output of the previous row, which depends on buffer row 0 only:
+// warp 4 computes its exact integer sums with dp4a (same digits, same recombination => the same bits as the tile
+// that owns that output).  Across blocks the discriminator's prev_theta is carried as state, like the reference.
 #include "fm_common.cuh"
 #include "tcgen05.cuh"
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 namespace fm {
 
-constexpr int K1T_ROWS = 128;                        // A rows per tile = TMEM lanes = threads
+constexpr int K1T_ROWS = 128;                        // A rows per tile = TMEM lanes
+constexpr int K1T_THREADS = 256;                     // two warpgroups: outputs 0..7 and 8..15 of every row
 constexpr int K1T_NCOL = 32;                         // 16 outputs x (re, im)
 constexpr int K1T_PLANES = 3;
 constexpr int K1T_N = K1T_NCOL * K1T_PLANES;         // 96 accumulator columns
 constexpr int K1T_ABUF = 17 * 1024;                  // 129 rows x 128 B, padded to the 1024-byte swizzle atom
+constexpr int K1T_NS = 4;                            // tile ring: up to 3 tiles (50 KB) of cp.async in flight per CTA
 constexpr int K1T_BCHUNK = K1T_N * 128;              // 12 KB: one 128-byte K chunk of G
 constexpr int K1T_BBYTES = 2 * K1T_BCHUNK;
 constexpr int K1T_TMEM_COLS = 256;                   // 2 accumulator buffers of 128 columns (96 used)
 constexpr float K1T_MAGIC = 12582912.0f;             // 1.5 * 2^23: as_float(0x4B400000 + v) == MAGIC + v for |v| < 2^22
-constexpr int K1T_SMEM = K1T_BBYTES + 2 * K1T_ABUF + 1024;
-constexpr int K1T_SMEM_DUAL = K1T_SMEM + 2 * K1T_ROWS * 128;
-
+constexpr int K1T_SMEM = K1T_BBYTES + K1T_NS * K1T_ABUF + 1024;
 
 __device__ __forceinline__ int dp4a_u8s8(uint32_t a_u8x4, int b_s8x4, int c) {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
     return d;
-}
-
-__device__ __forceinline__ float k1t_wrap_phase(float x) {       // fm_demod.cpp:6-10, as two selects
-    const float lo = x - 2.0f * PI_F, hi = x + 2.0f * PI_F;
-    return (x >= PI_F) ? lo : ((x <= -PI_F) ? hi : x);
 }
 
 // exact plane sums (integers) -> sum_k b[k] (u - 127): the same instruction sequence everywhere it is used
@@ -80,27 +79,36 @@ __device__ __forceinline__ float2 k1t_combine(uint32_t r0, uint32_t i0, uint32_t
     return __ffma2_rn(f0, W[0], __ffma2_rn(f1, W[1], __fmul2_rn(f2, W[2])));
 }
 
-template <bool DUAL>
-__global__ void __launch_bounds__(K1T_ROWS, 2)
+// fm_demod.cpp:6-10 and :36-44 for two outputs: wrap(theta - prev) * gain, the wrap as two selects per half
+__device__ __forceinline__ float2 k1t_discrim2(float2 d, float gain) {
+    const float2 lo = __fadd2_rn(d, make_float2(-2.0f * PI_F, -2.0f * PI_F)), hi = __fadd2_rn(d, make_float2(2.0f * PI_F, 2.0f * PI_F));
+    float2 w;
+    w.x = (d.x >= PI_F) ? lo.x : ((d.x <= -PI_F) ? hi.x : d.x);
+    w.y = (d.y >= PI_F) ? lo.y : ((d.y <= -PI_F) ? hi.y : d.y);
+    return __fmul2_rn(w, make_float2(gain, gain));
+}
+
+__global__ void __launch_bounds__(K1T_THREADS, 2)
 k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_in, uint8_t* __restrict__ hist_out,
                float2* __restrict__ hist_f32_out, float* __restrict__ fm_demod, const __grid_constant__ K1TParams p)
 {
     extern __shared__ uint8_t k1t_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)k1t_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;
-    uint8_t* sA = sB + K1T_BBYTES;                   // [2][K1T_ABUF]
-    uint8_t* sA2 = sA + 2 * K1T_ABUF;                // DUAL only: [2][128 rows] = the tile's rows 1..128 staged a second time
+    uint8_t* sA = sB + K1T_BBYTES;                   // [K1T_NS][K1T_ABUF]
     __shared__ __align__(8) uint64_t bar_acc[2];     // the MMAs of the tile in TMEM buffer b have completed
     __shared__ uint32_t s_tmem;
-    __shared__ float s_theta[2][4];                  // last angle of each warp's rows
+    __shared__ float s_mid[2][K1T_ROWS];             // angle of output 7 of every row (warpgroup 0 -> 1)
+    __shared__ float s_last[2][K1T_ROWS];            // angle of output 15 of every row (warpgroup 1 -> 0, next row)
     __shared__ float s_thprev[2];                    // angle of the output before the tile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < K1T_BBYTES / 16; i += K1T_ROWS) ((uint4*)sB)[i] = __ldg((const uint4*)p.bimg + i);
+    const int row = tid & (K1T_ROWS - 1), half = tid >> 7;         // this thread's A row and which 8 of its 16 outputs
+    for (int i = tid; i < K1T_BBYTES / 16; i += K1T_THREADS) ((uint4*)sB)[i] = __ldg((const uint4*)p.bimg + i);
     if (tid == 0) { tc::mbar_init(&bar_acc[0], 1); tc::mbar_init(&bar_acc[1], 1); tc::mbar_init_fence(); }
     if (warp == 0) tc::tmem_alloc(&s_tmem, K1T_TMEM_COLS);
     int pw[6] = { 0, 0, 0, 0, 0, 0 };
-    if (warp == 1) {
+    if (warp == 4) {
 #pragma unroll
         for (int q = 0; q < 6; q++) pw[q] = p.ptab[lane * 6 + q];
     }
@@ -109,53 +117,59 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t sA_addr = tc::smem_u32(sA), sA2_addr = tc::smem_u32(sA2), sB_addr = tc::smem_u32(sB);
+    const uint32_t sA_addr = tc::smem_u32(sA), sB_addr = tc::smem_u32(sB);
     const size_t stream_bytes = (size_t)p.n_rows * 128;
     const uint32_t Kc[3] = { 0x4B400000u - (uint32_t)p.off[0], 0x4B400000u - (uint32_t)p.off[1], 0x4B400000u - (uint32_t)p.off[2] };
     const float2 Wc[3] = { make_float2(p.w[0], p.w[0]), make_float2(p.w[1], p.w[1]), make_float2(p.w[2], p.w[2]) };
     constexpr uint32_t IDESC = tc::idesc_i8_u8s8(K1T_ROWS, K1T_N);
 
-    // buffer row q of a tile <-> data row row0 - 1 + q of its stream (q = 0: the halo = previous row / history)
-    auto stage = [&](int tile, int buf) {
-        const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
-        const int n_valid = min(K1T_ROWS, p.n_rows - row0);
-        const uint8_t* src = iq + (size_t)s * stream_bytes + (ptrdiff_t)(row0 - 1) * 128;
-        const uint8_t* hsrc = hist_in + (size_t)s * 128;
-        uint8_t* dst = sA + buf * K1T_ABUF;
-        uint8_t* dst2 = sA2 + buf * (K1T_ROWS * 128);
-        for (int ci = tid; ci < (n_valid + 1) * 8; ci += K1T_ROWS) {
-            const int q = ci >> 3, c = ci & 7;
-            const uint8_t* g = (row0 == 0 && q == 0) ? hsrc + c * 16 : src + (size_t)ci * 16;
-            tc::cp_async16(dst + q * 128 + ((c ^ (q & 7)) << 4), g);
-            if (DUAL && q >= 1) tc::cp_async16(dst2 + (q - 1) * 128 + ((c ^ ((q - 1) & 7)) << 4), g);
+    // buffer row q of a tile <-> data row row0 - 1 + q of its stream (q = 0: the halo = previous row / history).
+    // Always commits a group (an empty one past the last tile), so the group count per iteration is uniform.
+    auto stage = [&](int tile, int slot) {
+        if (tile < p.n_tiles) {
+            const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
+            const int n_valid = min(K1T_ROWS, p.n_rows - row0);
+            const uint8_t* src = iq + (size_t)s * stream_bytes + (ptrdiff_t)(row0 - 1) * 128;
+            const uint8_t* hsrc = hist_in + (size_t)s * 128;
+            uint8_t* dst = sA + slot * K1T_ABUF;
+            for (int ci = tid; ci < (n_valid + 1) * 8; ci += K1T_THREADS) {
+                const int q = ci >> 3, c = ci & 7;
+                const uint8_t* g = (row0 == 0 && q == 0) ? hsrc + c * 16 : src + (size_t)ci * 16;
+                tc::cp_async16(dst + q * 128 + ((c ^ (q & 7)) << 4), g);
+            }
         }
         tc::cp_async_commit();
     };
 
-    // everything of a tile that reads its bytes from shared memory (before the buffer is recycled)
-    auto pre_epilogue = [&](int tile, int buf) {
+    // everything of a tile that reads its bytes from shared memory (before the ring slot is recycled)
+    auto pre_epilogue = [&](int tile, int slot, int buf) {
         const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
         const int n_valid = min(K1T_ROWS, p.n_rows - row0);
-        const uint8_t* A = sA + buf * K1T_ABUF;
-        if (warp == 1) {
-            // the output before the tile = output 15 of buffer row 0: all 64 taps on that row's 128 bytes
-            const uint32_t w4 = *(const uint32_t*)(A + 4 * lane);                // row 0: swizzle key 0
-            int a[6];
+        const uint8_t* A = sA + slot * K1T_ABUF;
+        if (warp == 4) {
+            if (row0 == 0) {
+                // a block's first output: the discriminator's carried prev_theta (fm_demod.cpp:41-44; 0 for a new stream)
+                if (lane == 0) s_thprev[buf] = p.theta_in[s];
+            } else {
+                // the output before the tile = output 15 of buffer row 0: all 64 taps on that row's 128 bytes
+                const uint32_t w4 = *(const uint32_t*)(A + 4 * lane);            // row 0: swizzle key 0
+                int a[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) a[q] = __reduce_add_sync(0xffffffffu, dp4a_u8s8(w4, pw[q], 0));
-            if (lane == 0) {
-                const float2 z = k1t_combine((uint32_t)a[0], (uint32_t)a[1], (uint32_t)a[2], (uint32_t)a[3], (uint32_t)a[4], (uint32_t)a[5], Kc, Wc);
-                s_thprev[buf] = fm_atan2f(z.y, z.x);
+                for (int q = 0; q < 6; q++) a[q] = __reduce_add_sync(0xffffffffu, dp4a_u8s8(w4, pw[q], 0));
+                if (lane == 0) {
+                    const float2 z = k1t_combine((uint32_t)a[0], (uint32_t)a[1], (uint32_t)a[2], (uint32_t)a[3], (uint32_t)a[4], (uint32_t)a[5], Kc, Wc);
+                    s_thprev[buf] = fm_atan2f(z.y, z.x);
+                }
             }
-        } else if (row0 + n_valid == p.n_rows) {
+        } else if (warp >= 5 && row0 + n_valid == p.n_rows) {
             // history for the next block: the stream's last row, as bytes (this kernel) and as floats (cf32 kernel)
-            const uint8_t* row = A + n_valid * 128;
+            const uint8_t* rowp = A + n_valid * 128;
             const int key = n_valid & 7;
-            if (warp == 0 && lane < 8)
-                *(uint4*)(hist_out + (size_t)s * 128 + lane * 16) = *(const uint4*)(row + ((lane ^ key) << 4));
-            if (warp >= 2) {
-                const int t0 = (warp - 2) * 32 + lane;                           // 64 samples
-                const uint8_t* b = row + (((t0 >> 3) ^ key) << 4) + (t0 & 7) * 2;
+            if (warp == 7 && lane < 8)
+                *(uint4*)(hist_out + (size_t)s * 128 + lane * 16) = *(const uint4*)(rowp + ((lane ^ key) << 4));
+            if (warp <= 6) {
+                const int t0 = (warp - 5) * 32 + lane;                           // 64 samples
+                const uint8_t* b = rowp + (((t0 >> 3) ^ key) << 4) + (t0 & 7) * 2;
                 hist_f32_out[(size_t)s * K1_HIST + t0] = make_float2((float)b[0] - 127.0f, (float)b[1] - 127.0f);
             }
         }
@@ -164,76 +178,69 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
     auto epilogue = [&](int tile, int buf, int par) {
         const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
         const int n_valid = min(K1T_ROWS, p.n_rows - row0);
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128);
-        float out[16];
-        float prev = 0.0f;
-        const size_t o_base = (size_t)s * p.n_rows * 16 + (size_t)(row0 + tid) * 16;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t a0[16], a1[16], a2[16];
-            tc::tmem_ld16(lane_addr + 0 * K1T_NCOL + 16 * h, a0);
-            tc::tmem_ld16(lane_addr + 1 * K1T_NCOL + 16 * h, a1);
-            tc::tmem_ld16(lane_addr + 2 * K1T_NCOL + 16 * h, a2);
-            tc::tmem_ld_wait();
-            float2 z[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) z[j] = k1t_combine(a0[2 * j], a0[2 * j + 1], a1[2 * j], a1[2 * j + 1], a2[2 * j], a2[2 * j + 1], Kc, Wc);
-            if (p.dbg_fm_in && tid < n_valid) {
-                float4* d4 = (float4*)(p.dbg_fm_in + o_base + 8 * h);
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) d4[j >> 1] = make_float4(z[j].x, z[j].y, z[j + 1].x, z[j + 1].y);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                const float2 th = fm_atan2f_x2(z[j].y, z[j].x, z[j + 1].y, z[j + 1].x);
-                out[8 * h + j] = (h == 0 && j == 0) ? th.x : th.x - prev;        // out[0] is fixed up below
-                out[8 * h + j + 1] = th.y - th.x;
-                prev = th.y;
-            }
-        }
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * 128 + 16 * half);
+        const size_t o_base = (size_t)s * p.n_rows * 16 + (size_t)(row0 + row) * 16 + 8 * half;
+        uint32_t a0[16], a1[16], a2[16];
+        tc::tmem_ld16(lane_addr + 0 * K1T_NCOL, a0);
+        tc::tmem_ld16(lane_addr + 1 * K1T_NCOL, a1);
+        tc::tmem_ld16(lane_addr + 2 * K1T_NCOL, a2);
+        tc::tmem_ld_wait();
         tc::fence_before();                                                      // this thread's TMEM reads are done
-        // angle of the output before this thread's first one: previous lane / previous warp / dp4a path
-        float th_before = __shfl_up_sync(0xffffffffu, prev, 1);
-        if (lane == 31) s_theta[par][warp] = prev;
+        float2 z[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) z[j] = k1t_combine(a0[2 * j], a0[2 * j + 1], a1[2 * j], a1[2 * j + 1], a2[2 * j], a2[2 * j + 1], Kc, Wc);
+        if (p.dbg_fm_in && row < n_valid) {
+            float4* d4 = (float4*)(p.dbg_fm_in + o_base);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) d4[j >> 1] = make_float4(z[j].x, z[j].y, z[j + 1].x, z[j + 1].y);
+        }
+        float2 th[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) th[j] = fm_atan2f_x2(z[2 * j].y, z[2 * j].x, z[2 * j + 1].y, z[2 * j + 1].x);
+        // the angle before this thread's first output: output 7 of the same row (other warpgroup) or output 15 of the
+        // previous row / of the row before the tile
+        if (half == 0) s_mid[par][row] = th[3].y; else s_last[par][row] = th[3].y;
         __syncthreads();
-        if (lane == 0) th_before = (warp == 0) ? s_thprev[buf] : s_theta[par][warp - 1];
-        if (tid >= n_valid) return;
-        out[0] -= th_before;
-#pragma unroll
-        for (int r = 0; r < 16; r++) out[r] = k1t_wrap_phase(out[r]) * p.discrim_gain;
+        const float th_before = half ? s_mid[par][row] : (row == 0 ? s_thprev[buf] : s_last[par][row - 1]);
+        if (row >= n_valid) return;
+        if (half == 1 && row0 + row == p.n_rows - 1) p.theta_out[s] = th[3].y;     // the block's last angle -> next block
+        const float2 d0 = k1t_discrim2(make_float2(th[0].x - th_before, th[0].y - th[0].x), p.discrim_gain);
+        const float2 d1 = k1t_discrim2(make_float2(th[1].x - th[0].y, th[1].y - th[1].x), p.discrim_gain);
+        const float2 d2 = k1t_discrim2(make_float2(th[2].x - th[1].y, th[2].y - th[2].x), p.discrim_gain);
+        const float2 d3 = k1t_discrim2(make_float2(th[3].x - th[2].y, th[3].y - th[3].x), p.discrim_gain);
         float4* dst = (float4*)(fm_demod + o_base);
-#pragma unroll
-        for (int q = 0; q < 4; q++) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        dst[0] = make_float4(d0.x, d0.y, d1.x, d1.y);
+        dst[1] = make_float4(d2.x, d2.y, d3.x, d3.y);
     };
 
     int it = 0, prev_tile = -1;
-    if ((int)blockIdx.x < p.n_tiles) stage(blockIdx.x, 0);
+#pragma unroll
+    for (int k = 0; k < K1T_NS - 1; k++) stage((int)blockIdx.x + k * (int)gridDim.x, k);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
-        const int buf = it & 1;
-        tc::cp_async_wait<0>();
+        const int buf = it & 1, slot = it % K1T_NS;
+        tc::cp_async_wait<K1T_NS - 2>();             // all but the newest NS - 2 groups have landed: tile `it` is in place
         tc::fence_async_smem();
-        __syncthreads();                             // tile's bytes are in place; everyone has left iteration it - 1
+        __syncthreads();                             // ... for every thread's copies; everyone has left iteration it - 1
         if (tid == 0) {
             tc::fence_after();
-            const uint32_t a_base = sA_addr + buf * K1T_ABUF, a2_base = sA2_addr + buf * (K1T_ROWS * 128);
+            const uint32_t a_base = sA_addr + slot * K1T_ABUF;
 #pragma unroll
             for (int kc = 0; kc < 2; kc++)
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
-                    const uint64_t a_desc = DUAL ? tc::smem_desc_sw128((kc ? a2_base : a_base) + ks * 32)
-                                                 : tc::smem_desc_sw128(a_base + kc * 128 + ks * 32, kc ? (uint32_t)p.base_offset : 0u);
+                    // K chunk 1 = the same buffer one row (128 B) later; the 128-byte swizzle follows the absolute address
+                    const uint64_t a_desc = tc::smem_desc_sw128(a_base + kc * 128 + ks * 32);
                     const uint64_t b_desc = tc::smem_desc_sw128(sB_addr + kc * K1T_BCHUNK + ks * 32);
                     tc::mma_i8(tmem + (uint32_t)(buf * 128), a_desc, b_desc, IDESC, (kc | ks) != 0 ? 1u : 0u);
                 }
             tc::commit(&bar_acc[buf]);
         }
-        pre_epilogue(tile, buf);
+        pre_epilogue(tile, slot, buf);
         if (it >= 1) {
             tc::mbar_wait(&bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));   // tile it - 1: accumulators complete, its bytes dead
             tc::fence_after();
         }
-        const int next = tile + gridDim.x;
-        if (next < p.n_tiles) stage(next, buf ^ 1);
+        stage(tile + (K1T_NS - 1) * (int)gridDim.x, (it + K1T_NS - 1) % K1T_NS);  // into the slot of tile it - 1
         if (it >= 1) epilogue(prev_tile, buf ^ 1, it & 1);
         prev_tile = tile;
     }
@@ -242,6 +249,7 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
         tc::fence_after();
         epilogue(prev_tile, (it - 1) & 1, it & 1);
     }
+    tc::cp_async_wait<0>();
     tc::fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, K1T_TMEM_COLS);
@@ -286,19 +294,18 @@ void k1t_build_tables(const float* taps, std::vector<int8_t>& bimg, std::vector<
 }
 
 cudaError_t launch_k1t(const uint8_t* iq, const uint8_t* hist_in, uint8_t* hist_out, float2* hist_f32_out, float* fm_demod,
-                       const K1TParams& p, int variant, int n_ctas, cudaStream_t st)
+                       const K1TParams& p, int n_ctas, cudaStream_t st)
 {
-    cudaError_t e;
     const int grid = std::max(1, std::min(p.n_tiles, n_ctas));
-    if (variant == 0) {
-        e = cudaFuncSetAttribute(k1_toeplitz_i8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM_DUAL);
+    static std::atomic<bool> configured[64];             // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(k1_toeplitz_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM);
         if (e != cudaSuccess) return e;
-        k1_toeplitz_i8<true><<<grid, K1T_ROWS, K1T_SMEM_DUAL, st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
-    } else {
-        e = cudaFuncSetAttribute(k1_toeplitz_i8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM);
-        if (e != cudaSuccess) return e;
-        k1_toeplitz_i8<false><<<grid, K1T_ROWS, K1T_SMEM, st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
+    k1_toeplitz_i8<<<grid, K1T_THREADS, K1T_SMEM, st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
     return cudaGetLastError();
 }
 

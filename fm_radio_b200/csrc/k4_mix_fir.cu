@@ -33,6 +33,7 @@
 // signals is carried (not recomputed) because the reference's FIR history holds samples mixed with
 // the previous block's phase offset.
 #include "fm_common.cuh"
+#include <atomic>
 
 namespace fm {
 
@@ -345,11 +346,14 @@ cudaError_t launch_k4(const float2* fm_out_iq, const float* pll_dt,
                       float* lmr_phase, float2* audio_out, float2* rds_out, float* est_partial,
                       float* rds_power_partial, float* dbg_lpr, float* dbg_lmr, const K4Params& p, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: one flag per ordinal (a handle may live on any device of the process)
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(k4_mix_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const dim3 grid(p.n_tiles, (p.n_streams + 1) / 2);
     k4_mix_fir<<<grid, K4_THREADS, K4_SMEM_BYTES, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,

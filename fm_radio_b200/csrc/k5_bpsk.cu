@@ -16,8 +16,9 @@
 // because in a warp some lane dumps a symbol at almost every sample).  This version walks SYMBOL by symbol
 // (k5_symbol_step): every lane advances to its own next dump, so the dump work (atan2 -> carrier error) is done
 // once per symbol for all 32 lanes together, the carrier loop + rotation of the symbol's samples runs as one batch
-// with instruction-level parallelism, and only the timing loop's ~12-op chain remains per sample.  Lanes therefore
-// sit at different samples of their rows; loads are per-lane 8-byte reads of lines prefetched into the L1.
+// with instruction-level parallelism, and the timing loop runs branch-free over the batch (state snapshotted at the
+// dump), so only its short filter recurrence remains per sample.  Lanes therefore sit at different samples of their
+// rows; loads are per-lane 8-byte reads issued one symbol ahead for the two batch lengths of a locked clock.
 // Bit-identical to the per-sample loop (k5_sample; checked on the host by tests/test_k5_core_cpu.py and on the
 // device by FMGPU_K5_LITERAL=1 in tests/test_gpu_parity.py).
 #include "fm_common.cuh"
@@ -106,12 +107,12 @@ k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_p
             }
     } else {
         int pos = valid ? 0 : n;
+        K5Window<K5_NB> win;
+        win.valid = false;
         while (__any_sync(0xffffffffu, pos < n)) {
-            // the line 2-3 symbols ahead of this lane -> L1 (the row was written by K4 and sits in the L2)
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(fetch.row + min(pos + 24, n - 1)));
             float sr = 0.0f, si = 0.0f;
-            const bool d = KEEP ? k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, live)
-                                : k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, none);
+            const bool d = KEEP ? k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, live, win)
+                                : k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, none, win);
             if (d) {
                 pred_sym[o + total] = si;
                 if (KEEP) dbgp.raw_sym[o + total] = make_float2(sr, si);

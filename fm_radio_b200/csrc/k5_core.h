@@ -175,19 +175,42 @@ K5_HD bool k5_sample(const K5Coef& c, K5Lane& L, int i, float x_re, float x_im, 
     return is_ted;
 }
 
+// The samples of a lane's next batch, loaded one call ahead (so their latency hides behind the current symbol).
+template <int NB>
+struct K5Window { float xr[NB], xi[NB]; bool valid; };
+
 // One symbol (at most NB samples) of one lane.  fetch(i) returns sample i of the lane's row for 0 <= i < n.
 // Advances pos; returns true when a symbol was dumped (sym_re, sym_im).  Inactive lanes (active = false) execute the
 // same instruction stream on clamped loads and change nothing.
+//   * win holds samples pos .. pos + NB - 1 when win.valid (else they are fetched here).  The NEXT call's window is
+//     loaded at the start of this one, for the two batch lengths of a locked clock (NB - 1 and NB samples per
+//     symbol): NB + 1 samples from pos + NB - 1.  Any other length (acquisition) leaves win.valid = false.
+//   * B is branch-free: the timing loop runs over all NB samples on a scratch copy of the state and the state is
+//     snapshotted at the sample of the dump (or the block's last sample); what follows the dump is discarded.
+//     Without per-sample branches the scheduler overlaps the samples' independent work, and the dependent chain
+//     per sample is the 3-op filter recurrence, plus ~10 ops once per symbol at the zero crossing.
 template <int NB, class Fetch, class Dbg>
 K5_HD bool k5_symbol_step(const K5Coef& c, K5Lane& L, const Fetch& fetch, int& pos, int n, bool active,
-                          float& sym_re, float& sym_im, const Dbg& dbg) {
+                          float& sym_re, float& sym_im, const Dbg& dbg, K5Window<NB>& win) {
     float xr[NB], xi[NB], iq_re[NB], iq_im[NB], t_lpy[NB], t_int[NB], t_mix[NB], t_pi[NB];
+    if (!win.valid) {
 #pragma unroll
-    for (int q = 0; q < NB; q++) {
-        const int i = (pos + q < n) ? pos + q : n - 1;
-        const K5Sample s = fetch(i);
-        xr[q] = s.x_re * L.gain; xi[q] = s.x_im * L.gain;
+        for (int q = 0; q < NB; q++) {
+            const int i = (pos + q < n) ? pos + q : n - 1;
+            const K5Sample s = fetch(i);
+            win.xr[q] = s.x_re; win.xi[q] = s.x_im;
+        }
     }
+    // the candidates for the next call's window
+    float yr[NB + 1], yi[NB + 1];
+#pragma unroll
+    for (int q = 0; q <= NB; q++) {
+        const int i = (pos + NB - 1 + q < n) ? pos + NB - 1 + q : n - 1;
+        const K5Sample s = fetch(i);
+        yr[q] = s.x_re; yi[q] = s.x_im;
+    }
+#pragma unroll
+    for (int q = 0; q < NB; q++) { xr[q] = win.xr[q] * L.gain; xi[q] = win.xi[q] * L.gain; }
     {   // A: the carrier loop free-runs on the current error
         float lp_x1 = L.lp_x1, lp_y1 = L.lp_y1, int_pll = L.int_pll, mix_t = L.mix_t;
 #pragma unroll
@@ -196,30 +219,42 @@ K5_HD bool k5_symbol_step(const K5Coef& c, K5Lane& L, const Fetch& fetch, int& p
             t_lpy[q] = lp_y1; t_int[q] = int_pll; t_mix[q] = mix_t;
         }
     }
-    // B: the timing loop until the dump
-    bool dumped = false;
+    // B: the timing loop on a scratch state T; S = the state at the dump / at the block's last sample
+    K5Lane T = L, S = L;
+    bool done = !active, dumped = false;
     int consumed = 0;
+    const int q_last = (n - 1 - pos < NB - 1) ? n - 1 - pos : NB - 1;
     const float pll_prev_used = L.pll_prev;
 #pragma unroll
     for (int q = 0; q < NB; q++) {
-        const bool act = active && !dumped && (pos + q < n);
-        if (act) {
-            bool is_zcd; float PI_ted;
-            const bool is_ted = k5_timing(c, L, iq_re[q], iq_im[q], is_zcd, PI_ted);
-            L.lp_x1 = pll_prev_used; L.lp_y1 = t_lpy[q]; L.int_pll = t_int[q]; L.mix_t = t_mix[q];
-            consumed = q + 1;
-            float raw_pll = pll_prev_used;
-            if (is_ted) {
-                sym_re = L.dump_re; sym_im = L.dump_im;
-                L.dump_re = 0.0f; L.dump_im = 0.0f;
-                dumped = true;
-                if (Dbg::kLive) raw_pll = k5_symbol_error(sym_re, sym_im);    // display only: the value is recomputed in C
-            }
-            dbg.sample(pos + q, xr[q], xi[q], iq_re[q], iq_im[q], is_zcd, is_ted, L.ted_prev, PI_ted, raw_pll, t_pi[q], L.dump_re, L.dump_im);
+        bool is_zcd; float PI_ted;
+        const bool is_ted = k5_timing(c, T, iq_re[q], iq_im[q], is_zcd, PI_ted);
+        const bool take = !done && (is_ted || q == q_last);
+        if (Dbg::kLive && !done) {
+            const float raw_pll = is_ted ? k5_symbol_error(T.dump_re, T.dump_im) : pll_prev_used;
+            dbg.sample(pos + q, xr[q], xi[q], iq_re[q], iq_im[q], is_zcd, is_ted, T.ted_prev, PI_ted, raw_pll, t_pi[q],
+                       is_ted ? 0.0f : T.dump_re, is_ted ? 0.0f : T.dump_im);
         }
+        if (take) {
+            S.zcd_xn = T.zcd_xn; S.cooldown = T.cooldown; S.ted_yn = T.ted_yn; S.ted_phase_error = T.ted_phase_error;
+            S.ted_prev = T.ted_prev; S.lt_x1 = T.lt_x1; S.lt_y1 = T.lt_y1; S.int_ted = T.int_ted;
+            S.dump_re = is_ted ? 0.0f : T.dump_re; S.dump_im = is_ted ? 0.0f : T.dump_im;
+            S.lp_x1 = pll_prev_used; S.lp_y1 = t_lpy[q]; S.int_pll = t_int[q]; S.mix_t = t_mix[q];
+            sym_re = T.dump_re; sym_im = T.dump_im;
+            consumed = q + 1; dumped = is_ted;
+        }
+        done = done || take;
     }
+    L = S;
     // C: once per symbol
     if (dumped) L.pll_prev = k5_symbol_error(sym_re, sym_im);
+    // the next window, if this batch had one of the two lengths it was loaded for
+    win.valid = (consumed == NB - 1) || (consumed == NB);
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+        win.xr[q] = (consumed == NB) ? yr[q + 1] : yr[q];
+        win.xi[q] = (consumed == NB) ? yi[q + 1] : yi[q];
+    }
     pos += consumed;
     return dumped;
 }

@@ -88,7 +88,18 @@ int fmgpu_enqueue_cf32_device(fmgpu_demod* h, const float* iq_dev, void* after_s
 int fmgpu_stream_wait_input_free(fmgpu_demod* h, void* cuda_stream);
 int fmgpu_sync(fmgpu_demod* h);
 /* Copies slot's audio + symbols to the pinned host mirrors (asynchronously on the output stream;
- * valid after fmgpu_sync). */
+ * valid after fmgpu_sync).  What travels is chosen by fmgpu_set_fetch_mask (default: everything):
+ * the observers of the reference receive the 32 kHz float frames and the soft symbols
+ * (OnAudioOut / OnRDSOut, broadcast_fm_demod.h:226-227); a bulk consumer that wants int16 PCM
+ * (fm_scraper.cpp:74-78) or decodes RDS on the device (K6) need not pay for the others.  Symbols travel
+ * compacted: only the part of each stream's row that can hold symbols (the timing clock runs at
+ * <= 3500 Hz, ted_clock.cpp:31-44).  The symbol counts always travel.  fmgpu_get_buffer refuses a
+ * buffer the last fetch left on the device (FMGPU_ERR_STATE). */
+#define FMGPU_FETCH_AUDIO_F32   1u   /* GetAudioOut(): 32 kHz float frames */
+#define FMGPU_FETCH_PCM_S16     2u   /* int16 PCM at FMGPU_CTL_AUDIO_PCM_RATE_HZ (when that stage is on) */
+#define FMGPU_FETCH_RDS_SYMBOLS 4u   /* GetRDSPredSymbols() */
+#define FMGPU_FETCH_ALL         7u
+int fmgpu_set_fetch_mask(fmgpu_demod* h, unsigned mask);
 int fmgpu_fetch_outputs(fmgpu_demod* h, int slot);
 /* Makes the handle's first kernel wait for work already queued on an external CUDA stream
  * (cudaStream_t passed as void*, e.g. torch's current stream that produced iq_dev). */

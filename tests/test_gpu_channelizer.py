@@ -111,7 +111,7 @@ def test_wideband_chain_matches_checker_chain(kind):
     worst = 0.0
     for k in range(nblk):
         blk_d = iq_d[2 * B * D * k:2 * B * D * (k + 1)]
-        slot = rx.feed(blk_d, 0 if k else __import__("torch").cuda.current_stream().cuda_stream)
+        slot = rx.feed(blk_d, None if k else __import__("torch").cuda.current_stream().cuda_stream)
         rx.demod.fetch_outputs(slot)
         rx.demod.sync()
         blk = blk_d.cpu().numpy()
@@ -147,7 +147,7 @@ def test_config4_hundred_stations_each_decode_their_own_pi():
     assert rx.chan.mode == ChanMode.TENSOR
     ext = torch.cuda.current_stream().cuda_stream
     for k in range(nblk):
-        rx.feed(iq_d[2 * B * D * k:2 * B * D * (k + 1)], ext if k == 0 else 0)
+        rx.feed(iq_d[2 * B * D * k:2 * B * D * (k + 1)], ext if k == 0 else None)
     res = rx.results()
     bad = [(cid, hex(pi)) for (cid, pi, psn, rt, n), p in zip(res, ps) if pi != p.pi_code or psn != p.ps.encode()]
     assert not bad, bad

@@ -20,8 +20,7 @@ static void design_lpf(float* b, int N, float k) {      // dsp/filter_designer.c
 }
 
 int main(int argc, char** argv) {
-    const int variant = argc > 1 ? atoi(argv[1]) : 1;
-    const int base_offset = argc > 2 ? atoi(argv[2]) : 0;
+    const int variant = 1, base_offset = 0; (void)argc; (void)argv;
     float taps[64];
     design_lpf(taps, 64, 0.25f * 0.95f);
     std::vector<int8_t> bimg; std::vector<int> ptab;
@@ -31,7 +30,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_bimg, bimg.size())); CK(cudaMalloc(&d_ptab, ptab.size() * 4));
     CK(cudaMemcpy(d_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ptab, ptab.data(), ptab.size() * 4, cudaMemcpyHostToDevice));
-    p.bimg = d_bimg; p.ptab = d_ptab; p.base_offset = base_offset;
+    p.bimg = d_bimg; p.ptab = d_ptab;
     p.discrim_gain = 1.0f / (75e3f * 2.0f * 3.14159265358979323846f / 256000.0f) * 0.5f;
     int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
     printf("variant %d base_offset %d: off %d %d %d, w %.6g %.6g %.6g\n", variant, base_offset, p.off[0], p.off[1], p.off[2], p.w[0], p.w[1], p.w[2]);
@@ -59,9 +58,13 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&d_iq, h.size())); CK(cudaMemcpy(d_iq, h.data(), h.size(), cudaMemcpyHostToDevice));
         for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_hist[i], S * 128)); CK(cudaMemset(d_hist[i], 127, S * 128)); }
         CK(cudaMalloc(&d_hf, S * 64 * sizeof(float2))); CK(cudaMalloc(&d_out, (size_t)NB * S * (B / 4) * 4));
+        float* d_th[2];
+        for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_th[i], S * 4)); CK(cudaMemset(d_th[i], 0, S * 4)); }
         p.n_rows = B / 64; p.tiles_per_stream = (p.n_rows + 127) / 128; p.n_tiles = p.tiles_per_stream * S; p.n_streams = S; p.dbg_fm_in = nullptr;
-        for (int b = 0; b < NB; b++)
-            CK(fm::launch_k1t(d_iq + (size_t)b * S * 2 * B, d_hist[b & 1], d_hist[(b & 1) ^ 1], d_hf, d_out + (size_t)b * S * (B / 4), p, variant, 2 * n_sm, 0));
+        for (int b = 0; b < NB; b++) {
+            p.theta_in = d_th[b & 1]; p.theta_out = d_th[(b & 1) ^ 1];
+            CK(fm::launch_k1t(d_iq + (size_t)b * S * 2 * B, d_hist[b & 1], d_hist[(b & 1) ^ 1], d_hf, d_out + (size_t)b * S * (B / 4), p, 2 * n_sm, 0));
+        }
         CK(cudaDeviceSynchronize());
         std::vector<float> out((size_t)NB * S * (B / 4));
         CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -105,7 +108,7 @@ int main(int argc, char** argv) {
             printf("B %6d stream %d: worst |err| %.3e, bad %ld, wrap-ambiguous %ld, hist mismatches %ld\n", B, s, worst, n_bad, n_wrapamb, hbad);
             bad_total += (int)(n_bad + hbad);
         }
-        cudaFree(d_iq); cudaFree(d_hist[0]); cudaFree(d_hist[1]); cudaFree(d_hf); cudaFree(d_out);
+        cudaFree(d_iq); cudaFree(d_hist[0]); cudaFree(d_hist[1]); cudaFree(d_hf); cudaFree(d_out); cudaFree(d_th[0]); cudaFree(d_th[1]);
     }
     printf("variant %d base_offset %d: %s\n", variant, base_offset, bad_total == 0 ? "PASS" : "FAIL");
     // ---------------- timing: 1024 streams x 65536 samples, DRAM-cold input (4 x 134 MB rotated) ----------------
@@ -121,13 +124,16 @@ int main(int argc, char** argv) {
         }
         for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_hist[i], S * 128)); CK(cudaMemset(d_hist[i], 127, S * 128)); }
         CK(cudaMalloc(&d_hf, S * 64 * sizeof(float2))); CK(cudaMalloc(&d_out, (size_t)NBUF * S * (B / 4) * 4));
+        float* d_th[2];
+        for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_th[i], S * 4)); CK(cudaMemset(d_th[i], 0, S * 4)); }
+        p.theta_in = d_th[0]; p.theta_out = d_th[1];
         p.n_rows = B / 64; p.tiles_per_stream = (p.n_rows + 127) / 128; p.n_tiles = p.tiles_per_stream * S; p.n_streams = S;
         for (int ctas : { n_sm, 2 * n_sm, 2 * 132 }) {
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-            for (int i = 0; i < 5; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, variant, ctas, 0));
+            for (int i = 0; i < 5; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, ctas, 0));
             const int reps = 40;
             cudaEventRecord(e0);
-            for (int i = 0; i < reps; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, variant, ctas, 0));
+            for (int i = 0; i < reps; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, ctas, 0));
             cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
             printf("timing variant %d, %d CTAs: %.4f ms/launch = %.1f GS/s, %.0f GB/s algorithmic (3 B/sample)\n", variant, ctas, ms,
