@@ -150,6 +150,7 @@ struct K3Params {
     int n;                      // B/8
     int n_streams;
     int keep;
+    int exact;                  // 1: the exact body only (9 / 7-op chain); 0: the fast pass with exact redo (k3_pll.cu)
 };
 
 struct K4Params {
@@ -184,7 +185,7 @@ struct K5Params {
 };
 
 // indices into the [field][stream] SoA state arrays of the per-stream recurrences
-enum PllState { PLL_LPF_X1 = 0, PLL_LPF_Y1, PLL_INT, PLL_T, PLL_E_PREV, PLL_AGC_GAIN, PLL_STATE_N };
+enum PllState { PLL_LPF_X1 = 0, PLL_LPF_Y1, PLL_INT, PLL_T, PLL_E_PREV, PLL_AGC_GAIN, PLL_TH_PREV, PLL_STATE_N };
 enum BpskState {
     BP_LPF_PLL_X1 = 0, BP_LPF_PLL_Y1, BP_INT_PLL, BP_MIX_T, BP_PLL_PREV_ERR,
     BP_ZCD_XN, BP_COOLDOWN, BP_TED_YN, BP_TED_PHASE_ERR, BP_TED_PREV_ERR,

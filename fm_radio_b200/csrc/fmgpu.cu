@@ -92,7 +92,7 @@ struct fmgpu_demod {
     float k1t_taps[64] = { 0 }; bool k1t_ready = false, use_k1t = true;
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
-    bool k5_literal = false;
+    bool k5_literal = false, k3_exact = false;
     unsigned fetch_mask = FMGPU_FETCH_ALL, last_fetch_mask = 0;
     float* k2_hist_demod = nullptr; float* k2_hist_out = nullptr; float* k2_scal = nullptr;
     float* pll_state = nullptr;
@@ -281,6 +281,7 @@ int alloc_all(fmgpu_demod* h) {
     }
     h->use_k1t = std::getenv("FMGPU_K1_FP32") == nullptr;
     h->k5_literal = std::getenv("FMGPU_K5_LITERAL") != nullptr;
+    h->k3_exact = std::getenv("FMGPU_K3_EXACT") != nullptr;
     {
         int n_sm = 148;
         CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
@@ -515,7 +516,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.int_KTs = 0.1f * Ts; p.Kp = 0.01f;
         p.f_center = -19000.0f; p.f_gain = -100.0f; p.mixer_KTs = Ts;
         p.agc_target = 1.0f; p.agc_beta = 0.2f;
-        p.n = h->n8; p.n_streams = h->S; p.keep = keep;
+        p.n = h->n8; p.n_streams = h->S; p.keep = keep; p.exact = h->k3_exact ? 1 : 0;
         if (prof) CU(cudaEventRecord(prof[3], h->stB));
         CU(fm::launch_k3(sl.theta, sl.power, h->pll_state, sl.pll_dt, h->dbg.pll_raw, h->dbg.pll_pi, p, h->stB));
         if (prof) CU(cudaEventRecord(prof[4], h->stB));
@@ -1097,6 +1098,7 @@ long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
 // Implementation switches for A/B measurements and cross-checks (the defaults are the production path):
 //   "k1_fp32"     1: the u8 FIR + discriminator on the FP32 FMA pipe (k1_fir4_discrim_u8) instead of the tensor cores
 //   "k5_literal"  1: the BPSK synchroniser's per-sample loop instead of the symbol-wise loop (identical bits)
+//   "k3_exact"    1: the pilot PLL's exact body only, without the fast pass (k3_pll.cu)
 int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
     if (!h || !name) return fail(FMGPU_ERR_ARG, "set_option: null argument");
     const std::string n = name;
@@ -1104,6 +1106,7 @@ int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
         if (h->step != 0 && h->use_k1t != (value == 0)) return fail(FMGPU_ERR_STATE, "set_option: k1_fp32 must be chosen before the first block");
         h->use_k1t = value == 0;
     } else if (n == "k5_literal") h->k5_literal = value != 0;
+    else if (n == "k3_exact") h->k3_exact = value != 0;
     else return fail(FMGPU_ERR_ARG, "set_option: unknown option");
     return FMGPU_OK;
 }

@@ -123,27 +123,37 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
     const float2 Wc[3] = { make_float2(p.w[0], p.w[0]), make_float2(p.w[1], p.w[1]), make_float2(p.w[2], p.w[2]) };
     constexpr uint32_t IDESC = tc::idesc_i8_u8s8(K1T_ROWS, K1T_N);
 
+    // Tiles are walked without divisions: (stream, first row) of tile t + gridDim.x follows from those of tile t.
+    struct TileRef { int tile, s, row0; };
+    const int g_div = (int)gridDim.x / p.tiles_per_stream, g_mod = (int)gridDim.x % p.tiles_per_stream;
+    auto tile_ref = [&](int tile) { TileRef r; r.tile = tile; r.s = tile / p.tiles_per_stream; r.row0 = (tile - r.s * p.tiles_per_stream) * K1T_ROWS; return r; };
+    auto advance = [&](TileRef& r) {
+        r.tile += (int)gridDim.x; r.s += g_div; r.row0 += g_mod * K1T_ROWS;
+        if (r.row0 >= p.tiles_per_stream * K1T_ROWS) { r.row0 -= p.tiles_per_stream * K1T_ROWS; r.s++; }
+    };
     // buffer row q of a tile <-> data row row0 - 1 + q of its stream (q = 0: the halo = previous row / history).
+    // Thread t copies the 16-byte chunks t, t + 256, ...: chunk (t & 7) of buffer rows (t >> 3) + 32 k, whose swizzle
+    // key (row & 7) does not depend on k, so source and destination both advance by 4096 bytes per copy.
     // Always commits a group (an empty one past the last tile), so the group count per iteration is uniform.
-    auto stage = [&](int tile, int slot) {
-        if (tile < p.n_tiles) {
-            const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
-            const int n_valid = min(K1T_ROWS, p.n_rows - row0);
-            const uint8_t* src = iq + (size_t)s * stream_bytes + (ptrdiff_t)(row0 - 1) * 128;
-            const uint8_t* hsrc = hist_in + (size_t)s * 128;
-            uint8_t* dst = sA + slot * K1T_ABUF;
-            for (int ci = tid; ci < (n_valid + 1) * 8; ci += K1T_THREADS) {
-                const int q = ci >> 3, c = ci & 7;
-                const uint8_t* g = (row0 == 0 && q == 0) ? hsrc + c * 16 : src + (size_t)ci * 16;
-                tc::cp_async16(dst + q * 128 + ((c ^ (q & 7)) << 4), g);
-            }
+    const int st_q0 = tid >> 3, st_c = tid & 7;
+    const uint32_t st_dst0 = (uint32_t)(st_q0 * 128 + ((st_c ^ (st_q0 & 7)) << 4));
+    auto stage = [&](const TileRef& r, int slot) {
+        if (r.tile < p.n_tiles) {
+            const int n_valid = min(K1T_ROWS, p.n_rows - r.row0);
+            const uint8_t* src = iq + (size_t)r.s * stream_bytes + (ptrdiff_t)(r.row0 - 1) * 128 + tid * 16;
+            uint8_t* dst = sA + slot * K1T_ABUF + st_dst0;
+            if (r.row0 == 0 && tid < 8) tc::cp_async16(dst, hist_in + (size_t)r.s * 128 + st_c * 16);
+            else if (st_q0 <= n_valid) tc::cp_async16(dst, src);
+#pragma unroll
+            for (int k = 1; k < 5; k++)
+                if (st_q0 + 32 * k <= n_valid) tc::cp_async16(dst + 4096 * k, src + 4096 * k);
         }
         tc::cp_async_commit();
     };
 
     // everything of a tile that reads its bytes from shared memory (before the ring slot is recycled)
-    auto pre_epilogue = [&](int tile, int slot, int buf) {
-        const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
+    auto pre_epilogue = [&](const TileRef& r, int slot, int buf) {
+        const int s = r.s, row0 = r.row0;
         const int n_valid = min(K1T_ROWS, p.n_rows - row0);
         const uint8_t* A = sA + slot * K1T_ABUF;
         if (warp == 4) {
@@ -175,8 +185,8 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
         }
     };
 
-    auto epilogue = [&](int tile, int buf, int par) {
-        const int s = tile / p.tiles_per_stream, row0 = (tile - s * p.tiles_per_stream) * K1T_ROWS;
+    auto epilogue = [&](const TileRef& r, int buf, int par) {
+        const int s = r.s, row0 = r.row0;
         const int n_valid = min(K1T_ROWS, p.n_rows - row0);
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * 128 + 16 * half);
         const size_t o_base = (size_t)s * p.n_rows * 16 + (size_t)(row0 + row) * 16 + 8 * half;
@@ -213,15 +223,17 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
         dst[1] = make_float4(d2.x, d2.y, d3.x, d3.y);
     };
 
-    int it = 0, prev_tile = -1;
+    TileRef cur = tile_ref((int)blockIdx.x), pre = cur, prev = cur;
 #pragma unroll
-    for (int k = 0; k < K1T_NS - 1; k++) stage((int)blockIdx.x + k * (int)gridDim.x, k);
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++) {
+    for (int k = 0; k < K1T_NS - 1; k++) { stage(pre, k); advance(pre); }
+    const bool mma_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;                // warp-uniform
+    int it = 0;
+    for (; cur.tile < p.n_tiles; it++) {
         const int buf = it & 1, slot = it % K1T_NS;
         tc::cp_async_wait<K1T_NS - 2>();             // all but the newest NS - 2 groups have landed: tile `it` is in place
         tc::fence_async_smem();
         __syncthreads();                             // ... for every thread's copies; everyone has left iteration it - 1
-        if (tid == 0) {
+        if (mma_warp && tc::elect_one()) {
             tc::fence_after();
             const uint32_t a_base = sA_addr + slot * K1T_ABUF;
 #pragma unroll
@@ -235,19 +247,21 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
                 }
             tc::commit(&bar_acc[buf]);
         }
-        pre_epilogue(tile, slot, buf);
+        pre_epilogue(cur, slot, buf);
         if (it >= 1) {
             tc::mbar_wait(&bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));   // tile it - 1: accumulators complete, its bytes dead
             tc::fence_after();
         }
-        stage(tile + (K1T_NS - 1) * (int)gridDim.x, (it + K1T_NS - 1) % K1T_NS);  // into the slot of tile it - 1
-        if (it >= 1) epilogue(prev_tile, buf ^ 1, it & 1);
-        prev_tile = tile;
+        stage(pre, (it + K1T_NS - 1) % K1T_NS);      // tile it + 3 into the slot of tile it - 1
+        advance(pre);
+        if (it >= 1) epilogue(prev, buf ^ 1, it & 1);
+        prev = cur;
+        advance(cur);
     }
     if (it >= 1) {
         tc::mbar_wait(&bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
         tc::fence_after();
-        epilogue(prev_tile, (it - 1) & 1, it & 1);
+        epilogue(prev, (it - 1) & 1, it & 1);
     }
     tc::cp_async_wait<0>();
     tc::fence_before();

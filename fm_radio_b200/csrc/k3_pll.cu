@@ -34,6 +34,18 @@
 //     (t + KTs*fc) + (KTs*fg)*c, saves one more op but was rejected: it moves the NCO's rounding
 //     points and the loop's static phase error with them -- 3.7e-5 turns away from the reference
 //     instead of 9e-7, measured.)
+//   fast pass   w -> fma -> fma -> w: the wraps leave the chain as well.  From the two NCO / detector updates above,
+//               w[n+1] = wrap(w[n] + (theta[n+1] - theta[n] + KTs*fc) + KTs*fg*c[n+1]); the middle term e[n+1] depends on
+//               the input only, and for a locked loop nothing wraps (|w| ~ 1e-3 turn), so inside a group of 32 samples
+//               w[n+1] = fma(c[n+1], KTs*fg, w[n] + e[n+1]),  c[n+1] = fma(w[n+1], Kp*b1 + ci, Kp*m + integ)
+//               (the control from the merged coefficient; the filter, integrator and NCO STATES keep their own exact
+//               recurrences beside the chain).  The chain per sample is 2 ops + the IIR's own 3-op recurrence instead
+//               of 7; the loop becomes issue-bound at ~20 instructions per sample.  The detector value of the group's
+//               LAST sample is re-anchored on the exact expression wrap(theta + t), so rounding cannot accumulate in w
+//               (inside a group it stays below 2e-7 turn), and a group in which |w| >= 1/4 turn, a clamp could have
+//               acted or a NaN appeared is redone from the saved state by the exact body.  Not bit-identical to the
+//               exact body: the control differs in its last bit (below the NCO's 2^-9 Hz frequency quantum) and w
+//               carries less rounding noise; pll_dt stays within 2e-6 turn of the reference (tolerance 1e-4).
 // The AGC gain is a positive scale and does not enter the angle; if it is not finite (all-zero
 // block: sqrt(1/0)) the reference's pilot becomes NaN and poisons the loop for good -- such a lane
 // takes the slow loop below, which keeps the reference's clamp-of-NaN behaviour.  Per-thread I/O is
@@ -59,7 +71,7 @@ __device__ __forceinline__ float wrap_turn(float x) {
 
 constexpr int K3_RING = 8;      // groups of theta in flight per warp (8 x 4 KB of shared memory)
 
-template <bool KEEP, int WRAP>
+template <bool KEEP, int WRAP, bool FAST>
 __global__ void __launch_bounds__(32)
 k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* __restrict__ state,
        float* __restrict__ pll_dt, float* __restrict__ dbg_raw, float* __restrict__ dbg_pi,
@@ -75,6 +87,7 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
     float t = state[PLL_T * S + s];
     float w = state[PLL_E_PREV * S + s];        // phase error in turns
     float gain = state[PLL_AGC_GAIN * S + s];
+    float th_last = state[PLL_TH_PREV * S + s];  // theta of the previous block's last sample (fast pass only)
 
     // dsp/agc.h:12-19 (block-wise): P = mean |x|^2, g += beta*(sqrt(target/P) - g)
     const float avg_power = power[s] / (float)p.n;
@@ -139,6 +152,45 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
             // (or a NaN met fma.sat); the group is then redone from the saved state by the exact body.  A locked
             // or locking loop never clamps: |PI| stays below 0.05.
             const float sx1 = x1, sy1 = y1, sinteg = integ, st = t, sw = w;
+            bool redo;
+            if (FAST) {
+                // fast pass (header): 2-op detector chain, exact state recurrences beside it
+                const float cw = fmaf(Kp, b1t, ci), kfg = mixer_KTs * f_gain, d_nom = mixer_KTs * f_center;
+                float wmax = 0.0f, thp = th_last, t_before_last = t, freq_last = f_center;
+#pragma unroll
+                for (int q = 0; q < G / 4; q++) {
+                    const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
+                    float dt[4], raw[4], pie[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        // w = the detector value of THIS sample's input (state on entry: the previous sample's)
+                        const float m = fmaf(x1, b0t, y1 * a0);
+                        const float g = fmaf(m, Kp, integ);
+                        const float control = fmaf(w, cw, g);
+                        const float lpf = fmaf(w, b1t, m);
+                        integ = fmaf(ci, w, integ);
+                        x1 = w; y1 = lpf;
+                        const float freq = fmaf(control, f_gain, f_center);
+                        t_before_last = t; freq_last = freq;
+                        t = wrap_turn<WRAP>(fmaf(mixer_KTs, freq, t));
+                        const float e = wrap_turn<WRAP>((th[j] - thp) + d_nom);
+                        thp = th[j];
+                        w = fmaf(control, kfg, w + e);
+                        wmax = fmaxf(wmax, fabsf(w));
+                        dt[j] = t;
+                        if (KEEP) { raw[j] = w * TWO_PI_F; pie[j] = control; }
+                    }
+                    dt4[(i >> 2) + q] = make_float4(dt[0], dt[1], dt[2], dt[3]);
+                    if (KEEP) {
+                        raw4[(i >> 2) + q] = make_float4(raw[0], raw[1], raw[2], raw[3]);
+                        pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
+                    }
+                }
+                // re-anchor the detector on the exact expression of the group's last sample
+                w = wrap_turn<WRAP>(fmaf(mixer_KTs, freq_last, thp + t_before_last));
+                redo = !(wmax < 0.25f) || !(fabsf(integ) <= p.integ_safe);
+                if (!redo) th_last = thp;
+            } else {
 #pragma unroll
             for (int q = 0; q < G / 4; q++) {
                 const float th[4] = { cur[q].x, cur[q].y, cur[q].z, cur[q].w };
@@ -163,11 +215,14 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
                     pi4[(i >> 2) + q] = make_float4(pie[0], pie[1], pie[2], pie[3]);
                 }
             }
+                redo = !(fabsf(integ) <= p.integ_safe);
+            }
             // |w| <= 1/2 turn bounds the low-pass output and the integrator's step, so ONE test of the integrator at
             // the end of the group proves that neither clamp could have acted anywhere inside it (integ_safe is
             // derived on the host from the loop's coefficients, launch_k3; NaN fails the test; <= 0 = always redo)
-            if (!(fabsf(integ) <= p.integ_safe)) {
+            if (redo) {
                 x1 = sx1; y1 = sy1; integ = sinteg; t = st; w = sw;
+                th_last = cur[G / 4 - 1].w;
 #pragma unroll 1
                 for (int q = 0; q < G / 4; q++) {
                     const float4 c4 = th4[(i >> 2) + q];
@@ -221,6 +276,7 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
             if (KEEP) { dbg_raw[(size_t)s * p.n + i] = e; dbg_pi[(size_t)s * p.n + i] = PI_error; }
         }
         x1 = nan; w = nan;
+        th_last = theta[(size_t)s * p.n + p.n - 1];
     }
     state[PLL_LPF_X1 * S + s] = x1;
     state[PLL_LPF_Y1 * S + s] = y1;
@@ -228,6 +284,7 @@ k3_pll(const float* __restrict__ theta, const float* __restrict__ power, float* 
     state[PLL_T * S + s] = t;
     state[PLL_E_PREV * S + s] = w;
     state[PLL_AGC_GAIN * S + s] = gain;
+    state[PLL_TH_PREV * S + s] = th_last;
 }
 
 cudaError_t launch_k3(const float* theta, const float* power, float* state, float* pll_dt,
@@ -246,8 +303,13 @@ cudaError_t launch_k3(const float* theta, const float* power, float* state, floa
         const double safe = 1.0 - std::fabs((double)p.Kp) * lpf_max - 32.0 * std::fabs((double)p.int_KTs) * pi - 1e-3;
         p.integ_safe = safe > 0.0 ? (float)safe : 0.0f;
     }
-    if (p.keep) k3_pll<true, 0><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
-    else        k3_pll<false, 0><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+    if (p.exact) {
+        if (p.keep) k3_pll<true, 0, false><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+        else        k3_pll<false, 0, false><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+    } else {
+        if (p.keep) k3_pll<true, 0, true><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+        else        k3_pll<false, 0, true><<<grid, 32, 0, st>>>(theta, power, state, pll_dt, dbg_raw, dbg_pi, p);
+    }
     return cudaGetLastError();
 }
 

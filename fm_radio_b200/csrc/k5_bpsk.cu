@@ -18,7 +18,9 @@
 // once per symbol for all 32 lanes together, the carrier loop + rotation of the symbol's samples runs as one batch
 // with instruction-level parallelism, and the timing loop runs branch-free over the batch (state snapshotted at the
 // dump), so only its short filter recurrence remains per sample.  Lanes therefore sit at different samples of their
-// rows; loads are per-lane 8-byte reads issued one symbol ahead for the two batch lengths of a locked clock.
+// rows, each streaming it through a private shared-memory ring filled by cp.async two batches ahead (with plain
+// loads at the head of the step, ncu showed 30 % of the kernel's time waiting for them: the address depends on
+// where the previous symbol ended).
 // Bit-identical to the per-sample loop (k5_sample; checked on the host by tests/test_k5_core_cpu.py and on the
 // device by FMGPU_K5_LITERAL=1 in tests/test_gpu_parity.py).
 #include "fm_common.cuh"
@@ -29,7 +31,33 @@ namespace fm {
 
 constexpr int K5_NB = 7;        // samples per batch: a locked clock dumps every 6 or 7 samples (16000 / 2375 = 6.74)
 
-struct K5Fetch {
+// Each lane streams ITS row through a private ring of 64 samples in shared memory (512 B per lane), filled by the
+// lane's own cp.async 8 samples (64 B) at a time, at least two batches ahead of use.  16-byte unit u of lane l sits
+// at unit u ^ l of the lane's region, which spreads the lanes' reads over the banks.  A lane reads only what it
+// copied itself (cp.async.wait_group orders that), so no warp-level synchronisation is involved.
+constexpr int K5_RING = 64;     // samples per lane
+
+struct K5RingFetch {
+    const float2* row;          // the lane's row in global memory
+    const char* ring;           // the lane's 512-byte region
+    int lane;
+    __device__ __forceinline__ K5Sample operator()(int i) const {
+        const int u = ((i >> 1) ^ lane) & (K5_RING / 2 - 1);
+        const float2 v = *(const float2*)(ring + (u << 4) + ((i & 1) << 3));
+        return K5Sample{ v.x, v.y };
+    }
+    // copy samples [first, first + 8) of the row into the ring (first is a multiple of 8)
+    __device__ __forceinline__ void issue(int first) const {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(ring);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int u = (((first >> 1) + k) ^ lane) & (K5_RING / 2 - 1);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(base + (unsigned)(u << 4)), "l"(row + first + 2 * k));
+        }
+    }
+};
+
+struct K5DirectFetch {          // the per-sample loop's plain loads
     const float2* row;
     __device__ __forceinline__ K5Sample operator()(int i) const { const float2 v = __ldg(row + i); return K5Sample{ v.x, v.y }; }
 };
@@ -89,7 +117,8 @@ k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_p
 
     const size_t o = (size_t)s * p.n;
     const int n = p.n;
-    const K5Fetch fetch{ rds_in + o };
+    __shared__ __align__(16) char s_ring[32 * K5_RING * 8];
+    const K5DirectFetch fetch{ rds_in + o };
     int total = 0;
     K5LiveDebug live{ dbgp, o };
     K5NoDebug none;
@@ -106,19 +135,30 @@ k5_bpsk(const float2* __restrict__ rds_in, const float* __restrict__ rds_power_p
                 }
             }
     } else {
-        int pos = valid ? 0 : n;
-        K5Window<K5_NB> win;
-        win.valid = false;
+        // Symbol by symbol.  Ring invariant: after a step's issue, filled >= pos + 16 (pos advances by at most K5_NB = 7
+        // per step and one 8-sample chunk is issued per step while filled < pos + 23), so the samples of a step
+        // (< pos + 7) were issued by the PREVIOUS step's group at the latest: wait_group 1 after this step's commit.
+        const K5RingFetch rf{ rds_in + o, s_ring + threadIdx.x * (K5_RING * 8), (int)threadIdx.x };
+        int pos = valid ? 0 : n, filled = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (filled < n) { rf.issue(filled); filled += 8; }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         while (__any_sync(0xffffffffu, pos < n)) {
+            if (filled < n && filled < pos + K5_NB + 16) { rf.issue(filled); filled += 8; }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
             float sr = 0.0f, si = 0.0f;
-            const bool d = KEEP ? k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, live, win)
-                                : k5_symbol_step<K5_NB>(c, L, fetch, pos, n, pos < n, sr, si, none, win);
+            const bool d = KEEP ? k5_symbol_step<K5_NB>(c, L, rf, pos, n, pos < n, sr, si, live)
+                                : k5_symbol_step<K5_NB>(c, L, rf, pos, n, pos < n, sr, si, none);
             if (d) {
                 pred_sym[o + total] = si;
                 if (KEEP) dbgp.raw_sym[o + total] = make_float2(sr, si);
                 total++;
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     if (!valid) return;
     sym_count[s] = total;

@@ -175,42 +175,24 @@ K5_HD bool k5_sample(const K5Coef& c, K5Lane& L, int i, float x_re, float x_im, 
     return is_ted;
 }
 
-// The samples of a lane's next batch, loaded one call ahead (so their latency hides behind the current symbol).
-template <int NB>
-struct K5Window { float xr[NB], xi[NB]; bool valid; };
-
-// One symbol (at most NB samples) of one lane.  fetch(i) returns sample i of the lane's row for 0 <= i < n.
-// Advances pos; returns true when a symbol was dumped (sym_re, sym_im).  Inactive lanes (active = false) execute the
-// same instruction stream on clamped loads and change nothing.
-//   * win holds samples pos .. pos + NB - 1 when win.valid (else they are fetched here).  The NEXT call's window is
-//     loaded at the start of this one, for the two batch lengths of a locked clock (NB - 1 and NB samples per
-//     symbol): NB + 1 samples from pos + NB - 1.  Any other length (acquisition) leaves win.valid = false.
+// One symbol (at most NB samples) of one lane.  fetch(i) returns sample i of the lane's row for 0 <= i < n (the
+// kernel serves it from a per-lane shared-memory ring filled two batches ahead).  Advances pos; returns true when a
+// symbol was dumped (sym_re, sym_im).  Inactive lanes (active = false) execute the same instruction stream on
+// clamped loads and change nothing.
 //   * B is branch-free: the timing loop runs over all NB samples on a scratch copy of the state and the state is
 //     snapshotted at the sample of the dump (or the block's last sample); what follows the dump is discarded.
 //     Without per-sample branches the scheduler overlaps the samples' independent work, and the dependent chain
 //     per sample is the 3-op filter recurrence, plus ~10 ops once per symbol at the zero crossing.
 template <int NB, class Fetch, class Dbg>
 K5_HD bool k5_symbol_step(const K5Coef& c, K5Lane& L, const Fetch& fetch, int& pos, int n, bool active,
-                          float& sym_re, float& sym_im, const Dbg& dbg, K5Window<NB>& win) {
+                          float& sym_re, float& sym_im, const Dbg& dbg) {
     float xr[NB], xi[NB], iq_re[NB], iq_im[NB], t_lpy[NB], t_int[NB], t_mix[NB], t_pi[NB];
-    if (!win.valid) {
 #pragma unroll
-        for (int q = 0; q < NB; q++) {
-            const int i = (pos + q < n) ? pos + q : n - 1;
-            const K5Sample s = fetch(i);
-            win.xr[q] = s.x_re; win.xi[q] = s.x_im;
-        }
-    }
-    // the candidates for the next call's window
-    float yr[NB + 1], yi[NB + 1];
-#pragma unroll
-    for (int q = 0; q <= NB; q++) {
-        const int i = (pos + NB - 1 + q < n) ? pos + NB - 1 + q : n - 1;
+    for (int q = 0; q < NB; q++) {
+        const int i = (pos + q < n) ? pos + q : n - 1;
         const K5Sample s = fetch(i);
-        yr[q] = s.x_re; yi[q] = s.x_im;
+        xr[q] = s.x_re * L.gain; xi[q] = s.x_im * L.gain;
     }
-#pragma unroll
-    for (int q = 0; q < NB; q++) { xr[q] = win.xr[q] * L.gain; xi[q] = win.xi[q] * L.gain; }
     {   // A: the carrier loop free-runs on the current error
         float lp_x1 = L.lp_x1, lp_y1 = L.lp_y1, int_pll = L.int_pll, mix_t = L.mix_t;
 #pragma unroll
@@ -248,13 +230,6 @@ K5_HD bool k5_symbol_step(const K5Coef& c, K5Lane& L, const Fetch& fetch, int& p
     L = S;
     // C: once per symbol
     if (dumped) L.pll_prev = k5_symbol_error(sym_re, sym_im);
-    // the next window, if this batch had one of the two lengths it was loaded for
-    win.valid = (consumed == NB - 1) || (consumed == NB);
-#pragma unroll
-    for (int q = 0; q < NB; q++) {
-        win.xr[q] = (consumed == NB) ? yr[q + 1] : yr[q];
-        win.xi[q] = (consumed == NB) ? yi[q + 1] : yi[q];
-    }
     pos += consumed;
     return dumped;
 }

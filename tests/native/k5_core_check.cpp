@@ -25,11 +25,9 @@ static int run_step(const K5Coef& c, K5Lane& L, const float* x, int n, float* sy
     int pos = 0, total = 0;
     Fetch f{ x };
     K5NoDebug dbg;
-    K5Window<NB> win;
-    win.valid = false;
     while (pos < n) {
         float sr = 0, si = 0;
-        if (k5_symbol_step<NB>(c, L, f, pos, n, true, sr, si, dbg, win)) { sym[2 * total] = sr; sym[2 * total + 1] = si; total++; }
+        if (k5_symbol_step<NB>(c, L, f, pos, n, true, sr, si, dbg)) { sym[2 * total] = sr; sym[2 * total + 1] = si; total++; }
     }
     return total;
 }

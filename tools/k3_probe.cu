@@ -5,15 +5,15 @@
 #include <vector>
 #include <cmath>
 
-template <int WRAP>
+template <int WRAP, bool FAST = false>
 static float run(int S, int n, const float* theta, const float* power, float* state, float* dt, const fm::K3Params& p, int reps, int nb = 1) {
     // nb > 1: rotate over nb copies of theta / pll_dt (nb x 33.5 MB each) so every launch reads DRAM-cold input,
     // as in the chain where K2's 167 MB of traffic has pushed part of theta out of the L2
     const size_t stride = (size_t)S * n;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; i++) fm::k3_pll<false, WRAP><<<(S + 31) / 32, 32>>>(theta, power, state, dt, nullptr, nullptr, p);
+    for (int i = 0; i < 3; i++) fm::k3_pll<false, WRAP, FAST><<<(S + 31) / 32, 32>>>(theta, power, state, dt, nullptr, nullptr, p);
     cudaEventRecord(e0);
-    for (int i = 0; i < reps; i++) fm::k3_pll<false, WRAP><<<(S + 31) / 32, 32>>>(theta + (i % nb) * stride, power, state, dt + (i % nb) * stride, nullptr, nullptr, p);
+    for (int i = 0; i < reps; i++) fm::k3_pll<false, WRAP, FAST><<<(S + 31) / 32, 32>>>(theta + (i % nb) * stride, power, state, dt + (i % nb) * stride, nullptr, nullptr, p);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     return ms / reps;
@@ -44,6 +44,10 @@ int main() {
     const float ms0 = run<0>(S, n, d_th, d_pw, d_st, d_dt, p, 20);
     const float ms1 = run<1>(S, n, d_th, d_pw, d_st, d_dt, p, 20);
     const float ms2 = run<0>(S, n, d_th, d_pw, d_st, d_dt, p, 24, NB);
+    p.integ_safe = 0.9f;
+    const float ms3 = run<0, true>(S, n, d_th, d_pw, d_st, d_dt, p, 40);
+    const float ms4 = run<0, true>(S, n, d_th, d_pw, d_st, d_dt, p, 48, NB);
+    printf("k3 FAST pass (locked pilot): %.4f ms/launch = %.1f cycles/sample; DRAM-cold input %.4f ms = %.1f cycles/sample\n", ms3, ms3 * 1e-3 * clk * 1e3 / n, ms4, ms4 * 1e-3 * clk * 1e3 / n);
     printf("k3 WRAP=0, DRAM-cold input (8 x 33.5 MB rotated): %.4f ms/launch = %.1f cycles/sample\n", ms2, ms2 * 1e-3 * clk * 1e3 / n);
     printf("k3 WRAP=0 (magic adds): %.4f ms/launch = %.1f cycles/sample @%d kHz\n", ms0, ms0 * 1e-3 * clk * 1e3 / n, clk);
     printf("k3 WRAP=1 (FRND)      : %.4f ms/launch = %.1f cycles/sample\n", ms1, ms1 * 1e-3 * clk * 1e3 / n);
