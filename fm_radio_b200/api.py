@@ -143,6 +143,8 @@ EXPORTED_SYMBOLS = [
     "fmgpu_chan_wait_external_stream", "fmgpu_chan_sync", "fmgpu_chan_stream", "fmgpu_chan_launch_count",
     "fmgpu_profile_stages7", "fmgpu_polyphase_us_create", "fmgpu_polyphase_us_process", "fmgpu_resample_linear",
     "fmgpu_frames_to_s16", "fmgpu_calculate_fft", "fmgpu_get_fft", "fmgpu_set_option", "fmgpu_set_fetch_mask",
+    "fmgpu_create_iir_peak_2_filter", "fmgpu_window_hamming", "fmgpu_window_hann", "fmgpu_window_blackman",
+    "fmgpu_window_blackman_harris", "fmgpu_create_fir_lpf_window", "fmgpu_create_fir_hpf_window", "fmgpu_create_fir_bpf_window",
 ]
 
 _lib = None
@@ -194,6 +196,8 @@ def lib():
     L.fmgpu_create_iir_notch_filter.restype = None
     L.fmgpu_create_iir_peak_1_filter.argtypes = [vp, vp, C.c_float, C.c_float]
     L.fmgpu_create_iir_peak_1_filter.restype = None
+    L.fmgpu_create_iir_peak_2_filter.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float]
+    L.fmgpu_create_iir_peak_2_filter.restype = None
     L.fmgpu_polyphase_ds_create.argtypes = [ci, ci, ci, C.POINTER(vp)]
     L.fmgpu_polyphase_destroy.argtypes = [vp]
     L.fmgpu_polyphase_destroy.restype = None
@@ -697,3 +701,25 @@ def create_fir_hilbert(N: int): return _designer("fmgpu_create_fir_hilbert", N, 
 def create_iir_single_pole_lpf(k: float): return _designer("fmgpu_create_iir_single_pole_lpf", 2, 2, k)
 def create_iir_notch_filter(k: float, r: float): return _designer("fmgpu_create_iir_notch_filter", 3, 3, k, r)
 def create_iir_peak_1_filter(k: float, r: float): return _designer("fmgpu_create_iir_peak_1_filter", 3, 3, k, r)
+def create_iir_peak_2_filter(k: float, r: float, A_db: float): return _designer("fmgpu_create_iir_peak_2_filter", 3, 3, k, r, A_db)
+
+
+TOTAL_TAPS_IIR_SINGLE_POLE_LPF, TOTAL_TAPS_IIR_SECOND_ORDER_NOTCH_FILTER, TOTAL_TAPS_IIR_SECOND_ORDER_PEAK_FILTER = 2, 3, 3
+WINDOWS = ("hamming", "hann", "blackman", "blackman_harris")
+
+
+def _windowed(name: str, window: str, N: int, *ks):
+    """create_fir_{lpf,hpf,bpf}(b, N, k..., window) of dsp/filter_designer.h:9-11 with one of dsp/window_functions.h."""
+    L = lib()
+    fn = getattr(L, f"fmgpu_create_fir_{name}_window")
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * len(ks) + [C.c_void_p]
+    w = C.cast(getattr(L, f"fmgpu_window_{window}"), C.c_void_p)
+    b = np.zeros(N, np.float32)
+    fn(b.ctypes.data, N, *[float(k) for k in ks], w)
+    return b
+
+
+def create_fir_lpf_window(N: int, k: float, window: str = "hamming"): return _windowed("lpf", window, N, k)
+def create_fir_hpf_window(N: int, k: float, window: str = "hamming"): return _windowed("hpf", window, N, k)
+def create_fir_bpf_window(N: int, k1: float, k2: float, window: str = "hamming"): return _windowed("bpf", window, N, k1, k2)

@@ -250,6 +250,24 @@ void fmgpu_create_fir_hilbert(float* b, int N);
 void fmgpu_create_iir_single_pole_lpf(float* b, float* a, float k);
 void fmgpu_create_iir_notch_filter(float* b, float* a, float k, float r);
 void fmgpu_create_iir_peak_1_filter(float* b, float* a, float k, float r);
+/* Method 2 (zero and pole placement, A_db = attenuation outside the peak): dsp/filter_designer.h:27,
+ * filter_designer.cpp:312-367.  (The reference's normalisation memoises the first call's parameters in a
+ * `static` lambda, :347; this one uses every call's own.) */
+void fmgpu_create_iir_peak_2_filter(float* b, float* a, float k, float r, float A_db);
+/* The designers' window argument (dsp/filter_designer.h:3,9-11: `const window_func_t window = window_hamming`) and
+ * the windows of dsp/window_functions.h:11-38; window = NULL selects Hamming like the reference's default. */
+typedef float (*fmgpu_window_func_t)(float);
+float fmgpu_window_hamming(float x);
+float fmgpu_window_hann(float x);
+float fmgpu_window_blackman(float x);
+float fmgpu_window_blackman_harris(float x);
+void fmgpu_create_fir_lpf_window(float* b, int N, float k, fmgpu_window_func_t window);
+void fmgpu_create_fir_hpf_window(float* b, int N, float k, fmgpu_window_func_t window);
+void fmgpu_create_fir_bpf_window(float* b, int N, float k1, float k2, fmgpu_window_func_t window);
+/* dsp/filter_designer.h:34-36 */
+#define FMGPU_TOTAL_TAPS_IIR_SINGLE_POLE_LPF 2
+#define FMGPU_TOTAL_TAPS_IIR_SECOND_ORDER_NOTCH_FILTER 3
+#define FMGPU_TOTAL_TAPS_IIR_SECOND_ORDER_PEAK_FILTER 3
 
 /* ---- stand-alone resamplers: src/dsp/polyphase_filter.h (PolyphaseDownsampler<T>::process,
  * :41-64) on the GPU.  Host pointers; state (the last M*K inputs) lives in the object. ---------- */

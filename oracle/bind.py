@@ -84,6 +84,8 @@ def lib(kind: str = "ref"):
         L.create_iir_single_pole_lpf.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.create_iir_notch_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
         L.create_iir_peak_1_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+        L.create_iir_peak_2_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float]
+        L.create_fir_lpf_window.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.polyphase_ds_f32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.polyphase_ds_cf32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.polyphase_us_f32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]

@@ -114,6 +114,42 @@ void fmo_create_iir_peak_1_filter(float* b, float* a, float k, float r) {      /
     b[2] = K*0.0f; b[1] = K*0.0f; b[0] = K*1.0f;   /* _b[0]=0,_b[1]=0,_b[2]=1 -> b[2],b[1],b[0] */
     a[2] = 1.0f; a[1] = r*a0; a[0] = -r2;
 }
+/* filter_designer.cpp:312-367 (method 2: zero and pole placement), normalised with the call's own parameters */
+void fmo_create_iir_peak_2_filter(float* b, float* a, float k, float r, float A_db) {
+    const float A = powf(10.0f, A_db/20.0f);
+    const float rc = 1.0f-r;
+    const float rc_scale = rc*2.0f;
+    const float r0 = 1.0f - rc_scale;
+    const float r1 = 1.0f - rc_scale/A;
+    const float wn = PI_F*k;
+    const float a0 = 2.0f*cosf(wn);
+    const c32 z  = { cosf(PI_F*k), sinf(PI_F*k) };
+    const c32 z0 = z;
+    const c32 z1 = { cosf(-PI_F*k), sinf(-PI_F*k) };
+    const c32 n0 = { z.re-r0*z0.re, z.im-r0*z0.im }, n1 = { z.re-r0*z1.re, z.im-r0*z1.im };
+    const c32 d0 = { z.re-r1*z0.re, z.im-r1*z0.im }, d1 = { z.re-r1*z1.re, z.im-r1*z1.im };
+    const c32 num = c32_mul(n0, n1), den = c32_mul(d0, d1);
+    const float K = 1.0f/(cabs2f(num.re, num.im)/cabs2f(den.re, den.im));
+    b[2] = K*1.0f; b[1] = K*(-r0*a0); b[0] = K*(r0*r0);
+    a[2] = 1.0f; a[1] = r1*a0; a[0] = -r1*r1;
+}
+/* dsp/window_functions.h:11-38, window id: 0 hamming, 1 hann, 2 blackman, 3 blackman-harris */
+static float window_by_id(int id, float x) {
+    switch (id) {
+    case 1: { const float s = sinf(x/2.0f); return s*s; }
+    case 2: return 0.42659f - 0.49656f*cosf(x) + 0.076849f*cosf(2.0f*x);
+    case 3: return 0.35875f - 0.48829f*cosf(x) + 0.14128f*cosf(2.0f*x) - 0.01168f*cosf(3.0f*x);
+    default: return 0.53836f - 0.46164f*cosf(x);
+    }
+}
+void fmo_create_fir_lpf_window(float* b, int N, float k, int window_id) {      /* :84-107 with the window argument */
+    const float M = (float)(N-1);
+    for (int i = 0; i < N; i++) {
+        const float t0 = 2.0f*PI_F*(float)i/M;
+        const float t1 = (float)i - M/2.0f;
+        b[(N-1)-i] = window_by_id(window_id, t0) * (k*sincf(k*t1));
+    }
+}
 void fmo_create_fir_hilbert(float* b, int N) {                                 /* :369-383 */
     const int M = (N-1)/2;
     for (int i = 0; i < N; i++) {

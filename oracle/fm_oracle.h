@@ -54,6 +54,8 @@ void fmo_create_fir_hilbert(float* b, int N);
 void fmo_create_iir_single_pole_lpf(float* b, float* a, float k);
 void fmo_create_iir_notch_filter(float* b, float* a, float k, float r);
 void fmo_create_iir_peak_1_filter(float* b, float* a, float k, float r);
+void fmo_create_iir_peak_2_filter(float* b, float* a, float k, float r, float A_db);
+void fmo_create_fir_lpf_window(float* b, int N, float k, int window_id);   /* 0 hamming, 1 hann, 2 blackman, 3 blackman-harris */
 
 void fmo_polyphase_ds_f32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls);
 void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls);

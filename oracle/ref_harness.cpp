@@ -256,6 +256,11 @@ void fmref_create_fir_hilbert(float* b, int N) { create_fir_hilbert(b, N); }
 void fmref_create_iir_single_pole_lpf(float* b, float* a, float k) { create_iir_single_pole_lpf(b, a, k); }
 void fmref_create_iir_notch_filter(float* b, float* a, float k, float r) { create_iir_notch_filter(b, a, k, r); }
 void fmref_create_iir_peak_1_filter(float* b, float* a, float k, float r) { create_iir_peak_1_filter(b, a, k, r); }
+void fmref_create_iir_peak_2_filter(float* b, float* a, float k, float r, float A_db) { create_iir_peak_2_filter(b, a, k, r, A_db); }
+void fmref_create_fir_lpf_window(float* b, int N, float k, int window_id) {
+    const window_func_t w[4] = { window_hamming, window_hann, window_blackman, window_blackman_harris };
+    create_fir_lpf(b, N, k, w[window_id & 3]);
+}
 
 // dsp/polyphase_filter.h:9-87 stand-alone, for pinning the generic resampler kernels.
 void fmref_polyphase_ds_f32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls) {

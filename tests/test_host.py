@@ -64,6 +64,20 @@ def test_host_designers_match_checker(kind):
         Lc.create_iir_single_pole_lpf(rb.ctypes.data, ra.ctypes.data, k)
         b, a = fm.create_iir_single_pole_lpf(k)
         assert np.allclose(b, rb, rtol=2e-6) and np.allclose(a, ra, rtol=2e-6)
+    for wid, wname in enumerate(fm.WINDOWS):               # the designers' window argument (filter_designer.h:9-11)
+        for N, k in ((64, 0.2375), (128, 0.03125), (65, 0.6)):
+            ref = np.zeros(N, np.float32)
+            Lc.create_fir_lpf_window(ref.ctypes.data, N, k, wid)
+            assert np.abs(fm.create_fir_lpf_window(N, k, wname) - ref).max() < 2e-7, wname
+    assert np.array_equal(fm.create_fir_lpf_window(64, 0.3), fm.create_fir_lpf(64, 0.3))
+    # method-2 peak filter: ONE parameter set per process on the reference side (its normalisation memoises the first
+    # call's parameters in a static lambda, filter_designer.cpp:347)
+    rb, ra = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    Lc.create_iir_peak_2_filter(rb.ctypes.data, ra.ctypes.data, 0.296875, 0.999, 20.0)
+    b, a = fm.create_iir_peak_2_filter(0.296875, 0.999, 20.0)
+    assert np.allclose(b, rb, rtol=1e-3) and np.allclose(a, ra, rtol=2e-6)
+    assert (fm.api.TOTAL_TAPS_IIR_SINGLE_POLE_LPF, fm.api.TOTAL_TAPS_IIR_SECOND_ORDER_NOTCH_FILTER,
+            fm.api.TOTAL_TAPS_IIR_SECOND_ORDER_PEAK_FILTER) == (2, 3, 3)
     if kind == "port":      # the reference's peak/notch designers memoise their first (k, r), see test_oracle.py
         for k, r in ((0.296875, 0.9999), (0.1, 0.99)):
             rb, ra = np.zeros(3, np.float32), np.zeros(3, np.float32)
