@@ -413,7 +413,7 @@ def run_wideband_arm(args):
     cent = synth.wideband_centres(n_st)
     ps = [synth.StreamParams.for_stream(2000 + s) for s in range(n_st)]
     n_in = B * D
-    n_cap = 24                                               # 1.5 s of continuous signal, cycled
+    n_cap = 32                                               # 2.1 s of continuous signal, cycled
     if rank == 0:
         cap = synth.synth_wideband_u8(n_in * n_cap, cent, ps, device=dev)
         blocks = [cap[2 * n_in * k:2 * n_in * (k + 1)] for k in range(n_cap)]
@@ -485,7 +485,19 @@ def run_wideband_arm(args):
         tt = torch.tensor([t_dev, t_e2e, chan_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, chan_ms = float(tt[0]), float(tt[1]), float(tt[2])
-    res = gather_results(rx.results())
+    # correctness inside the bench: a FRESH receiver takes the n_cap continuous blocks once (the timed receiver has seen
+    # the capture wrap around, i.e. phase jumps every 2.1 s) and every station must decode its own PI on the device
+    rx.demod.sync()
+    chk = WidebandReceiver(synth.FS_WIDEBAND, cent, rank, world, B, D, 192, mode=ChanMode.AUTO, device=local_rank)
+    with torch.cuda.stream(side):
+        for k in range(n_cap):
+            if rank == 0:
+                stage.copy_(blocks[k], non_blocking=True)
+            chk.broadcast_and_feed(stage)
+        chk.demod.sync()
+        torch.cuda.synchronize()
+    res = gather_results(chk.results())
+    chk.close()
     own_pi = sum(1 for (c, pi, _ps, _rt, _n) in res if pi == ps[c].pi_code)
     my_st = len(rx.channel_ids)
     value = n_st * B * args.steps / t_dev / 1e6              # station-rate IQ samples demodulated per second, whole job

@@ -165,6 +165,8 @@ struct K4Params {
     int parity;
     int n_streams;
     int keep;
+    int v1;                     // 1: the one-tile-per-CTA kernel (k4_mix_fir); 0: the persistent producer / consumer kernel
+    int n_sm;                   // SMs of the partition the kernel runs on (grid of the persistent kernel)
 };
 
 struct K5Params {

@@ -92,7 +92,7 @@ struct fmgpu_demod {
     float k1t_taps[64] = { 0 }; bool k1t_ready = false, use_k1t = true;
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
-    bool k5_literal = false, k3_exact = false;
+    bool k5_literal = false, k3_exact = false, k4_v1 = false;
     unsigned fetch_mask = FMGPU_FETCH_ALL, last_fetch_mask = 0;
     float* k2_hist_demod = nullptr; float* k2_hist_out = nullptr; float* k2_scal = nullptr;
     float* pll_state = nullptr;
@@ -282,6 +282,7 @@ int alloc_all(fmgpu_demod* h) {
     h->use_k1t = std::getenv("FMGPU_K1_FP32") == nullptr;
     h->k5_literal = std::getenv("FMGPU_K5_LITERAL") != nullptr;
     h->k3_exact = std::getenv("FMGPU_K3_EXACT") != nullptr;
+    h->k4_v1 = std::getenv("FMGPU_K4_V1") != nullptr;
     {
         int n_sm = 148;
         CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
@@ -537,6 +538,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.harmonic_lmr = 38000.0f / 19000.0f; p.harmonic_rds = 57000.0f / 19000.0f;
         p.stereo_mix = h->ctl_stereo_mix; p.audio_out_mode = h->ctl_audio_out;
         p.n = h->n8; p.n_tiles = h->k4_tiles; p.parity = parity; p.n_streams = h->S; p.keep = keep;
+        p.v1 = h->k4_v1 ? 1 : 0; p.n_sm = h->n_sm_fir;
         if (keep) CU(cudaMemcpyAsync(h->dbg.lmr_phase_used, h->lmr_phase, (size_t)h->S * sizeof(float), cudaMemcpyDeviceToDevice, h->stC));
         if (prof) CU(cudaEventRecord(prof[5], h->stC));
         CU(fm::launch_k4(sl.fm_out_iq, sl.pll_dt, h->k4_hist_x[parity], h->k4_hist_m2[parity], h->k4_hist_m3[parity],
@@ -1099,6 +1101,7 @@ long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
 //   "k1_fp32"     1: the u8 FIR + discriminator on the FP32 FMA pipe (k1_fir4_discrim_u8) instead of the tensor cores
 //   "k5_literal"  1: the BPSK synchroniser's per-sample loop instead of the symbol-wise loop (identical bits)
 //   "k3_exact"    1: the pilot PLL's exact body only, without the fast pass (k3_pll.cu)
+//   "k4_v1"       1: the one-tile-per-CTA mixdown + FIR kernel instead of the persistent producer / consumer one (same bits)
 int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
     if (!h || !name) return fail(FMGPU_ERR_ARG, "set_option: null argument");
     const std::string n = name;
@@ -1107,6 +1110,7 @@ int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
         h->use_k1t = value == 0;
     } else if (n == "k5_literal") h->k5_literal = value != 0;
     else if (n == "k3_exact") h->k3_exact = value != 0;
+    else if (n == "k4_v1") h->k4_v1 = value != 0;
     else return fail(FMGPU_ERR_ARG, "set_option: unknown option");
     return FMGPU_OK;
 }
