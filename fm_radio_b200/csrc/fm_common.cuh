@@ -165,8 +165,7 @@ struct K4Params {
     int parity;
     int n_streams;
     int keep;
-    int v1;                     // 1: the one-tile-per-CTA kernel (k4_mix_fir); 0: the persistent producer / consumer kernel
-    int n_sm;                   // SMs of the partition the kernel runs on (grid of the persistent kernel)
+    int balanced;               // 1: FIR roles split 6 / 6 / 2 outputs per lane over the four warps; 0: the first version's 8 / 8 / 4+4 / sparse
 };
 
 struct K5Params {

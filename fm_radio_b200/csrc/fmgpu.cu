@@ -538,7 +538,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.harmonic_lmr = 38000.0f / 19000.0f; p.harmonic_rds = 57000.0f / 19000.0f;
         p.stereo_mix = h->ctl_stereo_mix; p.audio_out_mode = h->ctl_audio_out;
         p.n = h->n8; p.n_tiles = h->k4_tiles; p.parity = parity; p.n_streams = h->S; p.keep = keep;
-        p.v1 = h->k4_v1 ? 1 : 0; p.n_sm = h->n_sm_fir;
+        p.balanced = h->k4_v1 ? 0 : 1;
         if (keep) CU(cudaMemcpyAsync(h->dbg.lmr_phase_used, h->lmr_phase, (size_t)h->S * sizeof(float), cudaMemcpyDeviceToDevice, h->stC));
         if (prof) CU(cudaEventRecord(prof[5], h->stC));
         CU(fm::launch_k4(sl.fm_out_iq, sl.pll_dt, h->k4_hist_x[parity], h->k4_hist_m2[parity], h->k4_hist_m3[parity],
@@ -1101,7 +1101,7 @@ long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
 //   "k1_fp32"     1: the u8 FIR + discriminator on the FP32 FMA pipe (k1_fir4_discrim_u8) instead of the tensor cores
 //   "k5_literal"  1: the BPSK synchroniser's per-sample loop instead of the symbol-wise loop (identical bits)
 //   "k3_exact"    1: the pilot PLL's exact body only, without the fast pass (k3_pll.cu)
-//   "k4_v1"       1: the one-tile-per-CTA mixdown + FIR kernel instead of the persistent producer / consumer one (same bits)
+//   "k4_v1"       1: the mixdown + FIR kernel's first FIR-role split (one warp nearly idle) instead of the balanced one (same bits)
 int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
     if (!h || !name) return fail(FMGPU_ERR_ARG, "set_option: null argument");
     const std::string n = name;

@@ -45,7 +45,7 @@ constexpr int K4_SPARSE_MAX = 32;                             // >= ceil(256 / 1
 constexpr int K4_SMEM_BYTES = (5 * K4_PLEN + 3 * K4_NN) * (int)sizeof(float2);
 // epilogue arrays, aliased onto the sample planes once every FIR has finished
 constexpr int K4_RES_LPR = 0, K4_RES_LMR = K4_TS / 4, K4_RES_SPARSE = 2 * (K4_TS / 4), K4_RES_EST = K4_RES_SPARSE + K4_SPARSE_MAX,
-              K4_RES_END = K4_RES_EST + K4_THREADS;
+              K4_RES_RRE = K4_RES_EST + K4_THREADS, K4_RES_RIM = K4_RES_RRE + K4_TS / 8, K4_RES_END = K4_RES_RIM + K4_TS / 8;
 static_assert(K4_RES_END <= 5 * K4_PLEN, "epilogue arrays must fit in the planes");
 
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
@@ -113,6 +113,7 @@ __device__ __forceinline__ void fir128(const float2* __restrict__ sig, const flo
     }
 }
 
+template <bool BAL>
 __global__ void __launch_bounds__(K4_THREADS, 4)
 k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_dt,
            const float* __restrict__ hist_x_in, const float2* __restrict__ hist_m2_in, const float2* __restrict__ hist_m3_in,
@@ -210,44 +211,47 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         }
     }
 
-    // ---- the FIR roles; results stay in registers until every warp has finished with the planes ----
+    // ---- the FIR roles; results stay in registers until every warp has finished with the planes.  The /4 outputs are
+    //      split 192 + 64 (6 resp. 2 per lane) and the /8 planes one per warp, so that the four warps -- the four SM
+    //      sub-partitions -- carry 768 / 768 / 872 / 768 FFMA2 (p.balanced; the first version's 1024 / 1024 / 1024 / 104
+    //      left one sub-partition idle through the FIR phase: p.balanced = 0, kept for A/B) ----
     const int n_audio = nts >> 2, n_rds = nts >> 3;
     const int gi0 = n0 >> 2;                                    // audio index of the tile's first output within the block
     const int o_first = (10 - gi0 % 10) % 10;                   // first output of the tile the estimator reads
-    float2 acc8[8], sparse = make_float2(0.0f, 0.0f);
+    float2 acc8[8], acc4[4], sparse = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int r = 0; r < 8; r++) acc8[r] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < 4; r++) acc4[r] = make_float2(0.0f, 0.0f);
+    constexpr bool bal = BAL;
     if (warp < 2) {
-        // /4 FIR: output o = 8*lane + r reads staged samples 4o + 4 + k
-        if (8 * lane < n_audio)
-            fir128<4, 8>(s_sig + (warp == 0 ? 0 : 2 * K4_PLEN), s_taps + (warp == 0 ? 0 : K4_NN), 32 * lane + 4, acc8);
-    } else if (warp == 2) {
-        // /8 FIR, real then imaginary plane: output o = 4*lane + r reads staged samples 8o + 8 + k.
-        // This warp owns its outputs completely: RDS samples and their AGC power partial leave from registers.
-        float2 pw = make_float2(0.0f, 0.0f);
+        // /4 FIR: L+R on the real plane (warp 0), L-R on the imaginary plane of the 38 kHz mixdown (warp 1)
+        const float2* sg = s_sig + (warp == 0 ? 0 : 2 * K4_PLEN);
+        const float2* tp = s_taps + (warp == 0 ? 0 : K4_NN);
+        if (bal) {
+            if (6 * lane < n_audio) { float2 a6[6]; fir128<4, 6>(sg, tp, 24 * lane + 4, a6);
+#pragma unroll
+                for (int r = 0; r < 6; r++) acc8[r] = a6[r]; }
+        } else if (8 * lane < n_audio) fir128<4, 8>(sg, tp, 32 * lane + 4, acc8);
+    } else if (bal || warp == 2) {
+        // /8 FIR of the 57 kHz mixdown: real plane (warp 2), imaginary plane (warp 3; warp 2 as well when not balanced)
         if (4 * lane < n_rds) {
-            float2 re[4], im[4];
-            fir128<8, 4>(s_sig + 3 * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, re);
-            fir128<8, 4>(s_sig + 4 * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, im);
-            float4* dA4 = (float4*)(rds_out + (size_t)sA * (p.n >> 3) + (n0 >> 3) + 4 * lane);
-            dA4[0] = make_float4(re[0].x, im[0].x, re[1].x, im[1].x);
-            dA4[1] = make_float4(re[2].x, im[2].x, re[3].x, im[3].x);
-            if (hasB) {
-                float4* dB4 = (float4*)(rds_out + (size_t)sB * (p.n >> 3) + (n0 >> 3) + 4 * lane);
-                dB4[0] = make_float4(re[0].y, im[0].y, re[1].y, im[1].y);
-                dB4[1] = make_float4(re[2].y, im[2].y, re[3].y, im[3].y);
+            fir128<8, 4>(s_sig + (warp == 2 ? 3 : 4) * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, acc4);
+            if (!bal) {
+                float2 im[4];
+                fir128<8, 4>(s_sig + 4 * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, im);
+#pragma unroll
+                for (int r = 0; r < 4; r++) acc8[r] = im[r];
             }
-#pragma unroll
-            for (int r = 0; r < 4; r++) pw = __fadd2_rn(pw, __ffma2_rn(re[r], re[r], __fmul2_rn(im[r], im[r])));
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { pw.x += __shfl_xor_sync(0xffffffffu, pw.x, off); pw.y += __shfl_xor_sync(0xffffffffu, pw.y, off); }
-        if (lane == 0) {
-            rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
-            if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
+        // the last quarter of the /4 outputs, 192 + 2 lane, + 1: L+R (warp 2) / L-R (warp 3)
+        if (bal && 192 + 2 * lane < n_audio) {
+            float2 a2[2];
+            fir128<4, 2>(s_sig + (warp == 2 ? 0 : 2 * K4_PLEN), s_taps + (warp == 2 ? 0 : K4_NN), 4 * (192 + 2 * lane) + 4, a2);
+            acc8[0] = a2[0]; acc8[1] = a2[1];
         }
-    } else {
-        // warp 3 (no FIR role of its own): the 26 sparse outputs, off warp 1's critical path
+    }
+    if (warp == (bal ? 2 : 3)) {
         // real part of L-R where the estimator looks: output o_first + 10*lane, taps ascending
         const int o = o_first + 10 * lane;
         if (o < n_audio) {
@@ -265,13 +269,54 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         }
     }
     __syncthreads();                                            // planes and taps are dead from here on
-    if (warp < 2) {
-        float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 8 * lane;
+    // results -> shared memory (aliased onto the dead planes): lpr[256], lmr[256], sparse[32], est[128], rds re[128], rds im[128]
+    if (bal) {
+        if (warp < 2) {
+            float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 6 * lane;
 #pragma unroll
-        for (int q = 0; q < 4; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
+            for (int q = 0; q < 3; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
+        } else {
+            *(float4*)(s_res + (warp == 2 ? K4_RES_LPR : K4_RES_LMR) + 192 + 2 * lane) = make_float4(acc8[0].x, acc8[0].y, acc8[1].x, acc8[1].y);
+            float2* d = s_res + (warp == 2 ? K4_RES_RRE : K4_RES_RIM) + 4 * lane;
+            *(float4*)(d) = make_float4(acc4[0].x, acc4[0].y, acc4[1].x, acc4[1].y);
+            *(float4*)(d + 2) = make_float4(acc4[2].x, acc4[2].y, acc4[3].x, acc4[3].y);
+            if (warp == 2) s_res[K4_RES_SPARSE + lane] = sparse;
+        }
+    } else {
+        if (warp < 2) {
+            float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 8 * lane;
+#pragma unroll
+            for (int q = 0; q < 4; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
+        } else if (warp == 2) {
+            float2* d = s_res + K4_RES_RRE + 4 * lane; float2* e = s_res + K4_RES_RIM + 4 * lane;
+            *(float4*)(d) = make_float4(acc4[0].x, acc4[0].y, acc4[1].x, acc4[1].y); *(float4*)(d + 2) = make_float4(acc4[2].x, acc4[2].y, acc4[3].x, acc4[3].y);
+            *(float4*)(e) = make_float4(acc8[0].x, acc8[0].y, acc8[1].x, acc8[1].y); *(float4*)(e + 2) = make_float4(acc8[2].x, acc8[2].y, acc8[3].x, acc8[3].y);
+        } else s_res[K4_RES_SPARSE + lane] = sparse;
     }
-    if (warp == 3) s_res[K4_RES_SPARSE + lane] = sparse;
     __syncthreads();
+    // ---- RDS samples (thread t owns output t) and the AGC power partial of the tile (dsp/agc.h:21-30): lane l of warp 1
+    //      sums outputs 4 l .. 4 l + 3, the lanes are reduced by xor-shuffles ----
+    if (t < n_rds) {
+        const float2 re = s_res[K4_RES_RRE + t], im = s_res[K4_RES_RIM + t];
+        rds_out[(size_t)sA * (p.n >> 3) + (n0 >> 3) + t] = make_float2(re.x, im.x);
+        if (hasB) rds_out[(size_t)sB * (p.n >> 3) + (n0 >> 3) + t] = make_float2(re.y, im.y);
+    }
+    if (warp == 1) {
+        float2 pw = make_float2(0.0f, 0.0f);
+        if (4 * lane < n_rds) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float2 re = s_res[K4_RES_RRE + 4 * lane + r], im = s_res[K4_RES_RIM + 4 * lane + r];
+                pw = __fadd2_rn(pw, __ffma2_rn(re, re, __fmul2_rn(im, im)));
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { pw.x += __shfl_xor_sync(0xffffffffu, pw.x, off); pw.y += __shfl_xor_sync(0xffffffffu, pw.y, off); }
+        if (lane == 0) {
+            rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
+            if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
+        }
+    }
 
     // ---- MixAudio (:549-585) + phase-estimator partial sum (:496-511), 2 outputs per thread ----
     float2 est = make_float2(0.0f, 0.0f);
@@ -325,277 +370,6 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// k4_mix_fir_v2: the same arithmetic (sample for sample, tap order ascending), restructured around what ncu showed
-// for the kernel above -- FMA pipe 42 % busy, top stall `barrier`, one of four SM sub-partitions idle in the FIR phase:
-//   * persistent CTAs of 256 threads walk contiguous runs of (stream pair, tile) units; warps 4-7 are PRODUCERS (global
-//     loads + harmonic mixdown of unit u + 1 into the other plane buffer), warps 0-3 are CONSUMERS (FIRs + MixAudio /
-//     estimator epilogue of unit u): the mix of the next tile -- and its global-load latency -- overlaps the FIRs of
-//     this one, handed over with named barriers (full / empty per buffer) instead of CTA-wide __syncthreads;
-//   * inside a run the 128-sample FIR halo of a tile is the tail of the previous tile's planes (copied shared -> shared),
-//     not re-loaded and re-mixed; a run that starts inside a stream pair re-mixes its first halo (same phase offset,
-//     same bits as the owner of the previous tile computed), a pair's first tile takes the carried history;
-//   * the FIR roles are split 6 / 6 / 2 outputs per lane so that the four consumer warps carry 768 / 768 / 872 / 768
-//     FFMA2 instead of 1024 / 1024 / 1024 / 104: every SM sub-partition has the same FIR load.
-// Two CTAs per SM (2 x 46 KB of planes each).
-constexpr int K4V2_THREADS = 256;
-constexpr int K4V2_RES = 2 * (K4_TS / 4) + 2 * (K4_TS / 8) + K4_SPARSE_MAX + 128;        // lpr, lmr, rds re, rds im, sparse, est partials
-constexpr int K4V2_SMEM_BYTES = (2 * 5 * K4_PLEN + 3 * K4_NN + K4V2_RES) * (int)sizeof(float2);
-
-__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id, int count) { __threadfence_block(); asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-
-__global__ void __launch_bounds__(K4V2_THREADS, 2)
-k4_mix_fir_v2(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_dt,
-              const float* __restrict__ hist_x_in, const float2* __restrict__ hist_m2_in, const float2* __restrict__ hist_m3_in,
-              float* __restrict__ hist_x_out, float2* __restrict__ hist_m2_out, float2* __restrict__ hist_m3_out,
-              const float* __restrict__ lmr_phase, float2* __restrict__ audio_out, float2* __restrict__ rds_out,
-              float* __restrict__ est_partial, float* __restrict__ rds_power_partial,
-              float* __restrict__ dbg_lpr, float* __restrict__ dbg_lmr, const __grid_constant__ K4Params p)
-{
-    extern __shared__ __align__(16) float2 smem4[];
-    float2* s_planes = smem4;                                   // [2][5][K4_PLEN]: xr, m2r, m2i, m3r, m3i
-    float2* s_taps = smem4 + 2 * 5 * K4_PLEN;                   // [3][K4_NN] duplicated taps: lpr, lmr, rds
-    float2* s_res = s_taps + 3 * K4_NN;                         // consumer results: [lpr 256][lmr 256][rds re 128][rds im 128][sparse 32][est 128]
-    constexpr int R_LPR = 0, R_LMR = K4_TS / 4, R_RRE = 2 * (K4_TS / 4), R_RIM = R_RRE + K4_TS / 8, R_SP = R_RIM + K4_TS / 8, R_EST = R_SP + K4_SPARSE_MAX;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_pairs = (p.n_streams + 1) / 2;
-    const int n_units = n_pairs * p.n_tiles;
-    // contiguous run of units of this CTA
-    const int u_begin = (int)(((long long)n_units * blockIdx.x) / gridDim.x), u_end = (int)(((long long)n_units * (blockIdx.x + 1)) / gridDim.x);
-    if (u_begin >= u_end) return;
-
-    for (int k = tid; k < K4_NN; k += K4V2_THREADS) {
-        s_taps[k] = bc2(p.taps_lpr[k]); s_taps[K4_NN + k] = bc2(p.taps_lmr[k]); s_taps[2 * K4_NN + k] = bc2(p.taps_rds[k]);
-    }
-    if (tid < 16) {
-#pragma unroll
-        for (int a = 0; a < 5; a++) s_planes[((tid >> 3) * 5 + a) * K4_PLEN + K4_PLEN - 8 + (tid & 7)] = make_float2(0.0f, 0.0f);   // the quad a window may over-read
-    }
-    __syncthreads();
-    // barrier ids: 1 + b = full[b] (planes of buffer b are complete), 3 + b = empty[b] (consumers are done with buffer b), 5 = consumers only
-    if (warp >= 4) {
-        // ================= producers: global loads + mixdown into s_planes[b] =================
-        const int t = tid - 128;
-        for (int u = u_begin; u < u_end; u++) {
-            const int b = (u - u_begin) & 1;
-            const int pair = u / p.n_tiles, tile = u - pair * p.n_tiles;
-            const int sA = 2 * pair;
-            const bool hasB = sA + 1 < p.n_streams;
-            const int sB = hasB ? sA + 1 : sA;
-            const int n0 = tile * K4_TS;
-            const int nts = min(K4_TS, p.n - n0);
-            float2* sg = s_planes + b * 5 * K4_PLEN;
-            const float2 off2 = wrap2(make_float2(lmr_phase[sA], lmr_phase[sB]));
-            const float2 off_c = chebyshev_sine2(wrap2(__fadd2_rn(off2, bc2(0.25f)))), off_s = chebyshev_sine2(off2);
-            const float2* xA = fm_out_iq + (size_t)sA * p.n, * xB = fm_out_iq + (size_t)sB * p.n;
-            const float* dA = pll_dt + (size_t)sA * p.n, * dB = pll_dt + (size_t)sB * p.n;
-            // which part of the staged array [0, 128 + nts) is mixed from global memory: the whole of it when the run starts
-            // inside a pair (halo re-mixed), else only the tile; the halo then comes from history or the previous buffer
-            const bool remix_halo = (u == u_begin) && tile > 0;
-            const int idx0 = remix_halo ? 0 : K4_NN;
-            constexpr int NIT = (K4_LEN + 127) / 128;           // 9
-            float2 vxa[NIT], vxb[NIT], vdt[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; it++) {                  // every global load first (before waiting for the buffer)
-                const int idx = idx0 + t + it * 128;
-                const int n = n0 - K4_NN + idx;
-                if (idx < K4_NN + nts) {
-                    vxa[it] = __ldg(xA + n); vxb[it] = __ldg(xB + n);
-                    vdt[it] = make_float2(__ldg(dA + n), __ldg(dB + n));
-                } else { vxa[it] = vxb[it] = vdt[it] = make_float2(0.0f, 0.0f); }
-            }
-            if (u - u_begin >= 2) named_sync(3 + b, K4V2_THREADS);      // consumers have released this buffer
-            if (!remix_halo && t < K4_NN) {
-                const int a = a4(t);
-                if (tile == 0) {                                // the carried history of the pair's previous block
-                    const float2 h2a = hist_m2_in[(size_t)sA * K4_NN + t], h2b = hist_m2_in[(size_t)sB * K4_NN + t];
-                    const float2 h3a = hist_m3_in[(size_t)sA * K4_NN + t], h3b = hist_m3_in[(size_t)sB * K4_NN + t];
-                    sg[a] = make_float2(hist_x_in[(size_t)sA * K4_NN + t], hist_x_in[(size_t)sB * K4_NN + t]);
-                    sg[K4_PLEN + a] = make_float2(h2a.x, h2b.x); sg[2 * K4_PLEN + a] = make_float2(h2a.y, h2b.y);
-                    sg[3 * K4_PLEN + a] = make_float2(h3a.x, h3b.x); sg[4 * K4_PLEN + a] = make_float2(h3a.y, h3b.y);
-                } else {                                        // the tail of the previous tile (always a full tile), other buffer
-                    const float2* so = s_planes + (b ^ 1) * 5 * K4_PLEN;
-                    const int ao = a4(K4_TS + t);
-#pragma unroll
-                    for (int pl = 0; pl < 5; pl++) sg[pl * K4_PLEN + a] = so[pl * K4_PLEN + ao];
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < NIT; it++) {
-                const int idx = idx0 + t + it * 128;
-                if (idx >= K4_NN + nts) continue;
-                const float2 xr = make_float2(vxa[it].x, vxb[it].x);
-                const float2 xi = make_float2(vxa[it].y, vxb[it].y);
-                const float2 t1 = vdt[it];
-                const float2 c1 = chebyshev_sine2(__fadd2_rn(bc2(0.25f), make_float2(-fabsf(t1.x), -fabsf(t1.y))));
-                const float2 s1 = chebyshev_sine2(t1);
-                const float2 c2 = __ffma2_rn(c1, c1, neg2(__fmul2_rn(s1, s1)));
-                const float2 s2 = __fmul2_rn(__fadd2_rn(s1, s1), c1);
-                const float2 c3 = __ffma2_rn(c2, c1, neg2(__fmul2_rn(s2, s1)));
-                const float2 s3 = __ffma2_rn(s2, c1, __fmul2_rn(c2, s1));
-                const float2 C2 = __ffma2_rn(c2, off_c, neg2(__fmul2_rn(s2, off_s)));
-                const float2 S2 = __ffma2_rn(s2, off_c, __fmul2_rn(c2, off_s));
-                const int a = a4(idx);
-                sg[a] = xr;
-                sg[K4_PLEN + a] = __ffma2_rn(xr, C2, neg2(__fmul2_rn(xi, S2))); sg[2 * K4_PLEN + a] = __ffma2_rn(xr, S2, __fmul2_rn(xi, C2));
-                sg[3 * K4_PLEN + a] = __ffma2_rn(xr, c3, neg2(__fmul2_rn(xi, s3))); sg[4 * K4_PLEN + a] = __ffma2_rn(xr, s3, __fmul2_rn(xi, c3));
-            }
-            named_sync(6, 128);                                 // producers: the staged array is complete (history write below reads it)
-            if (n0 + nts == p.n && t < K4_NN) {                 // history for the next block: the last 128 staged samples of the pair
-                const int a = a4(nts + t);
-                const float2 x = sg[a], r2 = sg[K4_PLEN + a], i2 = sg[2 * K4_PLEN + a], r3 = sg[3 * K4_PLEN + a], i3 = sg[4 * K4_PLEN + a];
-                hist_x_out[(size_t)sA * K4_NN + t] = x.x;
-                hist_m2_out[(size_t)sA * K4_NN + t] = make_float2(r2.x, i2.x);
-                hist_m3_out[(size_t)sA * K4_NN + t] = make_float2(r3.x, i3.x);
-                if (hasB) {
-                    hist_x_out[(size_t)sB * K4_NN + t] = x.y;
-                    hist_m2_out[(size_t)sB * K4_NN + t] = make_float2(r2.y, i2.y);
-                    hist_m3_out[(size_t)sB * K4_NN + t] = make_float2(r3.y, i3.y);
-                }
-            }
-            named_arrive(1 + b, K4V2_THREADS);                  // full[b]
-        }
-    } else {
-        // ================= consumers: FIR roles + epilogue =================
-        for (int u = u_begin; u < u_end; u++) {
-            const int b = (u - u_begin) & 1;
-            const int pair = u / p.n_tiles, tile = u - pair * p.n_tiles;
-            const int sA = 2 * pair;
-            const bool hasB = sA + 1 < p.n_streams;
-            const int sB = hasB ? sA + 1 : sA;
-            const int n0 = tile * K4_TS;
-            const int nts = min(K4_TS, p.n - n0);
-            const float2* sg = s_planes + b * 5 * K4_PLEN;
-            const int n_audio = nts >> 2, n_rds = nts >> 3;
-            const int gi0 = n0 >> 2;
-            const int o_first = (10 - gi0 % 10) % 10;
-            named_sync(1 + b, K4V2_THREADS);                    // full[b]
-            if (warp < 2) {
-                // /4 FIR, outputs 6 lane .. 6 lane + 5 (< 192): L+R on the real plane (warp 0), L-R on the 38 kHz imaginary plane (warp 1)
-                if (6 * lane < n_audio) {
-                    float2 acc[6];
-                    fir128<4, 6>(sg + (warp == 0 ? 0 : 2 * K4_PLEN), s_taps + (warp == 0 ? 0 : K4_NN), 24 * lane + 4, acc);
-                    float2* d = s_res + (warp == 0 ? R_LPR : R_LMR) + 6 * lane;
-#pragma unroll
-                    for (int q = 0; q < 3; q++) *(float4*)(d + 2 * q) = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
-                }
-            } else {
-                // /8 FIR of one plane of the 57 kHz mixdown (warp 2: real, warp 3: imaginary), outputs 4 lane .. 4 lane + 3
-                if (4 * lane < n_rds) {
-                    float2 acc[4];
-                    fir128<8, 4>(sg + (warp == 2 ? 3 : 4) * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, acc);
-                    float2* d = s_res + (warp == 2 ? R_RRE : R_RIM) + 4 * lane;
-                    *(float4*)(d) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-                    *(float4*)(d + 2) = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-                }
-                // the last quarter of the /4 outputs, 192 + 2 lane, + 1: L+R (warp 2) / L-R (warp 3)
-                if (192 + 2 * lane < n_audio) {
-                    float2 acc[2];
-                    fir128<4, 2>(sg + (warp == 2 ? 0 : 2 * K4_PLEN), s_taps + (warp == 2 ? 0 : K4_NN), 4 * (192 + 2 * lane) + 4, acc);
-                    *(float4*)(s_res + (warp == 2 ? R_LPR : R_LMR) + 192 + 2 * lane) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-                }
-                if (warp == 2) {
-                    // real part of L-R where the estimator looks: output o_first + 10 lane, taps ascending
-                    const int o = o_first + 10 * lane;
-                    float2 sparse = make_float2(0.0f, 0.0f);
-                    if (o < n_audio) {
-                        const float2* sp = sg + K4_PLEN;
-                        const float2* tp = s_taps + K4_NN;
-#pragma unroll 4
-                        for (int q = 0; q < 32; q++) {
-                            const float4 x01 = *(const float4*)(sp + a4(4 * o + 4 + 4 * q)), x23 = *(const float4*)(sp + a4(4 * o + 4 + 4 * q + 2));
-                            const float4 b01 = *(const float4*)(tp + 4 * q), b23 = *(const float4*)(tp + 4 * q + 2);
-                            sparse = __ffma2_rn(make_float2(x01.x, x01.y), make_float2(b01.x, b01.y), sparse);
-                            sparse = __ffma2_rn(make_float2(x01.z, x01.w), make_float2(b01.z, b01.w), sparse);
-                            sparse = __ffma2_rn(make_float2(x23.x, x23.y), make_float2(b23.x, b23.y), sparse);
-                            sparse = __ffma2_rn(make_float2(x23.z, x23.w), make_float2(b23.z, b23.w), sparse);
-                        }
-                    }
-                    s_res[R_SP + lane] = sparse;
-                }
-            }
-            named_sync(5, 128);                                 // consumers: every result is in s_res; the planes are no longer read
-            named_arrive(3 + b, K4V2_THREADS);                  // empty[b]
-            // ---- RDS samples: thread t owns output t ----
-            if (tid < n_rds) {
-                const float2 re = s_res[R_RRE + tid], im = s_res[R_RIM + tid];
-                rds_out[(size_t)sA * (p.n >> 3) + (n0 >> 3) + tid] = make_float2(re.x, im.x);
-                if (hasB) rds_out[(size_t)sB * (p.n >> 3) + (n0 >> 3) + tid] = make_float2(re.y, im.y);
-            }
-            // ---- AGC power partial of the tile (dsp/agc.h:21-30), in the association of the kernel above: lane l sums
-            //      outputs 4 l .. 4 l + 3, the lanes are reduced by xor-shuffles ----
-            if (warp == 1) {
-                float2 pw = make_float2(0.0f, 0.0f);
-                if (4 * lane < n_rds) {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float2 re = s_res[R_RRE + 4 * lane + r], im = s_res[R_RIM + 4 * lane + r];
-                        pw = __fadd2_rn(pw, __ffma2_rn(re, re, __fmul2_rn(im, im)));
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) { pw.x += __shfl_xor_sync(0xffffffffu, pw.x, off); pw.y += __shfl_xor_sync(0xffffffffu, pw.y, off); }
-                if (lane == 0) {
-                    rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
-                    if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
-                }
-            }
-            // ---- MixAudio (:549-585) + phase-estimator partial sum (:496-511), 2 outputs per thread ----
-            float2 est = make_float2(0.0f, 0.0f);
-            if (2 * tid < n_audio) {
-                const int o = 2 * tid;
-                const size_t gi = (size_t)gi0 + o;
-                float4 frA, frB;
-                float* fA = &frA.x; float* fB = &frB.x;
-                float2 lprs[2], lmrs[2];
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const float2 lpr = s_res[R_LPR + o + j], lmr = s_res[R_LMR + o + j];
-                    lprs[j] = lpr; lmrs[j] = lmr;
-                    float2 L, R;
-                    if (p.audio_out_mode == 2) { L = __ffma2_rn(bc2(p.stereo_mix), lmr, lpr); R = __ffma2_rn(bc2(-p.stereo_mix), lmr, lpr); }
-                    else if (p.audio_out_mode == 1) { L = lmr; R = lmr; }
-                    else { L = lpr; R = lpr; }
-                    fA[2 * j] = L.x * 2.0f; fA[2 * j + 1] = R.x * 2.0f;
-                    fB[2 * j] = L.y * 2.0f; fB[2 * j + 1] = R.y * 2.0f;
-                    if ((gi + j) % 10 == 0) {
-                        const float2 lre = s_res[R_SP + (o + j - o_first) / 10];
-                        const float pa = atan2f(lmr.x, lre.x), pb = atan2f(lmr.y, lre.y);
-                        est.x += (pa > 0.0f) ? (PI_F / 2.0f - pa) : (-PI_F / 2.0f - pa);
-                        est.y += (pb > 0.0f) ? (PI_F / 2.0f - pb) : (-PI_F / 2.0f - pb);
-                    }
-                }
-                *(float4*)(audio_out + (size_t)sA * (p.n >> 2) + gi) = frA;
-                if (hasB) *(float4*)(audio_out + (size_t)sB * (p.n >> 2) + gi) = frB;
-                if (p.keep) {
-                    *(float2*)(dbg_lpr + (size_t)sA * (p.n >> 2) + gi) = make_float2(lprs[0].x, lprs[1].x);
-                    *(float2*)(dbg_lmr + (size_t)sA * (p.n >> 2) + gi) = make_float2(lmrs[0].x, lmrs[1].x);
-                    if (hasB) {
-                        *(float2*)(dbg_lpr + (size_t)sB * (p.n >> 2) + gi) = make_float2(lprs[0].y, lprs[1].y);
-                        *(float2*)(dbg_lmr + (size_t)sB * (p.n >> 2) + gi) = make_float2(lmrs[0].y, lmrs[1].y);
-                    }
-                }
-            }
-            // ---- estimator partials in the order of the kernel above: per thread -> 4 per lane -> xor-shuffles in warp 0 ----
-            s_res[R_EST + tid] = est;
-            named_sync(5, 128);
-            if (warp == 0) {
-                float2 v = s_res[R_EST + 4 * lane];
-#pragma unroll
-                for (int q = 1; q < 4; q++) { const float2 e = s_res[R_EST + 4 * lane + q]; v.x += e.x; v.y += e.y; }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, off); v.y += __shfl_xor_sync(0xffffffffu, v.y, off); }
-                if (lane == 0) {
-                    est_partial[(size_t)sA * p.n_tiles + tile] = v.x;
-                    if (hasB) est_partial[(size_t)sB * p.n_tiles + tile] = v.y;
-                }
-            }
-            named_sync(5, 128);                                 // s_res is free for the next unit
-        }
-    }
-}
-
 // broadcast_fm_demod.cpp:511-516: avg over ceil(N_audio/10) samples, err += 0.1*avg, fmod 2 pi.
 __global__ void k4b_lmr_phase(const float* __restrict__ est_partial, float* __restrict__ lmr_phase,
                               int n_tiles, int n_audio, int n_streams)
@@ -623,24 +397,19 @@ cudaError_t launch_k4(const float2* fm_out_iq, const float* pll_dt,
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(k4_mix_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k4_mix_fir<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k4_mix_fir_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, K4V2_SMEM_BYTES);
+        e = cudaFuncSetAttribute(k4_mix_fir<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
-    if (p.v1) {
-        const dim3 grid(p.n_tiles, (p.n_streams + 1) / 2);
-        k4_mix_fir<<<grid, K4_THREADS, K4_SMEM_BYTES, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,
-                                                hist_x_out, hist_m2_out, hist_m3_out, lmr_phase, audio_out, rds_out,
-                                                est_partial, rds_power_partial, dbg_lpr, dbg_lmr, p);
-    } else {
-        const int n_units = ((p.n_streams + 1) / 2) * p.n_tiles;
-        const int grid = std::max(1, std::min(n_units, 2 * std::max(1, p.n_sm)));
-        k4_mix_fir_v2<<<grid, K4V2_THREADS, K4V2_SMEM_BYTES, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,
-                                                hist_x_out, hist_m2_out, hist_m3_out, lmr_phase, audio_out, rds_out,
-                                                est_partial, rds_power_partial, dbg_lpr, dbg_lmr, p);
-    }
+    const dim3 grid(p.n_tiles, (p.n_streams + 1) / 2);
+    if (p.balanced) k4_mix_fir<true><<<grid, K4_THREADS, K4_SMEM_BYTES, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,
+                                            hist_x_out, hist_m2_out, hist_m3_out, lmr_phase, audio_out, rds_out,
+                                            est_partial, rds_power_partial, dbg_lpr, dbg_lmr, p);
+    else k4_mix_fir<false><<<grid, K4_THREADS, K4_SMEM_BYTES, st>>>(fm_out_iq, pll_dt, hist_x_in, hist_m2_in, hist_m3_in,
+                                            hist_x_out, hist_m2_out, hist_m3_out, lmr_phase, audio_out, rds_out,
+                                            est_partial, rds_power_partial, dbg_lpr, dbg_lmr, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k4b_lmr_phase<<<(p.n_streams + 127) / 128, 128, 0, st>>>(est_partial, lmr_phase, p.n_tiles, p.n >> 2, p.n_streams);
