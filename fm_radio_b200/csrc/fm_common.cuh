@@ -165,7 +165,7 @@ struct K4Params {
     int parity;
     int n_streams;
     int keep;
-    int balanced;               // 1: FIR roles split 6 / 6 / 2 outputs per lane over the four warps; 0: the first version's 8 / 8 / 4+4 / sparse
+    int balanced;               // 1: FIR taps as constant-bank operands (production); 0: from shared memory (first version, A/B)
 };
 
 struct K5Params {

@@ -71,6 +71,8 @@ struct HostMirror {                // pinned
 
 } // namespace
 
+namespace { struct GraphEntry { cudaGraphExec_t exec = nullptr; const void* in_ptr = nullptr; bool u8 = false; unsigned long long gen = 0; }; }
+
 struct fmgpu_demod {
     fmgpu_config cfg{};
     int B = 0, S = 0, n4 = 0, n8 = 0, n32 = 0, n64 = 0, depth = 0, k4_tiles = 0;
@@ -93,6 +95,11 @@ struct fmgpu_demod {
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
     bool k5_literal = false, k3_exact = false, k4_v1 = false;
+    // CUDA-graph replay of small blocks (enqueue_chain)
+    cudaStream_t stG = nullptr;
+    bool use_graph = false, last_was_graph = false;
+    unsigned long long graph_gen = 1;
+    std::vector<GraphEntry> graphs;
     unsigned fetch_mask = FMGPU_FETCH_ALL, last_fetch_mask = 0;
     float* k2_hist_demod = nullptr; float* k2_hist_out = nullptr; float* k2_scal = nullptr;
     float* pll_state = nullptr;
@@ -280,6 +287,12 @@ int alloc_all(fmgpu_demod* h) {
         CU(cudaStreamCreateWithPriority(&h->stE, cudaStreamNonBlocking, prio_hi));
     }
     h->use_k1t = std::getenv("FMGPU_K1_FP32") == nullptr;
+    CU(cudaStreamCreateWithFlags(&h->stG, cudaStreamNonBlocking));
+    h->graphs.assign((size_t)h->depth * 2, GraphEntry{});
+    // launch-bound regime: with few streams and short blocks every kernel lasts a few microseconds and the ~60 API calls
+    // of the multi-stream pipeline dominate; large batches keep the pipeline (its cross-block overlap hides the recurrences)
+    h->use_graph = !std::getenv("FMGPU_NO_GRAPH") && (size_t)h->S * (size_t)h->B <= (size_t)1 << 20 && h->B <= 16384;
+    if (const char* e = std::getenv("FMGPU_GRAPH")) h->use_graph = std::atoi(e) != 0;
     h->k5_literal = std::getenv("FMGPU_K5_LITERAL") != nullptr;
     h->k3_exact = std::getenv("FMGPU_K3_EXACT") != nullptr;
     h->k4_v1 = std::getenv("FMGPU_K4_V1") != nullptr;
@@ -364,8 +377,10 @@ int alloc_all(fmgpu_demod* h) {
 void free_all(fmgpu_demod* h) {
     // only this handle's streams are drained: other handles and streams of the device keep running
     {
-        cudaStream_t sts0[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
+        cudaStream_t sts0[10] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO, h->stG };
         for (auto st : sts0) if (st) cudaStreamSynchronize(st);
+        for (auto& ge : h->graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
+        if (h->stG) cudaStreamDestroy(h->stG);
     }
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int i = 0; i < 2; i++) { F(h->k1t_hist[i]); F(h->k1t_theta[i]); }
@@ -428,21 +443,35 @@ int prepare_pcm(fmgpu_demod* h) {
 }
 
 // Enqueue the chain for one block whose input is already ordered on stA (or signalled by ev_H).
-int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cudaEvent_t* prof = nullptr) {
-    // K1's FIR history is kept as bytes by the u8 kernels (exact) and as floats by the cf32 kernel; the u8 kernels also
-    // write the float copy, so cf32 may follow u8, but arbitrary floats cannot become bytes again
-    if (u8 && h->last_input_kind == 2)
-        return fail(FMGPU_ERR_STATE, "enqueue: a u8 block cannot follow a cf32 block on the same handle (the FIR history would be truncated to bytes)");
-    h->last_input_kind = u8 ? 1 : 2;
-    update_filters(h);
+// K1's tensor-core tables follow the fm_in taps (fmgpu_upload_taps may change them); synchronous, so never inside a capture
+int ensure_k1t_tables(fmgpu_demod* h) {
+    if (h->k1t_ready && std::memcmp(h->k1t_taps, h->taps.fm_in, sizeof(h->k1t_taps)) == 0) return FMGPU_OK;
+    std::vector<int8_t> bimg; std::vector<int> ptab;
+    fm::k1t_build_tables(h->taps.fm_in, bimg, ptab, h->k1t_off, h->k1t_w);
+    if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+    CU(cudaMemcpy(h->k1t_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->k1t_ptab, ptab.data(), ptab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    std::memcpy(h->k1t_taps, h->taps.fm_in, sizeof(h->k1t_taps));
+    h->k1t_ready = true;
+    return FMGPU_OK;
+}
+
+// The kernels of one block.  single == nullptr: the production pipeline -- every stage on its own stream, ordered by the
+// slot's events, blocks overlapping.  single != nullptr: every kernel on that one stream in chain order, no events --
+// the form that is captured into a CUDA graph for small, launch-bound blocks (enqueue_block below).
+int enqueue_chain_on(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cudaEvent_t* prof, cudaStream_t single) {
+    cudaStream_t stA = single ? single : stA, stA2 = single ? single : stA2, stP = single ? single : stP,
+                 stB = single ? single : stB, stC = single ? single : stC, stD = single ? single : stD, stE = single ? single : stE;
+#define EV_WAIT(st, ev) do { if (!single) CU(cudaStreamWaitEvent(st, ev, 0)); } while (0)
+#define EV_REC(ev, st) do { if (!single) CU(cudaEventRecord(ev, st)); } while (0)
     const int slot = (int)(h->step % (unsigned long long)h->depth);
     const int parity = (int)(h->step & 1ull);
     Slot& sl = h->slots[slot];
     const bool keep = h->cfg.keep_intermediates != 0;
 
     // ---- stage A: K1 + K2 ----
-    CU(cudaStreamWaitEvent(h->stA, sl.ev_C, 0));        // previous user of this slot's A/B buffers
-    if (wait_H) CU(cudaStreamWaitEvent(h->stA, sl.ev_H, 0));
+    EV_WAIT(stA, sl.ev_C);        // previous user of this slot's A/B buffers
+    if (wait_H) EV_WAIT(stA, sl.ev_H);
     {
         fm::K1Params p{};
         std::memcpy(p.taps, h->taps.fm_in, sizeof(p.taps));
@@ -463,18 +492,9 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         const float Ts = 1.0f / 256000.0f;
         p.discrim_gain = 1.0f / (Wd * Ts) * 0.5f;
         p.n_out = h->n4; p.parity = parity; p.n_streams = h->S; p.first_block = (h->step == 0); p.dbg_fm_in = keep ? h->dbg.fm_in : nullptr;
-        if (prof) CU(cudaEventRecord(prof[0], h->stA));
+        if (prof) CU(cudaEventRecord(prof[0], stA));
         if (u8 && h->use_k1t) {
-            // tensor-core path: the G image follows the fm_in taps (fmgpu_upload_taps may change them)
-            if (!h->k1t_ready || std::memcmp(h->k1t_taps, h->taps.fm_in, sizeof(h->k1t_taps)) != 0) {
-                std::vector<int8_t> bimg; std::vector<int> ptab;
-                fm::k1t_build_tables(h->taps.fm_in, bimg, ptab, h->k1t_off, h->k1t_w);
-                CU(cudaStreamSynchronize(h->stA));
-                CU(cudaMemcpy(h->k1t_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(h->k1t_ptab, ptab.data(), ptab.size() * sizeof(int), cudaMemcpyHostToDevice));
-                std::memcpy(h->k1t_taps, h->taps.fm_in, sizeof(h->k1t_taps));
-                h->k1t_ready = true;
-            }
+            // tensor-core path (tables ensured by the caller: ensure_k1t_tables)
             fm::K1TParams t{};
             t.bimg = h->k1t_bimg; t.ptab = h->k1t_ptab;
             for (int i = 0; i < 3; i++) { t.off[i] = h->k1t_off[i]; t.w[i] = h->k1t_w[i]; }
@@ -482,9 +502,9 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
             t.n_rows = h->B / 64; t.tiles_per_stream = (t.n_rows + 127) / 128; t.n_tiles = t.tiles_per_stream * h->S; t.n_streams = h->S;
             t.theta_in = h->k1t_theta[parity]; t.theta_out = h->k1t_theta[parity ^ 1]; t.dbg_fm_in = p.dbg_fm_in;
             CU(fm::launch_k1t((const uint8_t*)iq_dev, h->k1t_hist[parity], h->k1t_hist[parity ^ 1], h->k1_hist[parity ^ 1], sl.fm_demod,
-                              t, 2 * h->n_sm_fir, h->stA));
+                              t, 2 * h->n_sm_fir, stA));
         } else {
-            CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, h->stA));
+            CU(fm::launch_k1(u8, iq_dev, h->k1_hist[parity], h->k1_hist[parity ^ 1], sl.fm_demod, p, stA));
         }
     }
     {
@@ -495,21 +515,21 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         std::memcpy(p.peak_b, h->taps.peak_b, 12); std::memcpy(p.peak_a, h->taps.peak_a, 12);
         p.use_deemph = h->ctl_use_deemph; p.n_out = h->n8; p.keep = keep;
         fill_scan_matrices(p);
-        if (prof) CU(cudaEventRecord(prof[1], h->stA));
+        if (prof) CU(cudaEventRecord(prof[1], stA));
         // K2 runs on its own stream of the FIR partition: it is one wave of long-lived CTAs (one per stream pair,
         // 3.9 per SM) that leaves half of the FMA pipe idle, and K1 of the NEXT block -- which only needs a free
         // slot, not K2 -- fills those issue slots instead of queueing behind it.
         static const bool k2_own = std::getenv("FMGPU_K2_SAME_STREAM") == nullptr;
-        cudaStream_t st2 = k2_own ? h->stA2 : h->stA;
-        if (k2_own) { CU(cudaEventRecord(sl.ev_K1, h->stA)); CU(cudaStreamWaitEvent(st2, sl.ev_K1, 0)); }
+        cudaStream_t st2 = k2_own ? stA2 : stA;
+        if (k2_own && !single) { EV_REC(sl.ev_K1, stA); EV_WAIT(st2, sl.ev_K1); }
         CU(fm::launch_k2(sl.fm_demod, h->k2_hist_demod, h->k2_hist_out, h->k2_scal, sl.fm_out_iq, sl.theta, sl.power,
                          keep ? h->dbg.pilot : nullptr, p, h->S, st2));
         if (prof) CU(cudaEventRecord(prof[2], st2));
-        CU(cudaEventRecord(sl.ev_A, st2));
+        EV_REC(sl.ev_A, st2);
     }
 
     // ---- stage B: K3 ----
-    CU(cudaStreamWaitEvent(h->stB, sl.ev_A, 0));
+    EV_WAIT(stB, sl.ev_A);
     {
         fm::K3Params p{};
         std::memcpy(p.lpf_b, h->taps.pll_b, 8); std::memcpy(p.lpf_a, h->taps.pll_a, 8);
@@ -518,18 +538,18 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.f_center = -19000.0f; p.f_gain = -100.0f; p.mixer_KTs = Ts;
         p.agc_target = 1.0f; p.agc_beta = 0.2f;
         p.n = h->n8; p.n_streams = h->S; p.keep = keep; p.exact = h->k3_exact ? 1 : 0;
-        if (prof) CU(cudaEventRecord(prof[3], h->stB));
-        CU(fm::launch_k3(sl.theta, sl.power, h->pll_state, sl.pll_dt, h->dbg.pll_raw, h->dbg.pll_pi, p, h->stB));
-        if (prof) CU(cudaEventRecord(prof[4], h->stB));
-        if (keep) { CU(fm::launch_kdbg(h->dbg.pilot, h->pll_state, sl.pll_dt, h->dbg.pll, h->n8, h->S, h->stB)); h->launches++; }
+        if (prof) CU(cudaEventRecord(prof[3], stB));
+        CU(fm::launch_k3(sl.theta, sl.power, h->pll_state, sl.pll_dt, h->dbg.pll_raw, h->dbg.pll_pi, p, stB));
+        if (prof) CU(cudaEventRecord(prof[4], stB));
+        if (keep) CU(fm::launch_kdbg(h->dbg.pilot, h->pll_state, sl.pll_dt, h->dbg.pll, h->n8, h->S, stB));
     }
-    CU(cudaEventRecord(sl.ev_B, h->stB));
+    EV_REC(sl.ev_B, stB);
 
     // ---- stage C: K4 + K4b ----
-    CU(cudaStreamWaitEvent(h->stC, sl.ev_B, 0));
-    CU(cudaStreamWaitEvent(h->stC, sl.ev_D, 0));        // K5 of the slot's previous block read sl.rds
-    CU(cudaStreamWaitEvent(h->stC, sl.ev_O, 0));        // ... and the fetch read sl.audio
-    CU(cudaStreamWaitEvent(h->stC, sl.ev_P, 0));        // ... and so did K7
+    EV_WAIT(stC, sl.ev_B);
+    EV_WAIT(stC, sl.ev_D);        // K5 of the slot's previous block read sl.rds
+    EV_WAIT(stC, sl.ev_O);        // ... and the fetch read sl.audio
+    EV_WAIT(stC, sl.ev_P);        // ... and so did K7
     {
         fm::K4Params p{};
         std::memcpy(p.taps_lpr, h->taps.lpr, sizeof(p.taps_lpr));
@@ -539,24 +559,23 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.stereo_mix = h->ctl_stereo_mix; p.audio_out_mode = h->ctl_audio_out;
         p.n = h->n8; p.n_tiles = h->k4_tiles; p.parity = parity; p.n_streams = h->S; p.keep = keep;
         p.balanced = h->k4_v1 ? 0 : 1;
-        if (keep) CU(cudaMemcpyAsync(h->dbg.lmr_phase_used, h->lmr_phase, (size_t)h->S * sizeof(float), cudaMemcpyDeviceToDevice, h->stC));
-        if (prof) CU(cudaEventRecord(prof[5], h->stC));
+        if (keep) CU(cudaMemcpyAsync(h->dbg.lmr_phase_used, h->lmr_phase, (size_t)h->S * sizeof(float), cudaMemcpyDeviceToDevice, stC));
+        if (prof) CU(cudaEventRecord(prof[5], stC));
         CU(fm::launch_k4(sl.fm_out_iq, sl.pll_dt, h->k4_hist_x[parity], h->k4_hist_m2[parity], h->k4_hist_m3[parity],
                          h->k4_hist_x[parity ^ 1], h->k4_hist_m2[parity ^ 1], h->k4_hist_m3[parity ^ 1],
                          h->lmr_phase, sl.audio, sl.rds, sl.est_partial, sl.rds_pw_partial,
-                         h->dbg.lpr, h->dbg.lmr, p, h->stC));
+                         h->dbg.lpr, h->dbg.lmr, p, stC));
         if (keep) {
             // GUI mode: the complex decimator outputs behind the two audio spectra, then this block's last 128
             // fm_out_iq samples as the next block's history (before ev_C lets K2 overwrite the slot)
             CU(fm::launch_kdbg_audio_iq(sl.fm_out_iq, sl.pll_dt, h->dbg.hist_iq, h->k4_hist_m2[parity], h->dbg.lmr_phase_used,
-                                        h->dbg.lpr_iq, h->dbg.lmr_iq, p, h->stC));
+                                        h->dbg.lpr_iq, h->dbg.lmr_iq, p, stC));
             CU(cudaMemcpy2DAsync(h->dbg.hist_iq, fm::K4_NN * sizeof(float2), sl.fm_out_iq + (h->n8 - fm::K4_NN), (size_t)h->n8 * sizeof(float2),
-                                 fm::K4_NN * sizeof(float2), (size_t)h->S, cudaMemcpyDeviceToDevice, h->stC));
-            h->launches++;
+                                 fm::K4_NN * sizeof(float2), (size_t)h->S, cudaMemcpyDeviceToDevice, stC));
         }
     }
-    if (prof) CU(cudaEventRecord(prof[6], h->stC));
-    CU(cudaEventRecord(sl.ev_C, h->stC));
+    if (prof) CU(cudaEventRecord(prof[6], stC));
+    EV_REC(sl.ev_C, stC);
     // ---- K7 (audio output stage, off by default): on stage stream C behind ev_C, so the RDS stages do not wait for
     //      it.  Measured alternatives (1024 streams, ms per step): its own stream of the FIR partition
     //      (FMGPU_K7_OWN_STREAM) 0.291 vs 0.2805 here -- a fourth concurrent FIR-partition kernel only takes CTA slots
@@ -566,25 +585,24 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         const int rc7 = prepare_pcm(h);
         if (rc7 != FMGPU_OK) return rc7;
         static const bool k7_own = std::getenv("FMGPU_K7_OWN_STREAM") != nullptr;
-        cudaStream_t st7 = k7_own ? h->stP : h->stC;
-        if (k7_own) {
-            CU(cudaStreamWaitEvent(st7, sl.ev_C, 0));
-            CU(cudaStreamWaitEvent(st7, sl.ev_O, 0));   // the fetch of the slot's previous block read sl.pcm_s16
+        cudaStream_t st7 = k7_own ? stP : stC;
+        if (k7_own && !single) {
+            EV_WAIT(st7, sl.ev_C);
+            EV_WAIT(st7, sl.ev_O);   // the fetch of the slot's previous block read sl.pcm_s16
         }
         if (prof) CU(cudaEventRecord(prof[11], st7));
         CU(fm::launch_k7(sl.audio, h->pcm_table, sl.pcm_f32, sl.pcm_s16, h->n32, h->pcm_n, h->S, st7));
-        h->launches++;
         if (prof) CU(cudaEventRecord(prof[10], st7));
-        CU(cudaEventRecord(sl.ev_P, st7));
+        EV_REC(sl.ev_P, st7);
     } else if (prof) {
-        CU(cudaEventRecord(prof[11], h->stC));
-        CU(cudaEventRecord(prof[10], h->stC));
+        CU(cudaEventRecord(prof[11], stC));
+        CU(cudaEventRecord(prof[10], stC));
     }
 
     // ---- stage D: K5 ----
-    CU(cudaStreamWaitEvent(h->stD, sl.ev_C, 0));
-    CU(cudaStreamWaitEvent(h->stD, sl.ev_O, 0));        // the fetch read sl.pred_sym / sl.sym_count
-    CU(cudaStreamWaitEvent(h->stD, sl.ev_E, 0));        // ... and so did K6 of the slot's previous block
+    EV_WAIT(stD, sl.ev_C);
+    EV_WAIT(stD, sl.ev_O);        // the fetch read sl.pred_sym / sl.sym_count
+    EV_WAIT(stD, sl.ev_E);        // ... and so did K6 of the slot's previous block
     {
         fm::K5Params p{};
         std::memcpy(p.ted_b, h->taps.ted_b, 8); std::memcpy(p.ted_a, h->taps.ted_a, 8);
@@ -601,19 +619,70 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         p.ted_Kp = 0.3f; p.pll_Kp = 0.3f;
         p.agc_target = 0.5f; p.agc_beta = 0.2f;
         p.n = h->n64; p.n_tiles_k4 = h->k4_tiles; p.n_streams = h->S; p.keep = keep; p.literal = h->k5_literal ? 1 : 0;
-        if (prof) CU(cudaEventRecord(prof[7], h->stD));
-        CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, h->stD));
+        if (prof) CU(cudaEventRecord(prof[7], stD));
+        CU(fm::launch_k5(sl.rds, sl.rds_pw_partial, h->bpsk_state, sl.pred_sym, sl.sym_count, h->dbg.k5, p, stD));
     }
-    if (prof) CU(cudaEventRecord(prof[8], h->stD));
-    CU(cudaEventRecord(sl.ev_D, h->stD));
+    if (prof) CU(cudaEventRecord(prof[8], stD));
+    EV_REC(sl.ev_D, stD);
     // ---- stage E: K6 RDS bit path (symbols -> groups -> PI/PS/RT), per-stream state on the device.  Its own
     //      stream, so that K6 of block k overlaps K5 of block k+1 (both are latency-bound one-warp CTAs) ----
-    CU(cudaStreamWaitEvent(h->stE, sl.ev_D, 0));
+    EV_WAIT(stE, sl.ev_D);
     static const bool no_k6 = std::getenv("FMGPU_NO_K6") != nullptr;      // measurement aid
-    if (!no_k6) CU(fm::launch_k6(sl.pred_sym, sl.sym_count, h->rds_state, h->rds_tables, h->rds_glog, h->rds_blog, h->n64, h->rds_gcap, h->rds_bcap, h->S, h->stE));
-    if (prof) CU(cudaEventRecord(prof[9], h->stE));
-    CU(cudaEventRecord(sl.ev_E, h->stE));
-    h->launches += 7;
+    if (!no_k6) CU(fm::launch_k6(sl.pred_sym, sl.sym_count, h->rds_state, h->rds_tables, h->rds_glog, h->rds_blog, h->n64, h->rds_gcap, h->rds_bcap, h->S, stE));
+    if (prof) CU(cudaEventRecord(prof[9], stE));
+    EV_REC(sl.ev_E, stE);
+#undef EV_WAIT
+#undef EV_REC
+    return slot;
+}
+
+// One block: the multi-stream pipeline, or -- for small launch-bound blocks (h->use_graph) -- the same kernels replayed
+// as one CUDA graph per (ring slot, history parity) on a single stream: ~10 API calls instead of ~60 per block.  A graph
+// is re-captured when its input pointer, input kind or anything baked into the kernel parameters (controls, taps,
+// options: h->graph_gen) has changed.
+int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cudaEvent_t* prof = nullptr) {
+    // K1's FIR history is kept as bytes by the u8 kernels (exact) and as floats by the cf32 kernel; the u8 kernels also
+    // write the float copy, so cf32 may follow u8, but arbitrary floats cannot become bytes again
+    if (u8 && h->last_input_kind == 2)
+        return fail(FMGPU_ERR_STATE, "enqueue: a u8 block cannot follow a cf32 block on the same handle (the FIR history would be truncated to bytes)");
+    h->last_input_kind = u8 ? 1 : 2;
+    update_filters(h);
+    if (u8 && h->use_k1t) { const int rc = ensure_k1t_tables(h); if (rc != FMGPU_OK) return rc; }
+    if (h->ctl_pcm_rate > 0) { const int rc = prepare_pcm(h); if (rc != FMGPU_OK) return rc; }
+    const int slot = (int)(h->step % (unsigned long long)h->depth);
+    const bool graph = h->use_graph && !prof && h->step > 0;
+    if (graph != h->last_was_graph) {                   // cross-block state is ordered by stream order within one mode only
+        if (sync_all(h) != FMGPU_OK) return FMGPU_ERR_CUDA;
+        h->last_was_graph = graph;
+    }
+    int n_launch = 7 + (h->ctl_pcm_rate > 0 ? 1 : 0) + (h->cfg.keep_intermediates ? 2 : 0);
+    if (!graph) {
+        const int rc = enqueue_chain_on(h, iq_dev, u8, wait_H, prof, nullptr);
+        if (rc < 0) return rc;
+    } else {
+        Slot& sl = h->slots[slot];
+        GraphEntry& ge = h->graphs[(size_t)slot * 2 + (size_t)(h->step & 1ull)];
+        if (!ge.exec || ge.in_ptr != iq_dev || ge.u8 != u8 || ge.gen != h->graph_gen) {
+            if (ge.exec) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(h->stG, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_chain_on(h, iq_dev, u8, false, nullptr, h->stG);
+            const cudaError_t ec = cudaStreamEndCapture(h->stG, &g);
+            if (rc < 0) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ec != cudaSuccess) return fail(FMGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ec));
+            const cudaError_t ei = cudaGraphInstantiate(&ge.exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ei != cudaSuccess) { ge.exec = nullptr; return fail(FMGPU_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+            ge.in_ptr = iq_dev; ge.u8 = u8; ge.gen = h->graph_gen;
+        }
+        // previous users of the slot's buffers (the fetch of its previous block), and this block's input
+        CU(cudaStreamWaitEvent(h->stG, sl.ev_O, 0));
+        if (wait_H) CU(cudaStreamWaitEvent(h->stG, sl.ev_H, 0));
+        CU(cudaGraphLaunch(ge.exec, h->stG));
+        cudaEvent_t evs[7] = { sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_P, sl.ev_K1 };
+        for (auto ev : evs) CU(cudaEventRecord(ev, h->stG));
+    }
+    h->launches += n_launch;
     h->step++;
     h->dbg_valid = false;
     return slot;
@@ -656,6 +725,7 @@ int sync_all(fmgpu_demod* h) {
     CU(cudaStreamSynchronize(h->stD));
     CU(cudaStreamSynchronize(h->stE));
     CU(cudaStreamSynchronize(h->stO));
+    if (h->stG) CU(cudaStreamSynchronize(h->stG));
     return FMGPU_OK;
 }
 
@@ -900,7 +970,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-    cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[10] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO, h->stG };
     for (auto st : sts) CU(cudaStreamWaitEvent(st, ev, 0));
     CU(cudaEventDestroy(ev));
     return FMGPU_OK;
@@ -909,7 +979,7 @@ int fmgpu_wait_external_stream(fmgpu_demod* h, void* cuda_stream) {
 int fmgpu_signal_external_stream(fmgpu_demod* h, void* cuda_stream) {
     if (!h) return fail(FMGPU_ERR_ARG, "null handle");
     CU(cudaSetDevice(h->device));
-    cudaStream_t sts[9] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO };
+    cudaStream_t sts[10] = { h->stH, h->stA, h->stA2, h->stP, h->stB, h->stC, h->stD, h->stE, h->stO, h->stG };
     for (auto st : sts) {
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1038,6 +1108,7 @@ int fmgpu_set_control(fmgpu_demod* h, fmgpu_control which, double value) {
         h->ctl_pcm_rate = (int)value; break;
     default: return fail(FMGPU_ERR_ARG, "set_control: unknown id");
     }
+    h->graph_gen++;
     return FMGPU_OK;
 }
 
@@ -1069,6 +1140,7 @@ int fmgpu_upload_taps(fmgpu_demod* h, fmgpu_filter which, const float* b, const 
     update_filters(h);          // settle pending redesigns first so the upload is not overwritten
     std::memcpy(hb, b, sizeof(float) * n);
     if (ha) std::memcpy(ha, a, sizeof(float) * n);
+    h->graph_gen++;
     return FMGPU_OK;
 }
 
@@ -1101,7 +1173,8 @@ long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
 //   "k1_fp32"     1: the u8 FIR + discriminator on the FP32 FMA pipe (k1_fir4_discrim_u8) instead of the tensor cores
 //   "k5_literal"  1: the BPSK synchroniser's per-sample loop instead of the symbol-wise loop (identical bits)
 //   "k3_exact"    1: the pilot PLL's exact body only, without the fast pass (k3_pll.cu)
-//   "k4_v1"       1: the mixdown + FIR kernel's first FIR-role split (one warp nearly idle) instead of the balanced one (same bits)
+//   "graph"       1 / 0: force the CUDA-graph replay of the per-block chain on / off (default: on for small launch-bound blocks)
+//   "k4_v1"       1: the mixdown + FIR kernel reads its FIR taps from shared memory (first version) instead of the constant bank
 int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
     if (!h || !name) return fail(FMGPU_ERR_ARG, "set_option: null argument");
     const std::string n = name;
@@ -1111,7 +1184,9 @@ int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
     } else if (n == "k5_literal") h->k5_literal = value != 0;
     else if (n == "k3_exact") h->k3_exact = value != 0;
     else if (n == "k4_v1") h->k4_v1 = value != 0;
+    else if (n == "graph") h->use_graph = value != 0;
     else return fail(FMGPU_ERR_ARG, "set_option: unknown option");
+    h->graph_gen++;
     return FMGPU_OK;
 }
 

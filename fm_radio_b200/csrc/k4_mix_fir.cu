@@ -33,7 +33,6 @@
 // signals is carried (not recomputed) because the reference's FIR history holds samples mixed with
 // the previous block's phase offset.
 #include "fm_common.cuh"
-#include <algorithm>
 #include <atomic>
 
 namespace fm {
@@ -45,7 +44,7 @@ constexpr int K4_SPARSE_MAX = 32;                             // >= ceil(256 / 1
 constexpr int K4_SMEM_BYTES = (5 * K4_PLEN + 3 * K4_NN) * (int)sizeof(float2);
 // epilogue arrays, aliased onto the sample planes once every FIR has finished
 constexpr int K4_RES_LPR = 0, K4_RES_LMR = K4_TS / 4, K4_RES_SPARSE = 2 * (K4_TS / 4), K4_RES_EST = K4_RES_SPARSE + K4_SPARSE_MAX,
-              K4_RES_RRE = K4_RES_EST + K4_THREADS, K4_RES_RIM = K4_RES_RRE + K4_TS / 8, K4_RES_END = K4_RES_RIM + K4_TS / 8;
+              K4_RES_END = K4_RES_EST + K4_THREADS;
 static_assert(K4_RES_END <= 5 * K4_PLEN, "epilogue arrays must fit in the planes");
 
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
@@ -77,8 +76,8 @@ __device__ __forceinline__ float2 chebyshev_sine2(float2 x) {
 // unrolled version stalled on instruction fetch, ncu no_instruction 1.5).  Step pq's new quad, pq + 8,
 // goes into the slot of quad pq right after its last use.  taps2[k] = (b[k], b[k]).  Sum order: taps
 // ascending, as the scalar reference.
-template <int M, int R>
-__device__ __forceinline__ void fir128(const float2* __restrict__ sig, const float2* __restrict__ taps2, int s0, float2 (&acc)[R])
+template <int M, int R, bool CTAPS>
+__device__ __forceinline__ void fir128(const float2* __restrict__ sig, const float2* __restrict__ taps2, const float (&ctaps)[K4_NN], int s0, float2 (&acc)[R])
 {
     constexpr int QS = M / 4;
     static_assert(QS * (R - 1) + 1 <= 8, "window must fit the ring");
@@ -95,8 +94,17 @@ __device__ __forceinline__ void fir128(const float2* __restrict__ sig, const flo
 #pragma unroll
         for (int pp = 0; pp < 8; pp++) {
             const int pq = pb + pp;
-            const float4 b01 = *(const float4*)(taps2 + 4 * pq);      // (b0, b0, b1, b1)
-            const float4 b23 = *(const float4*)(taps2 + 4 * pq + 2);
+            // the four taps of this step: CTAPS = straight from the kernel parameters (constant bank, uniform-register
+            // operands: no shared-memory traffic -- the broadcast tap loads were half of this kernel's LDS count and the
+            // shared-memory pipe was as busy as the FMA pipe), else from the duplicated copy in shared memory
+            float4 b01, b23;
+            if (CTAPS) {
+                b01 = make_float4(ctaps[4 * pq], ctaps[4 * pq], ctaps[4 * pq + 1], ctaps[4 * pq + 1]);
+                b23 = make_float4(ctaps[4 * pq + 2], ctaps[4 * pq + 2], ctaps[4 * pq + 3], ctaps[4 * pq + 3]);
+            } else {
+                b01 = *(const float4*)(taps2 + 4 * pq);               // (b0, b0, b1, b1)
+                b23 = *(const float4*)(taps2 + 4 * pq + 2);
+            }
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const float4 x01 = win[(pp + QS * r) & 7][0], x23 = win[(pp + QS * r) & 7][1];
@@ -113,7 +121,7 @@ __device__ __forceinline__ void fir128(const float2* __restrict__ sig, const flo
     }
 }
 
-template <bool BAL>
+template <bool CTAPS>
 __global__ void __launch_bounds__(K4_THREADS, 4)
 k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_dt,
            const float* __restrict__ hist_x_in, const float2* __restrict__ hist_m2_in, const float2* __restrict__ hist_m3_in,
@@ -211,47 +219,46 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         }
     }
 
-    // ---- the FIR roles; results stay in registers until every warp has finished with the planes.  The /4 outputs are
-    //      split 192 + 64 (6 resp. 2 per lane) and the /8 planes one per warp, so that the four warps -- the four SM
-    //      sub-partitions -- carry 768 / 768 / 872 / 768 FFMA2 (p.balanced; the first version's 1024 / 1024 / 1024 / 104
-    //      left one sub-partition idle through the FIR phase: p.balanced = 0, kept for A/B) ----
+    // ---- the FIR roles; results stay in registers until every warp has finished with the planes ----
     const int n_audio = nts >> 2, n_rds = nts >> 3;
     const int gi0 = n0 >> 2;                                    // audio index of the tile's first output within the block
     const int o_first = (10 - gi0 % 10) % 10;                   // first output of the tile the estimator reads
-    float2 acc8[8], acc4[4], sparse = make_float2(0.0f, 0.0f);
+    float2 acc8[8], sparse = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int r = 0; r < 8; r++) acc8[r] = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int r = 0; r < 4; r++) acc4[r] = make_float2(0.0f, 0.0f);
-    constexpr bool bal = BAL;
     if (warp < 2) {
-        // /4 FIR: L+R on the real plane (warp 0), L-R on the imaginary plane of the 38 kHz mixdown (warp 1)
-        const float2* sg = s_sig + (warp == 0 ? 0 : 2 * K4_PLEN);
-        const float2* tp = s_taps + (warp == 0 ? 0 : K4_NN);
-        if (bal) {
-            if (6 * lane < n_audio) { float2 a6[6]; fir128<4, 6>(sg, tp, 24 * lane + 4, a6);
-#pragma unroll
-                for (int r = 0; r < 6; r++) acc8[r] = a6[r]; }
-        } else if (8 * lane < n_audio) fir128<4, 8>(sg, tp, 32 * lane + 4, acc8);
-    } else if (bal || warp == 2) {
-        // /8 FIR of the 57 kHz mixdown: real plane (warp 2), imaginary plane (warp 3; warp 2 as well when not balanced)
+        // /4 FIR: output o = 8*lane + r reads staged samples 4o + 4 + k
+        if (8 * lane < n_audio) {
+            if (warp == 0) fir128<4, 8, CTAPS>(s_sig, s_taps, p.taps_lpr, 32 * lane + 4, acc8);
+            else           fir128<4, 8, CTAPS>(s_sig + 2 * K4_PLEN, s_taps + K4_NN, p.taps_lmr, 32 * lane + 4, acc8);
+        }
+    } else if (warp == 2) {
+        // /8 FIR, real then imaginary plane: output o = 4*lane + r reads staged samples 8o + 8 + k.
+        // This warp owns its outputs completely: RDS samples and their AGC power partial leave from registers.
+        float2 pw = make_float2(0.0f, 0.0f);
         if (4 * lane < n_rds) {
-            fir128<8, 4>(s_sig + (warp == 2 ? 3 : 4) * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, acc4);
-            if (!bal) {
-                float2 im[4];
-                fir128<8, 4>(s_sig + 4 * K4_PLEN, s_taps + 2 * K4_NN, 32 * lane + 8, im);
-#pragma unroll
-                for (int r = 0; r < 4; r++) acc8[r] = im[r];
+            float2 re[4], im[4];
+            fir128<8, 4, CTAPS>(s_sig + 3 * K4_PLEN, s_taps + 2 * K4_NN, p.taps_rds, 32 * lane + 8, re);
+            fir128<8, 4, CTAPS>(s_sig + 4 * K4_PLEN, s_taps + 2 * K4_NN, p.taps_rds, 32 * lane + 8, im);
+            float4* dA4 = (float4*)(rds_out + (size_t)sA * (p.n >> 3) + (n0 >> 3) + 4 * lane);
+            dA4[0] = make_float4(re[0].x, im[0].x, re[1].x, im[1].x);
+            dA4[1] = make_float4(re[2].x, im[2].x, re[3].x, im[3].x);
+            if (hasB) {
+                float4* dB4 = (float4*)(rds_out + (size_t)sB * (p.n >> 3) + (n0 >> 3) + 4 * lane);
+                dB4[0] = make_float4(re[0].y, im[0].y, re[1].y, im[1].y);
+                dB4[1] = make_float4(re[2].y, im[2].y, re[3].y, im[3].y);
             }
+#pragma unroll
+            for (int r = 0; r < 4; r++) pw = __fadd2_rn(pw, __ffma2_rn(re[r], re[r], __fmul2_rn(im[r], im[r])));
         }
-        // the last quarter of the /4 outputs, 192 + 2 lane, + 1: L+R (warp 2) / L-R (warp 3)
-        if (bal && 192 + 2 * lane < n_audio) {
-            float2 a2[2];
-            fir128<4, 2>(s_sig + (warp == 2 ? 0 : 2 * K4_PLEN), s_taps + (warp == 2 ? 0 : K4_NN), 4 * (192 + 2 * lane) + 4, a2);
-            acc8[0] = a2[0]; acc8[1] = a2[1];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { pw.x += __shfl_xor_sync(0xffffffffu, pw.x, off); pw.y += __shfl_xor_sync(0xffffffffu, pw.y, off); }
+        if (lane == 0) {
+            rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
+            if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
         }
-    }
-    if (warp == (bal ? 2 : 3)) {
+    } else {
+        // warp 3 (no FIR role of its own): the 26 sparse outputs, off warp 1's critical path
         // real part of L-R where the estimator looks: output o_first + 10*lane, taps ascending
         const int o = o_first + 10 * lane;
         if (o < n_audio) {
@@ -269,54 +276,13 @@ k4_mix_fir(const float2* __restrict__ fm_out_iq, const float* __restrict__ pll_d
         }
     }
     __syncthreads();                                            // planes and taps are dead from here on
-    // results -> shared memory (aliased onto the dead planes): lpr[256], lmr[256], sparse[32], est[128], rds re[128], rds im[128]
-    if (bal) {
-        if (warp < 2) {
-            float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 6 * lane;
+    if (warp < 2) {
+        float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 8 * lane;
 #pragma unroll
-            for (int q = 0; q < 3; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
-        } else {
-            *(float4*)(s_res + (warp == 2 ? K4_RES_LPR : K4_RES_LMR) + 192 + 2 * lane) = make_float4(acc8[0].x, acc8[0].y, acc8[1].x, acc8[1].y);
-            float2* d = s_res + (warp == 2 ? K4_RES_RRE : K4_RES_RIM) + 4 * lane;
-            *(float4*)(d) = make_float4(acc4[0].x, acc4[0].y, acc4[1].x, acc4[1].y);
-            *(float4*)(d + 2) = make_float4(acc4[2].x, acc4[2].y, acc4[3].x, acc4[3].y);
-            if (warp == 2) s_res[K4_RES_SPARSE + lane] = sparse;
-        }
-    } else {
-        if (warp < 2) {
-            float2* d = s_res + (warp == 0 ? K4_RES_LPR : K4_RES_LMR) + 8 * lane;
-#pragma unroll
-            for (int q = 0; q < 4; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
-        } else if (warp == 2) {
-            float2* d = s_res + K4_RES_RRE + 4 * lane; float2* e = s_res + K4_RES_RIM + 4 * lane;
-            *(float4*)(d) = make_float4(acc4[0].x, acc4[0].y, acc4[1].x, acc4[1].y); *(float4*)(d + 2) = make_float4(acc4[2].x, acc4[2].y, acc4[3].x, acc4[3].y);
-            *(float4*)(e) = make_float4(acc8[0].x, acc8[0].y, acc8[1].x, acc8[1].y); *(float4*)(e + 2) = make_float4(acc8[2].x, acc8[2].y, acc8[3].x, acc8[3].y);
-        } else s_res[K4_RES_SPARSE + lane] = sparse;
+        for (int q = 0; q < 4; q++) *(float4*)(d + 2 * q) = make_float4(acc8[2 * q].x, acc8[2 * q].y, acc8[2 * q + 1].x, acc8[2 * q + 1].y);
     }
+    if (warp == 3) s_res[K4_RES_SPARSE + lane] = sparse;
     __syncthreads();
-    // ---- RDS samples (thread t owns output t) and the AGC power partial of the tile (dsp/agc.h:21-30): lane l of warp 1
-    //      sums outputs 4 l .. 4 l + 3, the lanes are reduced by xor-shuffles ----
-    if (t < n_rds) {
-        const float2 re = s_res[K4_RES_RRE + t], im = s_res[K4_RES_RIM + t];
-        rds_out[(size_t)sA * (p.n >> 3) + (n0 >> 3) + t] = make_float2(re.x, im.x);
-        if (hasB) rds_out[(size_t)sB * (p.n >> 3) + (n0 >> 3) + t] = make_float2(re.y, im.y);
-    }
-    if (warp == 1) {
-        float2 pw = make_float2(0.0f, 0.0f);
-        if (4 * lane < n_rds) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const float2 re = s_res[K4_RES_RRE + 4 * lane + r], im = s_res[K4_RES_RIM + 4 * lane + r];
-                pw = __fadd2_rn(pw, __ffma2_rn(re, re, __fmul2_rn(im, im)));
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { pw.x += __shfl_xor_sync(0xffffffffu, pw.x, off); pw.y += __shfl_xor_sync(0xffffffffu, pw.y, off); }
-        if (lane == 0) {
-            rds_power_partial[(size_t)sA * p.n_tiles + tile] = pw.x;
-            if (hasB) rds_power_partial[(size_t)sB * p.n_tiles + tile] = pw.y;
-        }
-    }
 
     // ---- MixAudio (:549-585) + phase-estimator partial sum (:496-511), 2 outputs per thread ----
     float2 est = make_float2(0.0f, 0.0f);
