@@ -55,6 +55,7 @@ struct Slot {
     float2* pcm_f32 = nullptr;     // [S][pcm_n] audio at the PCM rate (K7; allocated when the stage is switched on)
     short2* pcm_s16 = nullptr;     // [S][pcm_n]
     cudaEvent_t ev_H, ev_A, ev_B, ev_C, ev_D, ev_E, ev_O, ev_P, ev_K1;
+    bool fetched_in_graph = false; // the slot's outputs were copied to the host by the CUDA graph that produced them
 };
 
 struct DebugBufs {                 // keep_intermediates only (single set, not ringed)
@@ -410,6 +411,7 @@ void free_all(fmgpu_demod* h) {
 }
 
 int sync_all(fmgpu_demod* h);
+int fetch_copies(fmgpu_demod* h, int slot, unsigned mask, cudaStream_t st);
 
 // K7's buffers and read-position table, (re)built when FMGPU_CTL_AUDIO_PCM_RATE_HZ changes.
 int prepare_pcm(fmgpu_demod* h) {
@@ -460,8 +462,8 @@ int ensure_k1t_tables(fmgpu_demod* h) {
 // slot's events, blocks overlapping.  single != nullptr: every kernel on that one stream in chain order, no events --
 // the form that is captured into a CUDA graph for small, launch-bound blocks (enqueue_block below).
 int enqueue_chain_on(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cudaEvent_t* prof, cudaStream_t single) {
-    cudaStream_t stA = single ? single : stA, stA2 = single ? single : stA2, stP = single ? single : stP,
-                 stB = single ? single : stB, stC = single ? single : stC, stD = single ? single : stD, stE = single ? single : stE;
+    cudaStream_t stA = single ? single : h->stA, stA2 = single ? single : h->stA2, stP = single ? single : h->stP,
+                 stB = single ? single : h->stB, stC = single ? single : h->stC, stD = single ? single : h->stD, stE = single ? single : h->stE;
 #define EV_WAIT(st, ev) do { if (!single) CU(cudaStreamWaitEvent(st, ev, 0)); } while (0)
 #define EV_REC(ev, st) do { if (!single) CU(cudaEventRecord(ev, st)); } while (0)
     const int slot = (int)(h->step % (unsigned long long)h->depth);
@@ -659,6 +661,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     if (!graph) {
         const int rc = enqueue_chain_on(h, iq_dev, u8, wait_H, prof, nullptr);
         if (rc < 0) return rc;
+        h->slots[slot].fetched_in_graph = false;
     } else {
         Slot& sl = h->slots[slot];
         GraphEntry& ge = h->graphs[(size_t)slot * 2 + (size_t)(h->step & 1ull)];
@@ -666,7 +669,8 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
             if (ge.exec) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; }
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(h->stG, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_chain_on(h, iq_dev, u8, false, nullptr, h->stG);
+            int rc = enqueue_chain_on(h, iq_dev, u8, false, nullptr, h->stG);
+            if (rc >= 0 && fetch_copies(h, slot, h->fetch_mask, h->stG) != FMGPU_OK) rc = FMGPU_ERR_CUDA;   // the fetch rides in the graph
             const cudaError_t ec = cudaStreamEndCapture(h->stG, &g);
             if (rc < 0) { if (g) cudaGraphDestroy(g); return rc; }
             if (ec != cudaSuccess) return fail(FMGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ec));
@@ -681,6 +685,7 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
         CU(cudaGraphLaunch(ge.exec, h->stG));
         cudaEvent_t evs[7] = { sl.ev_A, sl.ev_B, sl.ev_C, sl.ev_D, sl.ev_E, sl.ev_P, sl.ev_K1 };
         for (auto ev : evs) CU(cudaEventRecord(ev, h->stG));
+        sl.fetched_in_graph = true;
     }
     h->launches += n_launch;
     h->step++;
@@ -688,28 +693,43 @@ int enqueue_chain(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, cuda
     return slot;
 }
 
-int fetch_slot(fmgpu_demod* h, int slot) {
+// The device -> host copies of one slot's outputs (what fmgpu_set_fetch_mask selects), on stream st.
+int fetch_copies(fmgpu_demod* h, int slot, unsigned mask, cudaStream_t st) {
     Slot& sl = h->slots[slot];
     HostMirror& m = h->mirrors[slot];
     const size_t S = h->S;
-    const unsigned mask = h->fetch_mask;
-    CU(cudaStreamWaitEvent(h->stO, sl.ev_D, 0));
     if (mask & FMGPU_FETCH_AUDIO_F32)
-        CU(cudaMemcpyAsync(m.audio, sl.audio, S * h->n32 * sizeof(float2), cudaMemcpyDeviceToHost, h->stO));
+        CU(cudaMemcpyAsync(m.audio, sl.audio, S * h->n32 * sizeof(float2), cudaMemcpyDeviceToHost, st));
     if (mask & FMGPU_FETCH_RDS_SYMBOLS) {
         // only the part of each stream's row that can hold symbols: the timing clock runs at <= f_center + f_gain =
         // 3500 Hz (ted_clock.cpp:31-44), i.e. at most n64 * 3500 / 16000 + 1 dumps per block (~152 at lock)
         const size_t cap = std::min<size_t>((size_t)h->n64, (size_t)h->n64 * 7 / 32 + 2);
         CU(cudaMemcpy2DAsync(m.pred_sym, (size_t)h->n64 * sizeof(float), sl.pred_sym, (size_t)h->n64 * sizeof(float),
-                             cap * sizeof(float), S, cudaMemcpyDeviceToHost, h->stO));
+                             cap * sizeof(float), S, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaMemcpyAsync(m.sym_count, sl.sym_count, S * sizeof(int), cudaMemcpyDeviceToHost, h->stO));
+    CU(cudaMemcpyAsync(m.sym_count, sl.sym_count, S * sizeof(int), cudaMemcpyDeviceToHost, st));
     const bool pcm_on = h->pcm_rate_built > 0 && h->ctl_pcm_rate == h->pcm_rate_built;
-    if (pcm_on && (mask & FMGPU_FETCH_PCM_S16)) {
-        CU(cudaStreamWaitEvent(h->stO, sl.ev_P, 0));
-        CU(cudaMemcpyAsync(m.pcm_s16, sl.pcm_s16, S * h->pcm_n * sizeof(short2), cudaMemcpyDeviceToHost, h->stO));
+    if (pcm_on && (mask & FMGPU_FETCH_PCM_S16))
+        CU(cudaMemcpyAsync(m.pcm_s16, sl.pcm_s16, S * h->pcm_n * sizeof(short2), cudaMemcpyDeviceToHost, st));
+    return FMGPU_OK;
+}
+
+int fetch_slot(fmgpu_demod* h, int slot) {
+    Slot& sl = h->slots[slot];
+    const unsigned mask = h->fetch_mask;
+    if (sl.fetched_in_graph) {
+        // the block was replayed as a CUDA graph whose last nodes are these copies (same mask: it is part of graph_gen)
+        sl.fetched_in_graph = false;
+        CU(cudaStreamWaitEvent(h->stO, sl.ev_D, 0));
+        CU(cudaEventRecord(sl.ev_O, h->stO));
+    } else {
+        CU(cudaStreamWaitEvent(h->stO, sl.ev_D, 0));
+        const bool pcm_on = h->pcm_rate_built > 0 && h->ctl_pcm_rate == h->pcm_rate_built;
+        if (pcm_on && (mask & FMGPU_FETCH_PCM_S16)) CU(cudaStreamWaitEvent(h->stO, sl.ev_P, 0));
+        const int rc = fetch_copies(h, slot, mask, h->stO);
+        if (rc != FMGPU_OK) return rc;
+        CU(cudaEventRecord(sl.ev_O, h->stO));
     }
-    CU(cudaEventRecord(sl.ev_O, h->stO));
     h->last_fetched_slot = slot;
     h->last_fetch_mask = mask;
     return FMGPU_OK;
@@ -766,7 +786,8 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
         // FMGPU_PRIME_MODE (measurement aid for the bisection in DESIGN.md section 9): which part of the scratch handle matters
         const char* pm = std::getenv("FMGPU_PRIME_MODE");
         const std::string mode = pm ? pm : "full";
-        if (mode == "gctx" || mode == "gctx_launch") {      // green contexts + stage streams only (+ one kernel on each partition)
+        if (mode == "gctx" || mode == "gctx_launch" || mode == "gctx_alloc" || mode == "gctx_events") {
+            // green contexts + stage streams (+ one kernel on each partition / + device allocations / + events and pinned memory)
             fmgpu_demod tmp{};
             tmp.device = dev;
             int lo = 0, hi = 0;
@@ -780,6 +801,21 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
                         cudaStreamSynchronize(tmp.stD); cudaStreamSynchronize(tmp.stA);
                         cudaFree(st8);
                     }
+                }
+                if (mode == "gctx_alloc") {
+                    std::vector<void*> ps;
+                    for (int i = 0; i < 40; i++) { void* q = nullptr; if (cudaMalloc(&q, 4096 + 4096 * i) == cudaSuccess) { cudaMemset(q, 0, 4096); ps.push_back(q); } }
+                    cudaDeviceSynchronize();
+                    for (void* q : ps) cudaFree(q);
+                }
+                if (mode == "gctx_events") {
+                    std::vector<cudaEvent_t> evs(36);
+                    for (auto& e : evs) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+                    std::vector<void*> hp(12, nullptr);
+                    for (auto& q : hp) cudaMallocHost(&q, 4096);
+                    for (auto& e : evs) { cudaEventRecord(e, tmp.stA); cudaEventDestroy(e); }
+                    cudaStreamSynchronize(tmp.stA);
+                    for (auto& q : hp) if (q) cudaFreeHost(q);
                 }
                 cudaStream_t sts[7] = { tmp.stA, tmp.stA2, tmp.stP, tmp.stB, tmp.stC, tmp.stD, tmp.stE };
                 for (auto st : sts) if (st) cudaStreamDestroy(st);
@@ -887,6 +923,7 @@ int fmgpu_enqueue_cf32_device(fmgpu_demod* h, const float* iq_dev, void* after_s
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ev, (cudaStream_t)after_stream));
         CU(cudaStreamWaitEvent(h->stA, ev, 0));
+        CU(cudaStreamWaitEvent(h->stG, ev, 0));             // the block may be replayed as a graph on stG
         CU(cudaEventDestroy(ev));
     }
     const int rc = enqueue_chain(h, iq_dev, false, false);
@@ -961,6 +998,7 @@ int fmgpu_set_fetch_mask(fmgpu_demod* h, unsigned mask) {
     if (!h) return fail(FMGPU_ERR_ARG, "set_fetch_mask: null handle");
     if (mask & ~(unsigned)FMGPU_FETCH_ALL) return fail(FMGPU_ERR_ARG, "set_fetch_mask: unknown bits");
     h->fetch_mask = mask;
+    h->graph_gen++;
     return FMGPU_OK;
 }
 
