@@ -776,13 +776,14 @@ int fmgpu_create(const fmgpu_config* cfg, fmgpu_demod** out) {
     cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return fail(FMGPU_ERR_CUDA, "fmgpu_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
-    // Measured on this pool (driver 580.159, tools/bisect_bench.py): the FIRST handle whose green contexts are created in
-    // a process runs its FIR partition 6-7 % slower than every later one (0.300 vs 0.281 ms per step at 1024 streams),
-    // for as long as it lives.  Scratch green contexts with streams and a kernel launch do not change that; a complete
-    // handle that is created and destroyed, however small and without processing anything, does.  The cause is not
-    // identified; until it is, the first create of a process on a device builds and drops a minimal handle first (a few ms).
+    // Round 1 measured (driver 580.159, tools/bisect_bench.py) that the FIRST handle whose green contexts are created in a
+    // process ran its FIR partition 6-7 % slower than every later one, and worked around it by building and dropping a
+    // scratch handle first.  Round 2's bisection (FMGPU_PRIME_MODE, profiles/r2_prime_modes.md): the scratch handle need
+    // not be destroyed, green contexts + streams alone give part of the effect -- and with the round-2 kernels (K1 on the
+    // tensor cores) the effect is gone altogether: 0.2469 ms per step without priming, 0.2468 with.  Priming is therefore
+    // OFF by default; FMGPU_PRIME=1 (or an explicit FMGPU_PRIME_MODE) brings the old behaviour back for measurements.
     static std::atomic<bool> primed[64];                    // per device ordinal (zero-initialised)
-    if (!std::getenv("FMGPU_NO_PARTITION") && !std::getenv("FMGPU_NO_PRIME") && dev < 64 && !primed[dev].exchange(true)) {
+    if ((std::getenv("FMGPU_PRIME") || std::getenv("FMGPU_PRIME_MODE")) && !std::getenv("FMGPU_NO_PARTITION") && dev < 64 && !primed[dev].exchange(true)) {
         // FMGPU_PRIME_MODE (measurement aid for the bisection in DESIGN.md section 9): which part of the scratch handle matters
         const char* pm = std::getenv("FMGPU_PRIME_MODE");
         const std::string mode = pm ? pm : "full";
