@@ -36,13 +36,21 @@ FLOP_PER_SAMPLE_CHAIN = 160.0      # SURVEY.md 8(d) headline figure
 BYTES_PER_SAMPLE_FUSED = 2.26      # 2 B u8 in + 0.25 B audio + 0.01 B symbols
 BYTES_PER_SAMPLE_K1 = 3.0          # K1 as built: 2 B u8 in + 4 B fm_demod out per 4 samples
 N_SM, FP32_LANES = 148, 128
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the roofline kernel at the default
-# workload (1024 streams x 65536 samples), from the committed `ncu --set full` capture; the algorithmic figure is
-# 3 B per IQ sample = 201 MB (134 MB of u8 in -- all of it read from DRAM -- and 67 MB of fm_demod out, of which
-# about half stays in the L2 for K2)
-NCU_K1_DRAM_BYTES = (134.8e6 + 35.4e6, "profiles/r1l_ncu_summary.md")
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel at the default workload come from the
+# `ncu --set full` capture of the same command, exported by tools/summarize_ncu.py --traffic-json (a run under a profiler is
+# never timed, so the bench can only read the capture; the file and its source are named in the JSON line)
+NCU_TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+
+
+def ncu_traffic():
+    try:
+        return json.load(open(NCU_TRAFFIC_JSON))
+    except Exception:
+        return {}
+
+
 # algorithmic FLOP per input IQ sample of each kernel (per-stage figures; FMA = 2)
-KERNEL_FLOP_PER_SAMPLE = {"k1_fir4_discrim": 64.0,      # a2 (a1 unpack 2.0 and a3 discriminator 1.0 not counted)
+KERNEL_FLOP_PER_SAMPLE = {"k1_fir4_discrim": 64.0,      # a2 (a1 unpack 2.0 and a3 discriminator 1.0 not counted); on the tensor cores since round 2
                           "k2_mpx": 16.0 + 16.25 + 3.0 + 0.6,   # a4 + a6 + a7 + a8
                           "k3_pll": 7.5,                 # a9
                           "k4_mix_fir": 16.0 + 7.5 + 16.0 + 8.0,   # a10 + a11 + a12 + a13
@@ -321,26 +329,42 @@ def run_cuda_arm(args):
         fp32_peak = N_SM * FP32_LANES * 2 * sm_max * 1e6 / 1e12             # TFLOP/s at max SM clock
         k1_ms = stage_ms["k1_fir4_discrim"]
         k1_flops = FLOP_PER_SAMPLE_K1 * S * B
-        k1_tflops = k1_flops / (k1_ms * 1e-3) / 1e12
+        k1_bytes = BYTES_PER_SAMPLE_K1 * S * B
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = ncu_traffic()
+        default_wl = (S == STREAMS_PER_GPU and B == BLOCK)
+        k1_name = "k1_fir4_discrim_u8" if os.environ.get("FMGPU_K1_FP32") else "k1_toeplitz_i8"
+        k1_on_tensor = not os.environ.get("FMGPU_K1_FP32")
+
+        def bound_of(name):
+            if name in ("k3_pll", "k5_bpsk", "k6_rds"):
+                return "latency (one thread per stream, dependent chain)"
+            if name == "k7_audio_pcm" or (name == "k1_fir4_discrim" and k1_on_tensor):
+                return "hbm"
+            return "fp32"
+        # K1 -- the kernel that touches every input byte -- runs its FIR on the tensor cores (tcgen05 kind::i8, exact), which
+        # takes it off the FP32 roofline: its bound is HBM (2 B in + 1 B out per IQ sample).  achieved = algorithmic bytes
+        # per launch / the launch's duration (CUDA events inside the library, one block at a time); peak = measured copy
+        # bandwidth (MEASURED_PEAKS.json).  The FP32 figures of the FMA-pipe kernels (K2, K4) are in "kernels".
         roof = {
-            "kernel": "k1_fir4_discrim", "bound": "fp32",
-            "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp32_peak,
-            "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no fp32 figure; "
-                           "the chain is FP32-FMA bound, not HBM or tensor bound, SURVEY.md 8d)",
-            "traffic": NCU_K1_DRAM_BYTES[0] if (S == STREAMS_PER_GPU and B == BLOCK) else None,
-            "traffic_source": NCU_K1_DRAM_BYTES[1] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-            "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE_K1 * S * B,
-            "hbm": {"achieved": BYTES_PER_SAMPLE_K1 * S * B / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": BYTES_PER_SAMPLE_K1 * S * B / (k1_ms * 1e-3) / 1e9 / hbm_peak,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
-            "flop_per_launch": k1_flops, "ms_per_launch": k1_ms,
+            "kernel": k1_name, "bound": "hbm" if k1_on_tensor else "fp32",
+            "achieved": (k1_bytes / (k1_ms * 1e-3) / 1e9) if k1_on_tensor else (k1_flops / (k1_ms * 1e-3) / 1e12),
+            "peak": hbm_peak if k1_on_tensor else fp32_peak, "unit": "GB/s" if k1_on_tensor else "TFLOP/s",
+            "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak) if k1_on_tensor else (k1_flops / (k1_ms * 1e-3) / 1e12 / fp32_peak),
+            "peak_source": ("MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth; the kernel is timed alone)" if "hbm_gbs" in peaks else "fallback 6650 GB/s")
+                           if k1_on_tensor else f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz",
+            "traffic": (traffic.get(k1_name, {}).get("dram_bytes") if default_wl else None),
+            "traffic_source": f"{os.path.relpath(NCU_TRAFFIC_JSON, ROOT)} <- {traffic.get('_source')} (ncu --set full of this command, "
+                              "dram__bytes_read.sum + dram__bytes_write.sum per launch; read from the capture, not measured by this run)",
+            "algorithmic_bytes_per_launch": k1_bytes, "flop_per_launch": k1_flops, "ms_per_launch": k1_ms,
+            "sm_partition_note": "the kernel runs on the FIR partition (132 of 148 SMs) of the handle",
+            "fp32_peak": {"value": fp32_peak, "unit": "TFLOP/s",
+                          "source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no fp32 figure; tools/ffma_probe.cu reached 72-73)"},
             "kernels": {name: {"ms": ms, "tflops": KERNEL_FLOP_PER_SAMPLE[name] * S * B / (ms * 1e-3) / 1e12,
                                "frac_fp32": KERNEL_FLOP_PER_SAMPLE[name] * S * B / (ms * 1e-3) / 1e12 / fp32_peak,
                                "gbs": KERNEL_BYTES_PER_SAMPLE[name] * S * B / (ms * 1e-3) / 1e9,
                                "frac_hbm": KERNEL_BYTES_PER_SAMPLE[name] * S * B / (ms * 1e-3) / 1e9 / hbm_peak,
-                               "bound": "latency (one thread per stream, dependent chain)" if name in ("k3_pll", "k5_bpsk", "k6_rds")
-                                        else ("hbm" if name == "k7_audio_pcm" else "fp32")}
+                               "bound": bound_of(name)}
                         for name, ms in stage_ms.items()},
             "chain": {"flop_per_sample": FLOP_PER_SAMPLE_CHAIN,
                       "achieved_tflops": FLOP_PER_SAMPLE_CHAIN * value * 1e6 / world / 1e12,
@@ -439,12 +463,14 @@ def run_wideband_arm(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     with torch.cuda.stream(side):
-        t_w = time.perf_counter()
-        k = 0
-        while (time.perf_counter() - t_w) * 1e3 < args.clock_warmup_ms or k < n_cap + args.warmup:
-            step(k); k += 1
-            if k % 8 == 0:
+        # clock ramp + warm-up: the SAME number of steps on every rank (each step is a collective: a time-based loop would
+        # leave the ranks with different broadcast counts and hang) -- at >= 0.17 ms per step this covers clock_warmup_ms
+        n_ramp = max(n_cap + args.warmup, int(args.clock_warmup_ms / 0.17))
+        for k in range(n_ramp):
+            step(k)
+            if (k + 1) % 8 == 0:
                 rx.demod.sync()
+        k = n_ramp
         barrier()
         sampler.mark()
         launches0 = rx.demod.launch_count + rx.chan.launch_count

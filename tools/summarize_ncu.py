@@ -64,5 +64,27 @@ def main(path):
         print(f"* `{name}`: " + ", ".join(f"{n} {v:.2f}" for v, n in st[:6]))
 
 
+def traffic_json(path, out_path):
+    """Per-kernel DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of an `ncu --set full` capture,
+    for bench.py's roofline.traffic: {kernel: {dram_bytes, duration_us}, "_source": csv path}."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {"_source": path}
+    for r in data:
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("fm::", "").split("<")[0]
+        b = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += float(r[col[key]]) * scale.get(units[col[key]], 1.0)
+        dur = float(r[col["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[col["gpu__time_duration.sum"]], 1.0)
+        out[name] = {"dram_bytes": b, "duration_us": dur}
+    json.dump(out, open(out_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
+        traffic_json(sys.argv[1], sys.argv[3])
+    else:
+        main(sys.argv[1])
