@@ -212,6 +212,7 @@ struct K1TParams {
     const float* theta_in;     // [S] the discriminator's prev_theta carried from the previous block (fm_demod.cpp:41-44)
     float* theta_out;          // [S] ... for the next block (ping-pong with theta_in)
     float2* dbg_fm_in;         // keep_intermediates: [S][n_out] FIR outputs before the discriminator, else null
+    int shape;                 // 0: 4-deep ring, 2 accumulator buffers, 2 CTAs/SM; 1: 2-deep ring, 1 buffer, 3 CTAs/SM
 };
 
 // K1 on the tensor cores (k1_toeplitz_i8.cu)

@@ -95,6 +95,7 @@ struct fmgpu_demod {
     float k1t_taps[64] = { 0 }; bool k1t_ready = false, use_k1t = true;
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
+    int k1t_shape = 0;
     bool k5_literal = false, k3_exact = false, k4_v1 = false;
     // CUDA-graph replay of small blocks (enqueue_chain)
     cudaStream_t stG = nullptr;
@@ -297,6 +298,7 @@ int alloc_all(fmgpu_demod* h) {
     h->k5_literal = std::getenv("FMGPU_K5_LITERAL") != nullptr;
     h->k3_exact = std::getenv("FMGPU_K3_EXACT") != nullptr;
     h->k4_v1 = std::getenv("FMGPU_K4_V1") != nullptr;
+    if (const char* e = std::getenv("FMGPU_K1T_SHAPE")) h->k1t_shape = std::atoi(e);
     {
         int n_sm = 148;
         CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
@@ -503,6 +505,7 @@ int enqueue_chain_on(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, c
             t.discrim_gain = p.discrim_gain;
             t.n_rows = h->B / 64; t.tiles_per_stream = (t.n_rows + 127) / 128; t.n_tiles = t.tiles_per_stream * h->S; t.n_streams = h->S;
             t.theta_in = h->k1t_theta[parity]; t.theta_out = h->k1t_theta[parity ^ 1]; t.dbg_fm_in = p.dbg_fm_in;
+            t.shape = h->k1t_shape;
             CU(fm::launch_k1t((const uint8_t*)iq_dev, h->k1t_hist[parity], h->k1t_hist[parity ^ 1], h->k1_hist[parity ^ 1], sl.fm_demod,
                               t, 2 * h->n_sm_fir, stA));
         } else {

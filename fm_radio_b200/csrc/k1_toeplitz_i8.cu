@@ -56,12 +56,13 @@ constexpr int K1T_NCOL = 32;                         // 16 outputs x (re, im)
 constexpr int K1T_PLANES = 3;
 constexpr int K1T_N = K1T_NCOL * K1T_PLANES;         // 96 accumulator columns
 constexpr int K1T_ABUF = 17 * 1024;                  // 129 rows x 128 B, padded to the 1024-byte swizzle atom
-constexpr int K1T_NS = 4;                            // tile ring: up to 3 tiles (50 KB) of cp.async in flight per CTA
 constexpr int K1T_BCHUNK = K1T_N * 128;              // 12 KB: one 128-byte K chunk of G
 constexpr int K1T_BBYTES = 2 * K1T_BCHUNK;
-constexpr int K1T_TMEM_COLS = 256;                   // 2 accumulator buffers of 128 columns (96 used)
 constexpr float K1T_MAGIC = 12582912.0f;             // 1.5 * 2^23: as_float(0x4B400000 + v) == MAGIC + v for |v| < 2^22
-constexpr int K1T_SMEM = K1T_BBYTES + K1T_NS * K1T_ABUF + 1024;
+// Two shapes of the pipeline (template parameters, measured against each other, launch_k1t picks by p.shape):
+//   NS = 4, NACC = 2, 2 CTAs/SM  four-deep tile ring, two accumulator buffers: the MMAs of tile i overlap the epilogue of i - 1
+//   NS = 2, NACC = 1, 3 CTAs/SM  two-deep ring, one accumulator buffer: no overlap inside a CTA, but 24 instead of 16 warps per SM
+constexpr int k1t_smem(int NS) { return K1T_BBYTES + NS * K1T_ABUF + 1024; }
 
 __device__ __forceinline__ int dp4a_u8s8(uint32_t a_u8x4, int b_s8x4, int c) {
     int d;
@@ -88,7 +89,8 @@ __device__ __forceinline__ float2 k1t_discrim2(float2 d, float gain) {
     return __fmul2_rn(w, make_float2(gain, gain));
 }
 
-__global__ void __launch_bounds__(K1T_THREADS, 2)
+template <int K1T_NS, int NACC>
+__global__ void __launch_bounds__(K1T_THREADS, NACC == 2 ? 2 : 3)
 k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_in, uint8_t* __restrict__ hist_out,
                float2* __restrict__ hist_f32_out, float* __restrict__ fm_demod, const __grid_constant__ K1TParams p)
 {
@@ -106,6 +108,7 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
     const int row = tid & (K1T_ROWS - 1), half = tid >> 7;         // this thread's A row and which 8 of its 16 outputs
     for (int i = tid; i < K1T_BBYTES / 16; i += K1T_THREADS) ((uint4*)sB)[i] = __ldg((const uint4*)p.bimg + i);
     if (tid == 0) { tc::mbar_init(&bar_acc[0], 1); tc::mbar_init(&bar_acc[1], 1); tc::mbar_init_fence(); }
+    constexpr uint32_t K1T_TMEM_COLS = 128 * NACC;       // accumulator buffers of 128 columns (96 used)
     if (warp == 0) tc::tmem_alloc(&s_tmem, K1T_TMEM_COLS);
     int pw[6] = { 0, 0, 0, 0, 0, 0 };
     if (warp == 4) {
@@ -229,7 +232,7 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
     const bool mma_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;                // warp-uniform
     int it = 0;
     for (; cur.tile < p.n_tiles; it++) {
-        const int buf = it & 1, slot = it % K1T_NS;
+        const int buf = NACC == 2 ? (it & 1) : 0, slot = it % K1T_NS;
         tc::cp_async_wait<K1T_NS - 2>();             // all but the newest NS - 2 groups have landed: tile `it` is in place
         tc::fence_async_smem();
         __syncthreads();                             // ... for every thread's copies; everyone has left iteration it - 1
@@ -248,17 +251,25 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
             tc::commit(&bar_acc[buf]);
         }
         pre_epilogue(cur, slot, buf);
-        if (it >= 1) {
-            tc::mbar_wait(&bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));   // tile it - 1: accumulators complete, its bytes dead
+        if (NACC == 2) {
+            if (it >= 1) {
+                tc::mbar_wait(&bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));   // tile it - 1: accumulators complete, its bytes dead
+                tc::fence_after();
+            }
+            stage(pre, (it + K1T_NS - 1) % K1T_NS);  // tile it + NS - 1 into the slot of tile it - 1
+            advance(pre);
+            if (it >= 1) epilogue(prev, buf ^ 1, it & 1);
+        } else {
+            stage(pre, (it + K1T_NS - 1) % K1T_NS);  // into the slot of tile it - 1 (its MMAs were awaited one iteration ago)
+            advance(pre);
+            tc::mbar_wait(&bar_acc[0], (uint32_t)(it & 1));
             tc::fence_after();
+            epilogue(cur, 0, it & 1);
         }
-        stage(pre, (it + K1T_NS - 1) % K1T_NS);      // tile it + 3 into the slot of tile it - 1
-        advance(pre);
-        if (it >= 1) epilogue(prev, buf ^ 1, it & 1);
         prev = cur;
         advance(cur);
     }
-    if (it >= 1) {
+    if (NACC == 2 && it >= 1) {
         tc::mbar_wait(&bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
         tc::fence_after();
         epilogue(prev, (it - 1) & 1, it & 1);
@@ -315,11 +326,18 @@ cudaError_t launch_k1t(const uint8_t* iq, const uint8_t* hist_in, uint8_t* hist_
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(k1_toeplitz_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k1_toeplitz_i8<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1t_smem(4));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k1_toeplitz_i8<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1t_smem(2));
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
-    k1_toeplitz_i8<<<grid, K1T_THREADS, K1T_SMEM, st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
+    if (p.shape == 1) {
+        const int grid3 = std::max(1, std::min(p.n_tiles, n_ctas * 3 / 2));
+        k1_toeplitz_i8<2, 1><<<grid3, K1T_THREADS, k1t_smem(2), st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
+    } else {
+        k1_toeplitz_i8<4, 2><<<grid, K1T_THREADS, k1t_smem(4), st>>>(iq, hist_in, hist_out, hist_f32_out, fm_demod, p);
+    }
     return cudaGetLastError();
 }
 

@@ -128,7 +128,8 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_th[i], S * 4)); CK(cudaMemset(d_th[i], 0, S * 4)); }
         p.theta_in = d_th[0]; p.theta_out = d_th[1];
         p.n_rows = B / 64; p.tiles_per_stream = (p.n_rows + 127) / 128; p.n_tiles = p.tiles_per_stream * S; p.n_streams = S;
-        for (int ctas : { n_sm, 2 * n_sm, 2 * 132 }) {
+        for (int shape : { 0, 1 }) for (int ctas : { 2 * n_sm, 2 * 132 }) {
+            p.shape = shape;
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             for (int i = 0; i < 5; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, ctas, 0));
             const int reps = 40;
@@ -136,7 +137,7 @@ int main(int argc, char** argv) {
             for (int i = 0; i < reps; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, ctas, 0));
             cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-            printf("timing variant %d, %d CTAs: %.4f ms/launch = %.1f GS/s, %.0f GB/s algorithmic (3 B/sample)\n", variant, ctas, ms,
+            printf("timing shape %d, %d (x1.5 for shape 1) CTAs: %.4f ms/launch = %.1f GS/s, %.0f GB/s algorithmic (3 B/sample)\n", variant, ctas, ms,
                    (double)S * B / (ms * 1e-3) / 1e9, 3.0 * S * B / (ms * 1e-3) / 1e9);
         }
     }
