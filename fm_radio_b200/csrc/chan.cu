@@ -35,6 +35,8 @@
 #include <string>
 #include <vector>
 #include "../../include/fmgpu.h"
+#include "tcgen05.cuh"
+#include "fm_common.cuh"
 
 extern "C" int fmgpu_set_last_error_(int code, const char* msg);            // fmgpu.cu
 
@@ -63,53 +65,16 @@ struct ChanMmaParams {
     float w0, w1, w2;           // weights of the digit planes
 };
 
-// ---------------------------------------------------------------- PTX wrappers (sm_100a) ----------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-// bounded spin: a broken pipeline traps (launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    for (uint32_t it = 0; it < (1u << 28); it++) {
-        uint32_t ok;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::i8, int32 accumulate
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
-// (start address >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 >> 4 in [32,46),
-// descriptor version 1 in [46,48), layout type 2 = SWIZZLE_128B in [61,64))
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor, kind::i8: D = s32 (c_format 2, bits [4,6)), A = unsigned 8-bit (0, bits [7,10)),
-// B = signed 8-bit (1, bits [10,13)), both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
-constexpr uint32_t CH_IDESC = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(CH_NG >> 3) << 17) | ((uint32_t)(CH_ROWS >> 4) << 24);
+// ---------------------------------------------------------------- PTX wrappers (sm_100a): tcgen05.cuh ----------
+using tc::smem_u32; using tc::mbar_init; using tc::mbar_wait; using tc::fence_async_smem;
+__device__ __forceinline__ void tc_fence_before() { tc::fence_before(); }
+__device__ __forceinline__ void tc_fence_after() { tc::fence_after(); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) { tc::commit(bar); }
+__device__ __forceinline__ void tc_mma_i8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { tc::mma_i8(d, a, b, idesc, acc); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { tc::tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_wait() { tc::tmem_ld_wait(); }
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) { return tc::smem_desc_sw128(saddr); }
+constexpr uint32_t CH_IDESC = tc::idesc_i8_u8s8(CH_ROWS, CH_NG);
 
 // ---------------------------------------------------------------- tensor-core kernel -------------
 // grid (ctas_per_group, n_groups), 128 threads, persistent over the time tiles of its group; two CTAs per SM
@@ -226,6 +191,162 @@ chan_mma_i8(const __grid_constant__ ChanMmaParams p)
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(CH_TMEM_COLS) : "memory");
+}
+
+// ---------------------------------------------------------------- tensor-core kernel, pipelined ----
+// The kernel above is synchronous: every thread copies its row of a K chunk through registers, the CTA meets at
+// a barrier, one thread issues the MMAs, and the epilogue (32 x sincospif per thread) runs with the tensor pipe
+// idle -- ncu: tensor pipe 4 % active, 61 us per launch for 100 stations x 65536 outputs, top stall
+// long_scoreboard.  This one is the classic three-role pipeline, one CTA of 256 threads per SM:
+//   warps 0-1  PRODUCERS   im2col of the raw capture into a ring of CH2_NSTG K-chunk stages with cp.async (8-byte
+//                          copies: window rows are 2 D = 40 bytes apart, so they are 8- but not 16-byte aligned,
+//                          which also rules out TMA), two chunks in flight ahead of the one being released;
+//   warp  2    MMA ISSUER  one elected lane: 12 tcgen05.mma (4 K steps x 3 digit planes) per chunk into one of TWO
+//                          accumulator buffers in TMEM, tcgen05.commit frees the stage / publishes the tile;
+//   warps 4-7  EPILOGUE    tcgen05.ld of the finished buffer while the next tile's MMAs run; the channel rotation
+//                          exp(-j ph) by the chain's own polynomial sine instead of sincospif.
+// All hand-offs are mbarriers (full / empty per stage, acc_full / acc_empty per accumulator buffer).
+constexpr int CH2_THREADS = 256;
+constexpr int CH2_NSTG = 6;                     // 6 x 16 KB ring + 72 KB of G = 168 KB of shared memory: one CTA per SM
+constexpr int CH2_TMEM_COLS = 512;              // 2 accumulator buffers, 192 of 256 columns used in each
+constexpr int CH2_LAG = 2;                      // chunks of cp.async in flight behind the producers' issue point
+
+__global__ void __launch_bounds__(CH2_THREADS, 1)
+chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;                                              // n_kchunks x 3 x 8 KB, resident
+    uint8_t* sA = sB + (size_t)p.n_kchunks * CH_PLANES * CH_BSUB_BYTES;   // CH2_NSTG x 16 KB ring
+    __shared__ __align__(8) uint64_t bar_full[CH2_NSTG], bar_empty[CH2_NSTG], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_off[CH_PLANES * CH_NG];
+    __shared__ uint4 s_meta[CH_SLOTS];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform
+    const int group = blockIdx.y;
+    {
+        const uint4* src = (const uint4*)(p.bimg + (size_t)group * p.n_kchunks * CH_PLANES * CH_BSUB_BYTES);
+        const int n16 = p.n_kchunks * CH_PLANES * CH_BSUB_BYTES / 16;
+        for (int i = tid; i < n16; i += CH2_THREADS) ((uint4*)sB)[i] = __ldg(src + i);
+    }
+    for (int i = tid; i < CH_PLANES * CH_NG; i += CH2_THREADS) s_off[i] = p.offs[(size_t)group * CH_PLANES * CH_NG + i];
+    if (tid < CH_SLOTS) s_meta[tid] = p.meta[(size_t)group * CH_SLOTS + tid];
+    if (tid == 0) {
+        for (int i = 0; i < CH2_NSTG; i++) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }   // full: one arrival per producer warp
+        for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 4); }  // acc_empty: one arrival per epilogue warp
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc(&s_tmem, CH2_TMEM_COLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int n_my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_chunks = n_my_tiles * p.n_kchunks;
+
+    if (warp < 2) {
+        // ---------------- producers: rows 64 warp + lane, + 32 of every tile ----------------
+        auto arrive_full = [&](int c) {              // this warp's copies of chunk c have landed
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_full[c % CH2_NSTG])) : "memory");
+        };
+        for (int c = 0; c < n_chunks; c++) {
+            const int stage = c % CH2_NSTG, use = c / CH2_NSTG;
+            const int tile = (int)blockIdx.x + (c / p.n_kchunks) * (int)gridDim.x, kc = c % p.n_kchunks;
+            if (use > 0) mbar_wait(&bar_empty[stage], (uint32_t)((use - 1) & 1));
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = 64 * warp + 32 * h + lane;
+                const uint8_t* src = p.iq + (size_t)(tile * CH_ROWS + r) * p.row_bytes + kc * CH_KCHUNK;
+                const uint32_t dst = smem_u32(sA + stage * CH_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + (uint32_t)((((j >> 1) ^ (r & 7)) << 4) + ((j & 1) << 3))), "l"(src + 8 * j));
+            }
+            tc::cp_async_commit();
+            if (c >= CH2_LAG) { tc::cp_async_wait<CH2_LAG>(); arrive_full(c - CH2_LAG); }
+        }
+        for (int c = max(0, n_chunks - CH2_LAG); c < n_chunks; c++) { tc::cp_async_wait<0>(); arrive_full(c); }
+    } else if (warp == 2) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+        for (int t = 0; t < n_my_tiles; t++) {
+            const int buf = t & 1;
+            if (t >= 2) mbar_wait(&bar_acc_empty[buf], (uint32_t)(((t >> 1) - 1) & 1));      // the epilogue has drained this buffer
+            tc_fence_after();
+            for (int kc = 0; kc < p.n_kchunks; kc++) {
+                const int c = t * p.n_kchunks + kc, stage = c % CH2_NSTG;
+                mbar_wait(&bar_full[stage], (uint32_t)((c / CH2_NSTG) & 1));
+                tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t a_base = sA_addr + stage * CH_A_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < CH_KCHUNK / 32; ks++) {
+                        const uint64_t a_desc = smem_desc_sw128(a_base + ks * 32);
+#pragma unroll
+                        for (int j = 0; j < CH_PLANES; j++) {
+                            const uint64_t b_desc = smem_desc_sw128(sB_addr + (kc * CH_PLANES + j) * CH_BSUB_BYTES + ks * 32);
+                            tc_mma_i8(tmem + (uint32_t)(buf * 256 + j * CH_NG), a_desc, b_desc, CH_IDESC, (kc | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&bar_empty[stage]);
+                    if (kc == p.n_kchunks - 1) tc_commit(&bar_acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: TMEM lane = output time, 8 channel slots (16 columns) per step ----------------
+        const int ew = warp - 4, row = ew * 32 + lane;
+        int n_valid = 0;
+        for (int s = 0; s < CH_SLOTS; s++) if (s_meta[s].z != 0xffffffffu) n_valid = s + 1;
+        for (int t = 0; t < n_my_tiles; t++) {
+            const int buf = t & 1;
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            mbar_wait(&bar_acc_full[buf], (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const int i_out = tile * CH_ROWS + row;
+            const uint32_t lane_addr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
+            for (int q = 0; q * 8 < n_valid; q++) {
+                uint32_t a0[16], a1[16], a2[16];
+                tmem_ld16(lane_addr + 0 * CH_NG + q * 16, a0);
+                tmem_ld16(lane_addr + 1 * CH_NG + q * 16, a1);
+                tmem_ld16(lane_addr + 2 * CH_NG + q * 16, a2);
+                tmem_ld_wait();
+                if ((q + 1) * 8 >= n_valid) {                    // last read of this buffer: hand it back before the arithmetic
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_acc_empty[buf])) : "memory");
+                }
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    const int slot = q * 8 + s;
+                    const uint4 m = s_meta[slot];
+                    if (m.z == 0xffffffffu) continue;
+                    const int c0 = 2 * slot, c1 = 2 * slot + 1;
+                    const float r0 = (float)((int)a0[2 * s] - s_off[c0]), r1 = (float)((int)a1[2 * s] - s_off[CH_NG + c0]),
+                                r2 = (float)((int)a2[2 * s] - s_off[2 * CH_NG + c0]);
+                    const float q0 = (float)((int)a0[2 * s + 1] - s_off[c1]), q1 = (float)((int)a1[2 * s + 1] - s_off[CH_NG + c1]),
+                                q2 = (float)((int)a2[2 * s + 1] - s_off[2 * CH_NG + c1]);
+                    const float re = fmaf(r0, p.w0, fmaf(r1, p.w1, r2 * p.w2));
+                    const float im = fmaf(q0, p.w0, fmaf(q1, p.w1, q2 * p.w2));
+                    const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)i_out;            // exact mod 2^32
+                    // exp(-j 2 pi t), t = ph / 2^32 in [-1/2, 1/2): the chain's polynomial sine (dsp/simd/chebyshev_sine.h,
+                    // 1.5e-7 max error) -- sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)
+                    const float tt = (float)(int)ph * 2.3283064365386963e-10f;
+                    const float sn = fm::chebyshev_sine(tt), cs = fm::chebyshev_sine(0.25f - fabsf(tt));
+                    p.out[(size_t)m.z * p.n_out + i_out] = make_float2(fmaf(re, cs, im * sn), fmaf(im, cs, -re * sn));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, CH2_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- FP32 FMA-pipe kernel -----------
@@ -366,6 +487,7 @@ int chan_upload_taps(fmgpu_chan* h) {
 }
 
 size_t chan_mma_smem(const fmgpu_chan* h) { return (size_t)h->n_kchunks * CH_PLANES * CH_BSUB_BYTES + 2 * CH_A_BYTES + 1024; }
+size_t chan_mma2_smem(const fmgpu_chan* h) { return (size_t)h->n_kchunks * CH_PLANES * CH_BSUB_BYTES + CH2_NSTG * CH_A_BYTES + 1024; }
 
 // staged buffer already holds history ++ block; writes slot, then rolls the history
 int chan_run(fmgpu_chan* h, int slot) {
@@ -383,8 +505,14 @@ int chan_run(fmgpu_chan* h, int slot) {
         p.n_tiles = h->n_out / CH_ROWS; p.w0 = h->w0; p.w1 = h->w1; p.w2 = h->w2;
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-        const int per_group = std::max(1, std::min(p.n_tiles, (2 * n_sm) / h->n_groups));
-        chan_mma_i8<<<dim3(per_group, h->n_groups), 128, chan_mma_smem(h), h->st>>>(p);
+        static const bool v1 = std::getenv("FMGPU_CHAN_V1") != nullptr;      // A/B aid: the synchronous first version
+        if (v1 || chan_mma2_smem(h) > 227 * 1024) {           // (long prototypes: G no longer fits beside the stage ring)
+            const int per_group = std::max(1, std::min(p.n_tiles, (2 * n_sm) / h->n_groups));
+            chan_mma_i8<<<dim3(per_group, h->n_groups), 128, chan_mma_smem(h), h->st>>>(p);
+        } else {
+            const int per_group = std::max(1, std::min(p.n_tiles, n_sm / h->n_groups));
+            chan_mma_i8_pipelined<<<dim3(per_group, h->n_groups), CH2_THREADS, chan_mma2_smem(h), h->st>>>(p);
+        }
     } else {
         ChanFp32Params p{};
         p.iq = h->d_stage; p.g = h->d_g; p.meta = h->d_meta32; p.out = h->d_out[slot]; p.n_newest0 = n_newest0;
@@ -482,6 +610,8 @@ int fmgpu_chan_create(const fmgpu_chan_config* cfg, const double* centre_hz, fmg
         A(cudaMalloc((void**)&h->d_offs, (size_t)h->n_groups * CH_PLANES * CH_NG * sizeof(int)));
         A(cudaMalloc((void**)&h->d_meta, (size_t)h->n_groups * CH_SLOTS * sizeof(uint4)));
         A(cudaFuncSetAttribute(chan_mma_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma_smem(h)));
+        if (chan_mma2_smem(h) <= 227 * 1024)
+            A(cudaFuncSetAttribute(chan_mma_i8_pipelined, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma2_smem(h)));
     }
     {
         const size_t smem = (size_t)(CF_TILE * D + NN - D) * sizeof(float2);

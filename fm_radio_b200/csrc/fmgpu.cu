@@ -95,7 +95,7 @@ struct fmgpu_demod {
     float k1t_taps[64] = { 0 }; bool k1t_ready = false, use_k1t = true;
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
-    int k1t_shape = 0;
+    int k1t_shape = 1;             // 3 CTAs/SM (measured 0.0574 vs 0.0627 ms for the 2-CTA shape, tools/k1t_probe.cu)
     bool k5_literal = false, k3_exact = false, k4_v1 = false;
     // CUDA-graph replay of small blocks (enqueue_chain)
     cudaStream_t stG = nullptr;

@@ -137,7 +137,7 @@ int main(int argc, char** argv) {
             for (int i = 0; i < reps; i++) CK(fm::launch_k1t(d_iq + (size_t)(i % NBUF) * S * 2 * B, d_hist[i & 1], d_hist[(i & 1) ^ 1], d_hf, d_out + (size_t)(i % NBUF) * S * (B / 4), p, ctas, 0));
             cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-            printf("timing shape %d, %d (x1.5 for shape 1) CTAs: %.4f ms/launch = %.1f GS/s, %.0f GB/s algorithmic (3 B/sample)\n", variant, ctas, ms,
+            printf("timing shape %d, %d (x1.5 for shape 1) CTAs: %.4f ms/launch = %.1f GS/s, %.0f GB/s algorithmic (3 B/sample)\n", shape, ctas, ms,
                    (double)S * B / (ms * 1e-3) / 1e9, 3.0 * S * B / (ms * 1e-3) / 1e9);
         }
     }
