@@ -201,12 +201,17 @@ chan_mma_i8(const __grid_constant__ ChanMmaParams p)
 //   warps 0-1  PRODUCERS   im2col of the raw capture into a ring of CH2_NSTG K-chunk stages with cp.async (8-byte
 //                          copies: window rows are 2 D = 40 bytes apart, so they are 8- but not 16-byte aligned,
 //                          which also rules out TMA), two chunks in flight ahead of the one being released;
-//   warp  2    MMA ISSUER  one elected lane: 12 tcgen05.mma (4 K steps x 3 digit planes) per chunk into one of TWO
+//   warp  2    MMA ISSUER  one elected lane: 4 tcgen05.mma (K steps; N = 192 = 3 digit planes) per chunk into one of TWO
 //                          accumulator buffers in TMEM, tcgen05.commit frees the stage / publishes the tile;
-//   warps 4-7  EPILOGUE    tcgen05.ld of the finished buffer while the next tile's MMAs run; the channel rotation
-//                          exp(-j ph) by the chain's own polynomial sine instead of sincospif.
+//   warps 4-11 EPILOGUE    two warpgroups taking alternate blocks of 8 channel slots: tcgen05.ld of the finished buffer
+//                          while the next tile's MMAs run; branch-free per-channel arithmetic (8 independent channels in
+//                          flight per thread); the channel rotation exp(-j ph) by the chain's own polynomial sine instead
+//                          of sincospif.  (With one epilogue warp per SM sub-partition and a branch per channel the
+//                          epilogue ran at IPC 0.2 and bounded the kernel: 51 us, ncu.)
+// The three digit planes of G sit side by side in shared memory, so each K step is ONE tcgen05.mma of N = 192 (100 clocks
+// measured, tools/umma_rate.cu) instead of three of N = 64 (3 x 50: small-N MMAs have a ~50-clock floor).
 // All hand-offs are mbarriers (full / empty per stage, acc_full / acc_empty per accumulator buffer).
-constexpr int CH2_THREADS = 256;
+constexpr int CH2_THREADS = 384;
 constexpr int CH2_NSTG = 6;                     // 6 x 16 KB ring + 72 KB of G = 168 KB of shared memory: one CTA per SM
 constexpr int CH2_TMEM_COLS = 512;              // 2 accumulator buffers, 192 of 256 columns used in each
 constexpr int CH2_LAG = 2;                      // chunks of cp.async in flight behind the producers' issue point
@@ -235,7 +240,7 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     if (tid < CH_SLOTS) s_meta[tid] = p.meta[(size_t)group * CH_SLOTS + tid];
     if (tid == 0) {
         for (int i = 0; i < CH2_NSTG; i++) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }   // full: one arrival per producer warp
-        for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 4); }  // acc_empty: one arrival per epilogue warp
+        for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }  // acc_empty: one arrival per epilogue warp
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc(&s_tmem, CH2_TMEM_COLS);
@@ -286,12 +291,10 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
                     const uint32_t a_base = sA_addr + stage * CH_A_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < CH_KCHUNK / 32; ks++) {
+                        // the chunk's three plane sub-tiles are contiguous: one 192-row B operand, plane j in columns 64 j ..
                         const uint64_t a_desc = smem_desc_sw128(a_base + ks * 32);
-#pragma unroll
-                        for (int j = 0; j < CH_PLANES; j++) {
-                            const uint64_t b_desc = smem_desc_sw128(sB_addr + (kc * CH_PLANES + j) * CH_BSUB_BYTES + ks * 32);
-                            tc_mma_i8(tmem + (uint32_t)(buf * 256 + j * CH_NG), a_desc, b_desc, CH_IDESC, (kc | ks) != 0 ? 1u : 0u);
-                        }
+                        const uint64_t b_desc = smem_desc_sw128(sB_addr + kc * CH_PLANES * CH_BSUB_BYTES + ks * 32);
+                        tc_mma_i8(tmem + (uint32_t)(buf * 256), a_desc, b_desc, tc::idesc_i8_u8s8(CH_ROWS, CH_PLANES * CH_NG), (kc | ks) != 0 ? 1u : 0u);
                     }
                     tc_commit(&bar_empty[stage]);
                     if (kc == p.n_kchunks - 1) tc_commit(&bar_acc_full[buf]);
@@ -300,33 +303,36 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
             }
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue: TMEM lane = output time, 8 channel slots (16 columns) per step ----------------
-        const int ew = warp - 4, row = ew * 32 + lane;
+        // ---------------- epilogue: TMEM lane = output time; warpgroup eg takes the blocks q = eg, eg + 2, .. of 8 channel slots ----------------
+        const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2, row = ew * 32 + lane;
         int n_valid = 0;
         for (int s = 0; s < CH_SLOTS; s++) if (s_meta[s].z != 0xffffffffu) n_valid = s + 1;
+        const int n_q = (n_valid + 7) / 8;
+        const int q_last = (n_q - 1 - eg >= 0) ? eg + 2 * ((n_q - 1 - eg) / 2) : -1;     // this warpgroup's last block (-1: none)
+        auto release = [&](int buf) {                    // this warp has finished reading accumulator buffer buf
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_acc_empty[buf])) : "memory");
+        };
         for (int t = 0; t < n_my_tiles; t++) {
             const int buf = t & 1;
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
             mbar_wait(&bar_acc_full[buf], (uint32_t)((t >> 1) & 1));
             tc_fence_after();
+            if (q_last < 0) release(buf);
             const int i_out = tile * CH_ROWS + row;
             const uint32_t lane_addr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
-            for (int q = 0; q * 8 < n_valid; q++) {
+            for (int q = eg; q < n_q; q += 2) {
                 uint32_t a0[16], a1[16], a2[16];
                 tmem_ld16(lane_addr + 0 * CH_NG + q * 16, a0);
                 tmem_ld16(lane_addr + 1 * CH_NG + q * 16, a1);
                 tmem_ld16(lane_addr + 2 * CH_NG + q * 16, a2);
                 tmem_ld_wait();
-                if ((q + 1) * 8 >= n_valid) {                    // last read of this buffer: hand it back before the arithmetic
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_acc_empty[buf])) : "memory");
-                }
+                if (q == q_last) release(buf);               // hand the buffer back before the arithmetic
 #pragma unroll
-                for (int s = 0; s < 8; s++) {
+                for (int s = 0; s < 8; s++) {                // branch-free: 8 independent channels; an empty slot only skips its store
                     const int slot = q * 8 + s;
                     const uint4 m = s_meta[slot];
-                    if (m.z == 0xffffffffu) continue;
                     const int c0 = 2 * slot, c1 = 2 * slot + 1;
                     const float r0 = (float)((int)a0[2 * s] - s_off[c0]), r1 = (float)((int)a1[2 * s] - s_off[CH_NG + c0]),
                                 r2 = (float)((int)a2[2 * s] - s_off[2 * CH_NG + c0]);
@@ -339,7 +345,7 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
                     // 1.5e-7 max error) -- sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)
                     const float tt = (float)(int)ph * 2.3283064365386963e-10f;
                     const float sn = fm::chebyshev_sine(tt), cs = fm::chebyshev_sine(0.25f - fabsf(tt));
-                    p.out[(size_t)m.z * p.n_out + i_out] = make_float2(fmaf(re, cs, im * sn), fmaf(im, cs, -re * sn));
+                    if (m.z != 0xffffffffu) p.out[(size_t)m.z * p.n_out + i_out] = make_float2(fmaf(re, cs, im * sn), fmaf(im, cs, -re * sn));
                 }
             }
         }
