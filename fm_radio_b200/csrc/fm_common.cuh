@@ -59,8 +59,7 @@ __device__ __forceinline__ float chebyshev_sine(float x) {
 __device__ __forceinline__ float fm_atan2f(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    float q = __fdividef(mn, mx);
-    q = (mx == 0.0f) ? 0.0f : q;                         // atan2(0, 0) = 0 as the reference's libm
+    const float q = __fdividef(mn, fmaxf(mx, 1e-30f));    // atan2(0, 0) = 0 as the reference's libm (0 / 1e-30, no select)
     const float s = q * q;
     float p = -0.004054562299f;
     p = fmaf(p, s, 0.021862939178f);
@@ -81,9 +80,7 @@ __device__ __forceinline__ float fm_atan2f(float y, float x) {
 __device__ __forceinline__ float2 fm_atan2f_x2(float y0, float x0, float y1, float x1) {
     const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
     const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
-    float2 q = make_float2(__fdividef(mn0, mx0), __fdividef(mn1, mx1));
-    q.x = (mx0 == 0.0f) ? 0.0f : q.x;
-    q.y = (mx1 == 0.0f) ? 0.0f : q.y;
+    const float2 q = make_float2(__fdividef(mn0, fmaxf(mx0, 1e-30f)), __fdividef(mn1, fmaxf(mx1, 1e-30f)));
     const float2 s = __fmul2_rn(q, q);
     float2 p = make_float2(-0.004054562299f, -0.004054562299f);
     p = __ffma2_rn(p, s, make_float2(0.021862939178f, 0.021862939178f));
@@ -94,10 +91,12 @@ __device__ __forceinline__ float2 fm_atan2f_x2(float y0, float x0, float y1, flo
     p = __ffma2_rn(p, s, make_float2(-0.333298607622f, -0.333298607622f));
     p = __ffma2_rn(p, s, make_float2(0.999999335572f, 0.999999335572f));
     float2 r = __fmul2_rn(p, q);
-    r.x = (ay0 > ax0) ? (0.5f * PI_F - r.x) : r.x;
-    r.y = (ay1 > ax1) ? (0.5f * PI_F - r.y) : r.y;
-    r.x = (x0 < 0.0f) ? (PI_F - r.x) : r.x;
-    r.y = (x1 < 0.0f) ? (PI_F - r.y) : r.y;
+    const float2 ra = __fadd2_rn(make_float2(0.5f * PI_F, 0.5f * PI_F), make_float2(-r.x, -r.y));     // pi/2 - r, both halves at once
+    r.x = (ay0 > ax0) ? ra.x : r.x;
+    r.y = (ay1 > ax1) ? ra.y : r.y;
+    const float2 rb = __fadd2_rn(make_float2(PI_F, PI_F), make_float2(-r.x, -r.y));                  // pi - r
+    r.x = (x0 < 0.0f) ? rb.x : r.x;
+    r.y = (x1 < 0.0f) ? rb.y : r.y;
     return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
 }
 

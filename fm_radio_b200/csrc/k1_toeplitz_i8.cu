@@ -80,12 +80,14 @@ __device__ __forceinline__ float2 k1t_combine(uint32_t r0, uint32_t i0, uint32_t
     return __ffma2_rn(f0, W[0], __ffma2_rn(f1, W[1], __fmul2_rn(f2, W[2])));
 }
 
-// fm_demod.cpp:6-10 and :36-44 for two outputs: wrap(theta - prev) * gain, the wrap as two selects per half
+// fm_demod.cpp:6-10 and :36-44 for two outputs: wrap(theta - prev) * gain.  The difference of two angles lies in (-2 pi, 2 pi), so
+// the reference's two compares (x >= pi -> x - 2 pi, x <= -pi -> x + 2 pi) are x - 2 pi * rint(x / 2 pi): four packed
+// instructions per pair instead of eleven scalar ones.  Same value (one rounding of x -+ 2 pi) whenever both take the same
+// branch; they can differ only for |x| within an ulp of pi -- a phase step of half a turn per sample, i.e. noise, never FM.
 __device__ __forceinline__ float2 k1t_discrim2(float2 d, float gain) {
-    const float2 lo = __fadd2_rn(d, make_float2(-2.0f * PI_F, -2.0f * PI_F)), hi = __fadd2_rn(d, make_float2(2.0f * PI_F, 2.0f * PI_F));
-    float2 w;
-    w.x = (d.x >= PI_F) ? lo.x : ((d.x <= -PI_F) ? hi.x : d.x);
-    w.y = (d.y >= PI_F) ? lo.y : ((d.y <= -PI_F) ? hi.y : d.y);
+    const float2 big = make_float2(12582912.0f, 12582912.0f);
+    const float2 k = __fadd2_rn(__ffma2_rn(d, make_float2(INV_TWO_PI_F, INV_TWO_PI_F), big), make_float2(-12582912.0f, -12582912.0f));
+    const float2 w = __ffma2_rn(k, make_float2(-TWO_PI_F, -TWO_PI_F), d);
     return __fmul2_rn(w, make_float2(gain, gain));
 }
 
