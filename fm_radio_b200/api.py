@@ -137,6 +137,7 @@ EXPORTED_SYMBOLS = [
     "fmgpu_rds_get_bytes", "fmgpu_rds_get_db", "fmgpu_last_error", "fmgpu_version",
     "fmgpu_rds_device_fetch", "fmgpu_rds_device_counts", "fmgpu_rds_device_get_groups",
     "fmgpu_rds_device_get_bytes", "fmgpu_rds_device_get_db", "fmgpu_get_partition",
+    "fmgpu_rds_get_db_ext", "fmgpu_rds_device_get_db_ext",
     "fmgpu_enqueue_cf32_device", "fmgpu_stream_wait_input_free",
     "fmgpu_chan_create", "fmgpu_chan_destroy", "fmgpu_chan_get_b", "fmgpu_chan_get_config", "fmgpu_chan_get_freqs",
     "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
@@ -148,6 +149,22 @@ EXPORTED_SYMBOLS = [
 ]
 
 _lib = None
+
+
+class RdsDbExt(C.Structure):
+    """fmgpu_rds_db_ext (include/fmgpu.h): RDS_Database beyond PI / PTY / PS / RT (rds_database.h:26-53)."""
+    _fields_ = [("programme_type_name", C.c_char * 8), ("year", C.c_int32), ("day", C.c_uint8), ("month", C.c_uint8),
+                ("hour", C.c_uint8), ("minute", C.c_uint8), ("local_time_offset", C.c_int8),
+                ("traffic_announcement", C.c_uint8), ("is_stereo", C.c_uint8), ("is_music", C.c_uint8),
+                ("is_artificial_head", C.c_uint8), ("is_compressed", C.c_uint8), ("is_dynamic_program_type", C.c_uint8),
+                ("ptyn_ab_flag", C.c_uint8)]
+
+    TRAFFIC = ("NONE", "EON_INFO", "AWAIT_EON_ANNOUNCE", "NOW_EON_ANNOUNCE")    # rds_database.h:19-24
+
+    def as_dict(self) -> dict:
+        d = {name: getattr(self, name) for name, _ in self._fields_ if name not in ("programme_type_name", "ptyn_ab_flag")}
+        d["programme_type_name"] = bytes(bytearray(self)[:8])
+        return d
 
 
 def lib():
@@ -221,6 +238,9 @@ def lib():
     L.fmgpu_rds_get_bytes.argtypes = [vp, vp, ci]
     L.fmgpu_rds_get_db.argtypes = [vp, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
     L.fmgpu_rds_get_db.restype = None
+    L.fmgpu_rds_get_db_ext.argtypes = [vp, vp]
+    L.fmgpu_rds_get_db_ext.restype = None
+    L.fmgpu_rds_device_get_db_ext.argtypes = [vp, ci, vp]
     L.fmgpu_get_partition.argtypes = [vp, C.POINTER(ci * 2)]
     L.fmgpu_set_option.argtypes = [vp, C.c_char_p, ci]
     L.fmgpu_set_fetch_mask.argtypes = [vp, C.c_uint]
@@ -485,6 +505,12 @@ class FMDemod:
         _check(self.L.fmgpu_rds_device_get_db(self.h, stream, C.byref(pi), ps, rt, C.byref(pty)), "fmgpu_rds_device_get_db")
         return {"pi": pi.value, "pty": pty.value, "ps": ps.raw, "rt": rt.raw}
 
+    def rds_db_ext(self, stream: int = 0) -> dict:
+        """The rest of RDS_Database (rds_database.h:26-53): TA/TP, M/S, DI flags, clock, programme type name."""
+        e = RdsDbExt()
+        _check(self.L.fmgpu_rds_device_get_db_ext(self.h, stream, C.byref(e)), "fmgpu_rds_device_get_db_ext")
+        return e.as_dict()
+
 
 class Channelizer:
     """Wideband channelizer (include/fmgpu.h, fmgpu_chan_*): one u8 IQ capture at `fs_in_hz` ->
@@ -602,6 +628,11 @@ class RDSDecoder:
         ps, rt = C.create_string_buffer(8), C.create_string_buffer(64)
         self.L.fmgpu_rds_get_db(self.h, C.byref(pi), ps, rt, C.byref(pty))
         return {"pi": pi.value, "pty": pty.value, "ps": ps.raw, "rt": rt.raw}
+
+    def db_ext(self) -> dict:
+        e = RdsDbExt()
+        self.L.fmgpu_rds_get_db_ext(self.h, C.byref(e))
+        return e.as_dict()
 
 
 class PolyphaseDownsampler:

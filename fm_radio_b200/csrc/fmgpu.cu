@@ -1300,6 +1300,14 @@ int fmgpu_rds_device_get_db(fmgpu_demod* h, int stream, uint16_t* pi, char ps8[8
     return FMGPU_OK;
 }
 
+int fmgpu_rds_device_get_db_ext(fmgpu_demod* h, int stream, fmgpu_rds_db_ext* out) {
+    const rds::State* st = rds_fetched(h, stream);
+    if (!st) return FMGPU_ERR_STATE;
+    if (!out) return fail(FMGPU_ERR_ARG, "rds_device_get_db_ext: null out");
+    *out = st->ext;
+    return FMGPU_OK;
+}
+
 // ---- stand-alone polyphase decimator (dsp/polyphase_filter.h:9-87) ----
 struct fmgpu_polyphase {
     int M, K, NN, is_complex;

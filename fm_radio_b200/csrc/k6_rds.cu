@@ -7,7 +7,7 @@
 // realtime that loop would have to take 19 M symbols/s off the device.  The integer program is the
 // one of rds_core.h, shared with the host decoder, so device and host results are bit-identical.
 //
-// Per stream the kernel keeps rds::State (144 bytes) and two rings in HBM: the last `gcap` groups
+// Per stream the kernel keeps rds::State (168 bytes) and two rings in HBM: the last `gcap` groups
 // and the last `bcap` packet bytes, indexed by the running totals, so the host can collect results
 // every block or every few blocks (fmgpu_rds_device_fetch).  ~150 symbols per 65536-sample block:
 // the kernel is a few microseconds on stage stream D behind K5.

@@ -6,8 +6,9 @@
 //   DifferentialManchesterDecoder::Process/PushBit  rds_decoder/differential_manchester_decoder.h:25-59
 //   RDS_Group_Sync (FindingSync / ReadingGroup)     rds_decoder/rds_group_sync.cpp:29-237
 //   CalculateCRC10 / single-bit error patterns      rds_decoder/crc10.cpp:9-60, rds_constants.h:15-28
-//   RDS_Decoder::ProcessGroup, groups 0A and 2A     rds_decoder/rds_decoder.cpp:82-126, 167-245, 301-340
-//   RDS_Database_Decoder_Handler                    rds_decoder/rds_database_decoder_handler.cpp:15-50
+//   RDS_Decoder::ProcessGroup, groups 0A 2A 4A 10A  rds_decoder/rds_decoder.cpp:82-126, 159-245, 301-340, 363-441
+//   RDS_Database_Decoder_Handler                    rds_decoder/rds_database_decoder_handler.cpp:15-138
+//   mjd_to_ymd                                      rds_decoder/modified_julian_date.h:8-24
 #pragma once
 #include <stdint.h>
 #include "../../include/fmgpu.h"
@@ -83,12 +84,14 @@ struct State {
     char ps[8];
     char rt[64];
     unsigned long long n_groups, n_bytes;      // totals since creation
+    fmgpu_rds_db_ext ext;              // flags, TA, PTYN, clock: written a few times a second
 };
 
 // The same state while a decoder runs: scalars only (no indexed arrays), so that on the device it
 // lives in registers -- with the stored layout used directly the whole struct went to local memory
 // and the kernel took 0.08 ms alone / 0.18 ms next to K3 (measured).  The RadioText buffer, touched
-// once per 2A group, stays in memory behind `rt`.
+// once per 2A group, and the rest of the database (0A flags, 4A clock, 10A name) stay in memory
+// behind `rt` / `ext`.
 struct Work {
     uint32_t pk0, pk1, pk2, pk3, shift;
     uint32_t byte_index, bit_index, take, prev_level, locked, rt_ab, block_slot, block_errors, bits_in_block, bad_groups, pty, pi;
@@ -97,12 +100,14 @@ struct Work {
     unsigned long long ps;             // ps[i] at bits 8 i
     unsigned long long n_groups, n_bytes;
     char* rt;
+    fmgpu_rds_db_ext* ext;
 };
 
 RDS_HD void init(State& s) {
     unsigned char* p = (unsigned char*)&s;
     for (unsigned i = 0; i < sizeof(State); i++) p[i] = 0;
     s.rt_ab = 0b100;                                             // "unknown" A/B flag: first 2A group clears the text
+    s.ext.ptyn_ab_flag = 0b100;                                  // same for the programme type name (handler.h:12)
 }
 
 RDS_HD void load(Work& w, State& s) {
@@ -119,6 +124,7 @@ RDS_HD void load(Work& w, State& s) {
     for (int i = 0; i < 8; i++) w.ps |= (unsigned long long)(unsigned char)s.ps[i] << (8 * i);
     w.n_groups = s.n_groups; w.n_bytes = s.n_bytes;
     w.rt = s.rt;
+    w.ext = &s.ext;
 }
 
 RDS_HD void group_of(const Work& w, fmgpu_rds_group& g) {
@@ -184,6 +190,14 @@ RDS_HD void update_database(Work& w) {
     const bool has_d = v3 && ((w.cur_type >> 24) & 0xFFu) == OFF_D;
     if (code == 0) {
         const int seg = (int)(bw & 3u);
+        fmgpu_rds_db_ext& x = *w.ext;
+        x.is_music = (uint8_t)((bw >> 3) & 1u);
+        x.traffic_announcement = (uint8_t)((((bw >> 10) & 1u) << 1) | ((bw >> 4) & 1u));   // TP:TA, table 8
+        const uint8_t di = (uint8_t)((bw >> 2) & 1u);              // decoder identification bit d(3 - seg), table 9
+        if (seg == 0) x.is_dynamic_program_type = di;
+        else if (seg == 1) x.is_compressed = di;
+        else if (seg == 2) x.is_artificial_head = di;
+        else x.is_stereo = di;
         if (has_d) { w.ps = put_char64(w.ps, 2 * seg, d3 >> 8); w.ps = put_char64(w.ps, 2 * seg + 1, d3 & 0xFFu); }
     } else if (code == 2) {
         const uint32_t ab = (bw >> 4) & 1u;
@@ -192,6 +206,30 @@ RDS_HD void update_database(Work& w) {
         w.rt_ab = ab;
         if (has_c) { put_char(w.rt, 4 * seg, d2 >> 8); put_char(w.rt, 4 * seg + 1, d2 & 0xFFu); }
         if (has_d) { put_char(w.rt, 4 * seg + 2, d3 >> 8); put_char(w.rt, 4 * seg + 3, d3 & 0xFFu); }
+    } else if (code == 4) {
+        fmgpu_rds_db_ext& x = *w.ext;
+        if (has_c) {                                             // OnDate: Modified Julian Day -> calendar date
+            int J = (int)(((bw & 3u) << 15) | (d2 >> 1)) + 2400001 + 68569;
+            const int C = 4 * J / 146097;
+            J = J - (146097 * C + 3) / 4;
+            const int Y = 4000 * (J + 1) / 1461001;
+            J = J - 1461 * Y / 4 + 31;
+            const int M = 80 * J / 2447;
+            x.day = (uint8_t)(J - 2447 * M / 80);
+            J = M / 11;
+            x.month = (uint8_t)(M + 2 - 12 * J);
+            x.year = 100 * (C - 49) + Y + J;
+        }
+        if (has_c && has_d) { x.hour = (uint8_t)(((d2 & 1u) << 4) | (d3 >> 12)); x.minute = (uint8_t)((d3 >> 6) & 63u); }
+        if (has_d) { const int v = (int)(d3 & 31u); x.local_time_offset = (int8_t)(((d3 >> 5) & 1u) ? -v : v); }
+    } else if (code == 10) {
+        fmgpu_rds_db_ext& x = *w.ext;
+        const uint8_t ab = (uint8_t)((bw >> 4) & 1u);
+        const int seg = (int)(bw & 1u);
+        if (ab != x.ptyn_ab_flag) for (int i = 0; i < 8; i++) x.programme_type_name[i] = 0;
+        x.ptyn_ab_flag = ab;
+        if (has_c) { put_char(x.programme_type_name, 4 * seg, d2 >> 8); put_char(x.programme_type_name, 4 * seg + 1, d2 & 0xFFu); }
+        if (has_d) { put_char(x.programme_type_name, 4 * seg + 2, d3 >> 8); put_char(x.programme_type_name, 4 * seg + 3, d3 & 0xFFu); }
     }
 }
 

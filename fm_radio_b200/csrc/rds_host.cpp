@@ -5,8 +5,8 @@
 //   DifferentialManchesterDecoder::PushBit      rds_decoder/differential_manchester_decoder.h:32-59
 //   RDS_Group_Sync                              rds_decoder/rds_group_sync.cpp:29-237
 //   CalculateCRC10 / single-bit error patterns  rds_decoder/crc10.cpp:9-60, rds_constants.h:15-28
-//   RDS_Decoder::ProcessGroup, 0A and 2A        rds_decoder/rds_decoder.cpp:82-126, 167-245, 301-340
-//   RDS_Database_Decoder_Handler                rds_decoder/rds_database_decoder_handler.cpp:15-50
+//   RDS_Decoder::ProcessGroup, 0A 2A 4A 10A     rds_decoder/rds_decoder.cpp:82-126, 159-245, 301-340, 363-441
+//   RDS_Database_Decoder_Handler                rds_decoder/rds_database_decoder_handler.cpp:15-138
 #include <cstring>
 #include <vector>
 #include "rds_core.h"
@@ -60,6 +60,9 @@ void fmgpu_rds_get_db(const fmgpu_rds* r, uint16_t* pi, char ps8[8], char rt64[6
     if (pty) *pty = r->st.pty;
     if (ps8) std::memcpy(ps8, r->st.ps, 8);
     if (rt64) std::memcpy(rt64, r->st.rt, 64);
+}
+void fmgpu_rds_get_db_ext(const fmgpu_rds* r, fmgpu_rds_db_ext* out) {
+    if (r && out) *out = r->st.ext;
 }
 
 } // extern "C"

@@ -49,6 +49,18 @@ class StreamParams:
     f_offset_hz: float = 0.0      # carrier (tuning) offset
     tones_left: tuple = ((1000.0, 0.5), (3500.0, 0.2))
     tones_right: tuple = ((1700.0, 0.5), (5200.0, 0.2))
+    # group 0A flag bits (EN 50067 3.1.5.1) and, when extended_groups is set, one 10A (programme type name)
+    # and one 4A (clock-time and date) group after every six 0A/2A groups
+    tp: int = 0
+    ta: int = 0
+    ms: int = 1
+    di: int = 0                   # d3 d2 d1 d0 = dynamic PTY, compressed, artificial head, stereo
+    extended_groups: bool = False
+    ptyn: str = "B200 PTY"
+    mjd: int = 61331              # 2026-10-18
+    hour: int = 13
+    minute: int = 37
+    lto: int = -7                 # local time offset in half hours
 
     @staticmethod
     def for_stream(s: int) -> "StreamParams":
@@ -79,17 +91,33 @@ def rds_block(data16: int, offset_name: str) -> int:
 
 
 def rds_group_words(p: StreamParams, index: int) -> list[int]:
-    """The four 16-bit data words of the index-th transmitted group (0A and 2A alternate)."""
+    """The four 16-bit data words of the index-th transmitted group (0A and 2A alternate; with
+    p.extended_groups every 7th is a 10A and every 8th a 4A)."""
+    pty_tp = ((p.tp & 1) << 10) | ((p.pty & 31) << 5)
+    if p.extended_groups:
+        cyc, pos = divmod(index, 8)
+        if pos == 6:                                            # 10A, figure 31
+            seg = cyc % 2
+            name = p.ptyn.ljust(8)[:8].encode("latin-1")
+            b = (10 << 12) | pty_tp | (0 << 4) | seg
+            return [p.pi_code & 0xFFFF, b, (name[4 * seg] << 8) | name[4 * seg + 1], (name[4 * seg + 2] << 8) | name[4 * seg + 3]]
+        if pos == 7:                                            # 4A, figure 20
+            minute = (p.minute + cyc) % 60
+            b = (4 << 12) | pty_tp | ((p.mjd >> 15) & 3)
+            c = ((p.mjd & 0x7FFF) << 1) | ((p.hour >> 4) & 1)
+            d = ((p.hour & 15) << 12) | (minute << 6) | ((1 if p.lto < 0 else 0) << 5) | (abs(p.lto) & 31)
+            return [p.pi_code & 0xFFFF, b, c, d]
+        index = cyc * 6 + pos
     k = index // 2
     if index % 2 == 0:
         seg = k % 4
-        b = (0 << 12) | (0 << 11) | (0 << 10) | ((p.pty & 31) << 5) | (0 << 4) | (1 << 3) | (0 << 2) | seg
+        b = (0 << 12) | (0 << 11) | pty_tp | ((p.ta & 1) << 4) | ((p.ms & 1) << 3) | (((p.di >> (3 - seg)) & 1) << 2) | seg
         c = ((p.af_pair[0] & 0xFF) << 8) | (p.af_pair[1] & 0xFF)
         ps = p.ps.ljust(8)[:8].encode("latin-1")
         d = (ps[2 * seg] << 8) | ps[2 * seg + 1]
     else:
         seg = k % 16
-        b = (2 << 12) | (0 << 11) | (0 << 10) | ((p.pty & 31) << 5) | (0 << 4) | seg
+        b = (2 << 12) | (0 << 11) | pty_tp | (0 << 4) | seg
         rt = p.radiotext.ljust(64)[:64].encode("latin-1")
         c = (rt[4 * seg] << 8) | rt[4 * seg + 1]
         d = (rt[4 * seg + 2] << 8) | rt[4 * seg + 3]

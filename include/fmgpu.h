@@ -30,6 +30,22 @@ typedef struct fmgpu_rds_group {
     uint8_t  type[4];        /* BlockOffsetID: A=0 B=1 C=2 C1=3 D=4 (rds_constants.h:29)       */
 } fmgpu_rds_group;
 
+/* The RDS_Database fields beyond PI / PTY / PS / RT (rds_decoder/rds_database.h:26-53) that
+ * RDS_Database_Decoder_Handler fills (rds_database_decoder_handler.cpp:30-138) from groups
+ * 0A (TA/TP, M/S, DI bits; rds_decoder.cpp:159-245), 4A (clock-time and date, :363-405; the
+ * Modified Julian Day conversion is modified_julian_date.h:8-24) and 10A (programme type name,
+ * :407-441).  Alternative frequencies are a TODO in the reference handler (:117-119) and are not
+ * kept here either. */
+typedef struct fmgpu_rds_db_ext {
+    char programme_type_name[8];
+    int32_t year;                    /* datetime: zero until a 4A group with a valid block C arrives */
+    uint8_t day, month, hour, minute;
+    int8_t local_time_offset;        /* half hours, signed */
+    uint8_t traffic_announcement;    /* rds_database.h:19-24: 0 NONE, 1 EON_INFO, 2 AWAIT_EON_ANNOUNCE, 3 NOW_EON_ANNOUNCE */
+    uint8_t is_stereo, is_music, is_artificial_head, is_compressed, is_dynamic_program_type;
+    uint8_t ptyn_ab_flag;            /* decoder state (rds_database_decoder_handler.h:12): last 10A A/B flag, 4 = none yet */
+} fmgpu_rds_db_ext;
+
 enum {
     FMGPU_OK = 0,
     FMGPU_ERR_ARG = -1,      /* bad argument (null, wrong size, unknown id)            */
@@ -229,7 +245,7 @@ long long fmgpu_launch_count(fmgpu_demod* h);
  * each block (app.cpp:66-77): DifferentialManchesterDecoder::Process
  * (rds_decoder/differential_manchester_decoder.h:25-59) -> RDS_Decoding_Chain::Process
  * (rds_decoding_chain.h:24) -> RDS_Group_Sync / CalculateCRC10 / RDS_Decoder::ProcessGroup and the
- * PI/PTY/PS/RT part of RDS_Database.  Results stay on the device: per stream the running totals,
+ * RDS_Database fields (PI/PTY/PS/RT, and fmgpu_rds_db_ext).  Results stay on the device: per stream the running totals,
  * the database, and rings of the most recent groups and 16-byte packets (the rings hold at least
  * what two blocks produce).  fmgpu_rds_device_fetch synchronises the handle and copies them to
  * the host once; the getters then read that copy.  Indices are absolute (0 = first group / byte
@@ -241,6 +257,7 @@ int fmgpu_rds_device_counts(fmgpu_demod* h, int stream, unsigned long long* n_gr
 int fmgpu_rds_device_get_groups(fmgpu_demod* h, int stream, unsigned long long first, fmgpu_rds_group* out, int max_groups);
 int fmgpu_rds_device_get_bytes(fmgpu_demod* h, int stream, unsigned long long first, uint8_t* out, int max_bytes);
 int fmgpu_rds_device_get_db(fmgpu_demod* h, int stream, uint16_t* pi, char ps8[8], char rt64[64], uint8_t* pty);
+int fmgpu_rds_device_get_db_ext(fmgpu_demod* h, int stream, fmgpu_rds_db_ext* out);
 
 /* ---- host-side filter designers: src/dsp/filter_designer.h:8-35, same signatures ----------- */
 void fmgpu_create_fir_lpf(float* b, int N, float k);
@@ -303,7 +320,7 @@ int fmgpu_calculate_fft(const float* x_host, float* y_host, int n, int fftshift)
 int fmgpu_get_fft(fmgpu_demod* h, int stream, fmgpu_buffer buf, int fftshift, float* y_host, size_t* n_out);
 
 /* ---- RDS bit path on the host (differential_manchester_decoder.h:25-59, rds_group_sync.cpp,
- * crc10.cpp, and the PI/PTY/PS/RT subset of rds_decoder.cpp) ---------------------------------- */
+ * crc10.cpp, and the database-filling part of rds_decoder.cpp: groups 0A, 2A, 4A, 10A) ---------------------------------- */
 fmgpu_rds* fmgpu_rds_create(void);
 void fmgpu_rds_destroy(fmgpu_rds* r);
 void fmgpu_rds_push_symbols(fmgpu_rds* r, const float* sym, size_t n);
@@ -312,6 +329,7 @@ int  fmgpu_rds_get_groups(const fmgpu_rds* r, fmgpu_rds_group* out, int max_grou
 int  fmgpu_rds_n_bytes(const fmgpu_rds* r);
 int  fmgpu_rds_get_bytes(const fmgpu_rds* r, uint8_t* out, int max_bytes);
 void fmgpu_rds_get_db(const fmgpu_rds* r, uint16_t* pi, char ps8[8], char rt64[64], uint8_t* pty);
+void fmgpu_rds_get_db_ext(const fmgpu_rds* r, fmgpu_rds_db_ext* out);
 
 /* ---- wideband channelizer (BASELINE config 4) --------------------------
  * New component: the reference tunes ONE station in hardware and has no channelizer (its TODO on a

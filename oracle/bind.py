@@ -69,6 +69,8 @@ def lib(kind: str = "ref"):
         L.n_rds_bytes.argtypes = [C.c_void_p]
         L.get_rds_bytes.argtypes = [C.c_void_p, C.c_void_p]
         L.get_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.get_db_ext.argtypes = [C.c_void_p, C.c_void_p]
+        L.rds_get_db_ext.argtypes = [C.c_void_p, C.c_void_p]
         L.rds_create.restype = C.c_void_p
         L.rds_destroy.argtypes = [C.c_void_p]
         L.rds_push_symbols.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -109,6 +111,23 @@ def _groups(n, getter, h):
     if n:
         getter(h, data.ctypes.data, valid.ctypes.data, typ.ctypes.data)
     return data, valid, typ
+
+
+class DbExt(C.Structure):
+    """fmo_db_ext (oracle/fm_oracle.h); the harness fills the same 24 bytes from the reference's RDS_Database."""
+    _fields_ = [("programme_type_name", C.c_char * 8), ("year", C.c_int32), ("day", C.c_uint8), ("month", C.c_uint8),
+                ("hour", C.c_uint8), ("minute", C.c_uint8), ("local_time_offset", C.c_int8),
+                ("traffic_announcement", C.c_uint8), ("is_stereo", C.c_uint8), ("is_music", C.c_uint8),
+                ("is_artificial_head", C.c_uint8), ("is_compressed", C.c_uint8), ("is_dynamic_program_type", C.c_uint8),
+                ("ptyn_ab_flag", C.c_uint8)]
+
+
+def _db_ext(getter, h) -> dict:
+    e = DbExt()
+    getter(h, C.byref(e))
+    d = {name: getattr(e, name) for name, _ in DbExt._fields_ if name not in ("programme_type_name", "ptyn_ab_flag")}
+    d["programme_type_name"] = bytes(bytearray(e)[:8])
+    return d
 
 
 def _db(getter, h):
@@ -189,6 +208,9 @@ class CpuDemod:
     def db(self):
         return _db(self.L.get_db, self.h)
 
+    def db_ext(self) -> dict:
+        return _db_ext(self.L.get_db_ext, self.h)
+
 
 class CpuRds:
     """The RDS bit path alone (DifferentialManchesterDecoder -> RDS_Decoding_Chain)."""
@@ -218,3 +240,6 @@ class CpuRds:
 
     def db(self):
         return _db(self.L.rds_get_db, self.h)
+
+    def db_ext(self) -> dict:
+        return _db_ext(self.L.rds_get_db_ext, self.h)

@@ -558,12 +558,14 @@ typedef struct {
     uint8_t* bytes; int n_bytes, cap_bytes;
     /* database subset */
     uint16_t pi; uint8_t pty; char ps[8]; char rt[64]; uint8_t ab_flag_rt;
+    fmo_db_ext ext;                          /* rds_database.h:26-53 beyond PI/PTY/PS/RT */
 } rds_t;
 
 static void rds_init(rds_t* r) {
     memset(r, 0, sizeof(*r));
     r->max_group_desyncs_for_reset = 3;      /* rds_group_sync.cpp:22 */
     r->ab_flag_rt = 4;                       /* rds_database_decoder_handler.h:11 */
+    r->ext.ptyn_ab_flag = 4;                 /* rds_database_decoder_handler.h:12 */
 }
 static void rds_free(rds_t* r) { free(r->groups); free(r->bytes); }
 
@@ -578,8 +580,17 @@ static void rds_decode_group(rds_t* r, const grp_t* g) {   /* rds_decoder.cpp:82
     if (version) return;
     const int has_C = g->valid[2] && g->type[2] == 2;
     const int has_D = g->valid[3] && g->type[3] == 4;
-    if (group_code == 0) {                                 /* OnGroup0A :167-245 */
+    if (group_code == 0) {                                 /* OnGroup0A :159-245 */
         const uint8_t seg = descriptor & 3;
+        const uint8_t tp = (descriptor >> 10) & 1, ta = (descriptor >> 4) & 1, di = (descriptor >> 2) & 1;
+        r->ext.is_music = (descriptor >> 3) & 1;           /* handler.cpp:74-76 */
+        r->ext.traffic_announcement = (uint8_t)((tp << 1) | ta);   /* handler.cpp:53-72, enum order rds_database.h:19-24 */
+        switch (seg) {                                     /* :211-228 */
+        case 0: r->ext.is_dynamic_program_type = di; break;
+        case 1: r->ext.is_compressed = di; break;
+        case 2: r->ext.is_artificial_head = di; break;
+        default: r->ext.is_stereo = di; break;
+        }
         if (has_D) {
             char c0 = (char)(g->data[3] >> 8), c1 = (char)(g->data[3] & 0xFF);
             if (c0 == '\r') c0 = 0;
@@ -595,6 +606,34 @@ static void rds_decode_group(rds_t* r, const grp_t* g) {   /* rds_decoder.cpp:82
         for (int i = 0; i < 4; i++) if (c[i] == '\r') c[i] = 0;
         if (has_C) { r->rt[4*seg] = c[0]; r->rt[4*seg+1] = c[1]; }
         if (has_D) { r->rt[4*seg+2] = c[2]; r->rt[4*seg+3] = c[3]; }
+    } else if (group_code == 4) {                          /* OnGroup4A :363-405 */
+        const uint32_t mjd = ((uint32_t)(descriptor & 3) << 15) | ((g->data[2] & 0xFFFE) >> 1);
+        const uint8_t hour = (uint8_t)(((g->data[2] & 1) << 4) | ((g->data[3] & 0xF000) >> 12));
+        const uint8_t minute = (uint8_t)((g->data[3] & 0x0FC0) >> 6);
+        const int lto_sign = (g->data[3] >> 5) & 1, lto_val = g->data[3] & 31;
+        if (has_C) {                                       /* modified_julian_date.h:8-24 */
+            long J = (long)mjd + 2400001 + 68569;
+            const long C = 4 * J / 146097;
+            J = J - (146097 * C + 3) / 4;
+            const long Y = 4000 * (J + 1) / 1461001;
+            J = J - 1461 * Y / 4 + 31;
+            const long M = 80 * J / 2447;
+            r->ext.day = (uint8_t)(J - 2447 * M / 80);
+            J = M / 11;
+            r->ext.month = (uint8_t)(M + 2 - (12 * J));
+            r->ext.year = (int32_t)(100 * (C - 49) + Y + J);
+        }
+        if (has_C && has_D) { r->ext.hour = hour; r->ext.minute = minute; }
+        if (has_D) r->ext.local_time_offset = (int8_t)(lto_sign ? -lto_val : lto_val);
+    } else if (group_code == 10) {                         /* OnGroup10A :407-441 */
+        const uint8_t ab = (descriptor >> 4) & 1;
+        const uint8_t seg = descriptor & 1;
+        if (ab != r->ext.ptyn_ab_flag) memset(r->ext.programme_type_name, 0, 8);   /* handler.cpp:30-35 */
+        r->ext.ptyn_ab_flag = ab;
+        char c[4] = { (char)(g->data[2] >> 8), (char)(g->data[2] & 0xFF), (char)(g->data[3] >> 8), (char)(g->data[3] & 0xFF) };
+        for (int i = 0; i < 4; i++) if (c[i] == '\r') c[i] = 0;
+        if (has_C) { r->ext.programme_type_name[4*seg] = c[0]; r->ext.programme_type_name[4*seg+1] = c[1]; }
+        if (has_D) { r->ext.programme_type_name[4*seg+2] = c[2]; r->ext.programme_type_name[4*seg+3] = c[3]; }
     }
 }
 
@@ -705,6 +744,7 @@ static void copy_db(const rds_t* r, uint16_t* pi, char* ps8, char* rt64, uint8_t
     *pi = r->pi; *pty = r->pty; memcpy(ps8, r->ps, 8); memcpy(rt64, r->rt, 64);
 }
 void fmo_rds_get_db(void* rv, uint16_t* pi, char* ps8, char* rt64, uint8_t* pty) { copy_db((rds_t*)rv, pi, ps8, rt64, pty); }
+void fmo_rds_get_db_ext(void* rv, fmo_db_ext* out) { *out = ((rds_t*)rv)->ext; }
 
 /* ------------------------------------------------------------------------------------------
  * fm_demod/broadcast_fm_demod.{h,cpp}
@@ -1037,6 +1077,7 @@ void fmo_get_groups(void* hv, uint16_t* data, uint8_t* valid, uint8_t* type) { c
 int fmo_n_rds_bytes(void* hv) { return ((demod_t*)hv)->rdsdec.n_bytes; }
 void fmo_get_rds_bytes(void* hv, uint8_t* out) { demod_t* d = (demod_t*)hv; memcpy(out, d->rdsdec.bytes, d->rdsdec.n_bytes); }
 void fmo_get_db(void* hv, uint16_t* pi, char* ps8, char* rt64, uint8_t* pty) { copy_db(&((demod_t*)hv)->rdsdec, pi, ps8, rt64, pty); }
+void fmo_get_db_ext(void* hv, fmo_db_ext* out) { *out = ((demod_t*)hv)->rdsdec.ext; }
 
 /* ------------------------------------------------------------------------------------------
  * Wideband channelizer oracle (BASELINE config 4).  The reference has NO channelizer (SURVEY.md

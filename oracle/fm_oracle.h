@@ -23,6 +23,19 @@
 extern "C" {
 #endif
 
+/* rds_database.h:26-53 beyond PI / PTY / PS / RT, flattened (traffic_announcement = the enum's ordinal, :19-24;
+ * ptyn_ab_flag = the handler's AB_flag_programme_type_name, rds_database_decoder_handler.h:12).
+ * The harness fills the same layout from the reference's own RDS_Database. */
+typedef struct fmo_db_ext {
+    char programme_type_name[8];
+    int32_t year;
+    uint8_t day, month, hour, minute;
+    int8_t local_time_offset;
+    uint8_t traffic_announcement;
+    uint8_t is_stereo, is_music, is_artificial_head, is_compressed, is_dynamic_program_type;
+    uint8_t ptyn_ab_flag;
+} fmo_db_ext;
+
 void* fmo_create(int block_size);
 void fmo_destroy(void* h);
 int fmo_process_u8(void* h, const uint8_t* iq);
@@ -37,6 +50,7 @@ void fmo_get_groups(void* h, uint16_t* data, uint8_t* valid, uint8_t* type);
 int fmo_n_rds_bytes(void* h);
 void fmo_get_rds_bytes(void* h, uint8_t* out);
 void fmo_get_db(void* h, uint16_t* pi, char* ps8, char* rt64, uint8_t* pty);
+void fmo_get_db_ext(void* h, fmo_db_ext* out);
 
 void* fmo_rds_create(void);
 void fmo_rds_destroy(void* r);
@@ -46,6 +60,7 @@ void fmo_rds_get_groups(void* r, uint16_t* data, uint8_t* valid, uint8_t* type);
 int fmo_rds_n_bytes(void* r);
 void fmo_rds_get_bytes(void* r, uint8_t* out);
 void fmo_rds_get_db(void* r, uint16_t* pi, char* ps8, char* rt64, uint8_t* pty);
+void fmo_rds_get_db_ext(void* r, fmo_db_ext* out);
 
 void fmo_create_fir_lpf(float* b, int N, float k);
 void fmo_create_fir_hpf(float* b, int N, float k);

@@ -217,6 +217,30 @@ void fmref_get_db(void* hv, uint16_t* pi, char* ps8, char* rt64, uint8_t* pty) {
     std::memcpy(rt64, db.radio_text, 64);
 }
 
+// RDS_Database beyond PI / PTY / PS / RT, in the flat layout of fm_oracle.h's fmo_db_ext (24 bytes).
+// ptyn_ab_flag is private decoder state in the reference (rds_database_decoder_handler.h:12) and is
+// reported as 0xFF here: comparisons skip it.
+struct RefDbExt {
+    char programme_type_name[8];
+    int32_t year;
+    uint8_t day, month, hour, minute;
+    int8_t local_time_offset;
+    uint8_t traffic_announcement;
+    uint8_t is_stereo, is_music, is_artificial_head, is_compressed, is_dynamic_program_type;
+    uint8_t ptyn_ab_flag;
+};
+static void fill_db_ext(const RDS_Database& db, RefDbExt* o) {
+    std::memcpy(o->programme_type_name, db.programme_type_name, 8);
+    o->year = db.datetime.year; o->day = (uint8_t)db.datetime.day; o->month = (uint8_t)db.datetime.month;
+    o->hour = db.datetime.hour; o->minute = db.datetime.minute;
+    o->local_time_offset = db.local_time_offset;
+    o->traffic_announcement = (uint8_t)db.traffic_announcement;
+    o->is_stereo = db.is_stereo; o->is_music = db.is_music; o->is_artificial_head = db.is_artificial_head;
+    o->is_compressed = db.is_compressed; o->is_dynamic_program_type = db.is_dynamic_program_type;
+    o->ptyn_ab_flag = 0xFF;
+}
+void fmref_get_db_ext(void* hv, RefDbExt* out) { fill_db_ext(((RefHandle*)hv)->rds.chain->db, out); }
+
 // Stand-alone RDS bit path (differential_manchester_decoder.h:25-59 -> rds_group_sync.cpp:29):
 // feeds arbitrary soft symbols through the reference decoder; used to judge symbols produced
 // by the CUDA path with the reference's own decoder.
@@ -247,6 +271,8 @@ void fmref_rds_get_db(void* rv, uint16_t* pi, char* ps8, char* rt64, uint8_t* pt
     std::memcpy(ps8, db.service_name, 8);
     std::memcpy(rt64, db.radio_text, 64);
 }
+
+void fmref_rds_get_db_ext(void* rv, RefDbExt* out) { fill_db_ext(((RefRdsChain*)rv)->chain->db, out); }
 
 // Filter designers (dsp/filter_designer.h:8-35) for pinning the host-side re-implementation.
 void fmref_create_fir_lpf(float* b, int N, float k) { create_fir_lpf(b, N, k); }

@@ -293,3 +293,43 @@ def test_cuda_graph_replay_equals_multi_stream_pipeline(S, bs, keep):
         assert a.rds_counts(s) == b.rds_counts(s)
     assert a.launch_count == b.launch_count
     a.close(); b.close()
+
+
+def test_device_rds_database_flags_clock_and_programme_type_name():
+    """K6 keeps all of RDS_Database the reference's handler fills (rds_database.h:26-53): the signal carries 0A
+    flag bits, 4A clock groups and 10A programme-type-name groups; per stream the device's database equals the
+    host decoder's (same symbols) and the checker chain's, field for field, and shows what was transmitted."""
+    import dataclasses
+    import torch
+    S, nblk = 3, 80
+    ps = [dataclasses.replace(synth.StreamParams.for_stream(70 + s), extended_groups=True, tp=1, ta=s & 1, ms=(s >> 1) & 1,
+                              di=(0b1011, 0b0100, 0b1111)[s], ptyn=("Jazz\rXY ", "NEWSTALK", "B200 PTY")[s],
+                              mjd=61331 + 1000 * s, hour=7 + 8 * s, minute=10, lto=(-7, 11, 0)[s]) for s in range(S)]
+    caps = np.stack([synth.synth_u8_numpy(H.B * nblk, p) for p in ps])
+    dev_in = torch.from_numpy(caps).cuda()
+    g = fm.FMDemod(H.B, S, pipeline_depth=3)
+    g.wait_external_stream(torch.cuda.current_stream().cuda_stream)
+    decs = [fm.RDSDecoder() for _ in range(S)]
+    keep = []
+    for k in range(nblk):
+        keep.append(dev_in[:, 2 * H.B * k:2 * H.B * (k + 1)].contiguous())
+        slot = g.enqueue_u8_device(keep[-1])
+        g.fetch_outputs(slot); g.sync()
+        for s in range(S):
+            decs[s].push_symbols(g.get(Buf.RDS_PRED_SYM, s))
+    g.rds_fetch()
+    for s in range(S):
+        e = g.rds_db_ext(s)
+        assert e == decs[s].db_ext() and g.rds_db(s) == decs[s].db()
+        p = ps[s]
+        assert e["programme_type_name"] == p.ptyn.replace("\r", "\0").encode()
+        assert (e["year"], e["month"], e["day"]) == ((2026, 10, 18), (2029, 7, 14), (2032, 4, 9))[s]
+        assert e["hour"] == p.hour and e["local_time_offset"] == p.lto and 10 <= e["minute"] <= 16
+        assert e["traffic_announcement"] == 2 + p.ta and e["is_music"] == p.ms
+        assert [e["is_dynamic_program_type"], e["is_compressed"], e["is_artificial_head"], e["is_stereo"]] == [(p.di >> k) & 1 for k in (3, 2, 1, 0)]
+    for kind in H.cpu_checker_kinds():
+        chk = bind.CpuDemod(H.B, kind)
+        for k in range(nblk):
+            chk.process_u8(caps[1, 2 * H.B * k:2 * H.B * (k + 1)])
+        assert g.rds_db_ext(1) == chk.db_ext() and g.rds_db(1) == chk.db()
+    g.close()

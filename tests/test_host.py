@@ -2,6 +2,7 @@
 include/fmgpu.h declares, the host filter designers and the host RDS bit path agree with the
 checkers, and -- without a GPU -- compute entry points fail loudly instead of falling back."""
 import ctypes as C
+import dataclasses
 import os
 import re
 
@@ -125,6 +126,58 @@ def test_host_rds_decoder_matches_checker(kind, flip):
         d, v, _ = mine.groups()
         assert len(d) >= 57 and v.all()
         assert mine.db()["pi"] == p.pi_code and mine.db()["ps"] == p.ps.encode()
+
+
+def _ext_params(seed: int) -> synth.StreamParams:
+    return dataclasses.replace(synth.StreamParams.for_stream(seed), extended_groups=True, tp=1, ta=seed & 1, ms=(seed >> 1) & 1,
+                               di=0b1011 if seed % 3 else 0b0100, ptyn=("Jazz\rXY " if seed % 2 else "NEWSTALK"),
+                               mjd=61331 + 400 * seed, hour=7 + seed, minute=55, lto=(-7 if seed % 2 else 11))
+
+
+@pytest.mark.parametrize("kind", H.cpu_checker_kinds())
+@pytest.mark.parametrize("flip", [0.0, 0.004, 0.02])
+def test_host_rds_database_groups_0a_4a_10a_match_checker(kind, flip):
+    """TA/TP, M/S, DI, clock (4A) and programme type name (10A) of RDS_Database (rds_database.h:26-53):
+    product host decoder == plain-C restatement == the compiled reference, after every ragged push."""
+    rng = np.random.default_rng(5)
+    for seed in (1, 2, 6):
+        p = _ext_params(seed)
+        bits = synth.rds_bits(p, 104 * 96)
+        sym = _symbols_from_bits(np.concatenate([rng.integers(0, 2, 11).astype(np.uint8), bits]), rng, flip=flip)
+        mine, ref = fm.RDSDecoder(), bind.CpuRds(kind)
+        for chunk in np.array_split(sym, 17):
+            mine.push_symbols(chunk)
+            ref.push_symbols(chunk)
+            assert mine.db_ext() == ref.db_ext()
+            assert mine.db() == ref.db()
+        if flip == 0.0:
+            e = mine.db_ext()
+            assert e["programme_type_name"] == p.ptyn.replace("\r", "\0").encode()
+            assert (e["year"], e["month"], e["day"]) == _ymd(p.mjd) and e["hour"] == p.hour and e["local_time_offset"] == p.lto
+            assert e["traffic_announcement"] == 2 * p.tp + p.ta and e["is_music"] == p.ms
+            assert [e["is_dynamic_program_type"], e["is_compressed"], e["is_artificial_head"], e["is_stereo"]] == [(p.di >> k) & 1 for k in (3, 2, 1, 0)]
+
+
+def _ymd(mjd: int):
+    import datetime
+    d = datetime.date(1858, 11, 17) + datetime.timedelta(days=mjd)
+    return d.year, d.month, d.day
+
+
+def test_rds_clock_date_conversion_over_the_17_bit_mjd_range():
+    """modified_julian_date.h:8-24 as restated in rds_core.h (32-bit arithmetic): every 97th day of the 17-bit MJD
+    range through a hand-built 4A group, against the calendar."""
+    p = synth.StreamParams(extended_groups=True)
+    rng = np.random.default_rng(0)
+    for mjd in list(range(0, 1 << 17, 97 * 64)) + [0, 15078, 51544, 61331, (1 << 17) - 1]:
+        q = dataclasses.replace(p, mjd=mjd, hour=23, minute=3, lto=0)
+        words = synth.rds_group_words(q, 7)
+        bits = np.concatenate([[(synth.rds_block(w, n) >> b) & 1 for b in range(25, -1, -1)] for w, n in zip(words, "ABCD")] * 4).astype(np.uint8)
+        mine = fm.RDSDecoder()
+        mine.push_symbols(_symbols_from_bits(bits, rng, flip=0.0))
+        e = mine.db_ext()
+        assert (e["year"], e["month"], e["day"]) == _ymd(mjd), mjd
+        assert (e["hour"], e["minute"]) == (23, 3)
 
 
 def test_rds_encoder_crc_known_answer():
