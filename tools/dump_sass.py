@@ -15,11 +15,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "fm_radio_b200", "libfmgpu.so")
 WANT = [  # (file stem, regex on the demangled name)
-    ("k1_toeplitz_i8", r"k1_toeplitz_i8"), ("k1_fir4_discrim_u8", r"k1_fir4_discrim_u8"),
+    ("k1_toeplitz_i8", r"k1_toeplitz_i8<\(int\)2, \(int\)1>"), ("k1_fir4_discrim_u8", r"k1_fir4_discrim_u8"),
+    ("k1_fir4_discrim_cf32", r"k1_fir4_discrim_cf32"),
     ("k2_mpx_sparse_hilbert", r"k2_mpx<\(bool\)1>"), ("k3_pll_fast", r"k3_pll<\(bool\)0, \(int\)0, \(bool\)1>"),
     ("k3_pll_exact", r"k3_pll<\(bool\)0, \(int\)0, \(bool\)0>"), ("k4_mix_fir", r"k4_mix_fir"), ("k4b_lmr_phase", r"k4b_lmr_phase"),
     ("k5_bpsk_symbolwise", r"k5_bpsk<\(bool\)0, \(bool\)0>"), ("k6_rds", r"k6_rds\("), ("k7_audio_pcm", r"k7_audio_pcm"),
-    ("chan_mma_i8", r"chan_mma_i8"), ("chan_fir_fp32", r"chan_fir_fp32"),
+    ("chan_mma_i8_pipelined", r"chan_mma_i8_pipelined"), ("chan_mma_i8_v1", r"chan_mma_i8\("), ("chan_fir_fp32", r"chan_fir_fp32"),
 ]
 
 

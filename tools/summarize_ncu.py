@@ -17,6 +17,8 @@ KEYS = [
     ("FMA pipe instr % of peak", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
     ("ALU pipe instr % of peak", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
     ("LSU pipe instr % of peak", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+    ("tensor pipe busy % (cycles)", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+    ("tensor pipe (i8/subpipe) busy %", "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active"),
     ("warp instructions", "smsp__inst_executed.sum"),
     ("DRAM read MB", "dram__bytes_read.sum"),
     ("DRAM write MB", "dram__bytes_write.sum"),
@@ -43,6 +45,11 @@ def main(path):
                 v = r[col[key]]
                 try:
                     f = float(v)
+                    u = units[col[key]]
+                    if label.endswith(" MB"):
+                        f *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
+                    elif label.endswith(" us"):
+                        f *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
                     cells.append(f"{f:.1f}" if abs(f) < 1e4 else f"{f:.3e}")
                 except ValueError:
                     cells.append(v)
