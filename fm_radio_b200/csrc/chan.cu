@@ -197,22 +197,25 @@ chan_mma_i8(const __grid_constant__ ChanMmaParams p)
 // The kernel above is synchronous: every thread copies its row of a K chunk through registers, the CTA meets at
 // a barrier, one thread issues the MMAs, and the epilogue (32 x sincospif per thread) runs with the tensor pipe
 // idle -- ncu: tensor pipe 4 % active, 61 us per launch for 100 stations x 65536 outputs, top stall
-// long_scoreboard.  This one is the classic three-role pipeline, one CTA of 256 threads per SM:
-//   warps 0-1  PRODUCERS   im2col of the raw capture into a ring of CH2_NSTG K-chunk stages with cp.async (8-byte
+// long_scoreboard.  This one is the classic three-role pipeline, one CTA of 416 threads per SM:
+//   warps 0-3  PRODUCERS   im2col of the raw capture into a ring of CH2_NSTG K-chunk stages with cp.async (8-byte
 //                          copies: window rows are 2 D = 40 bytes apart, so they are 8- but not 16-byte aligned,
 //                          which also rules out TMA), two chunks in flight ahead of the one being released;
-//   warp  2    MMA ISSUER  one elected lane: 4 tcgen05.mma (K steps; N = 192 = 3 digit planes) per chunk into one of TWO
+//   warp  4    MMA ISSUER  one elected lane: 4 tcgen05.mma (K steps; N = 192 = 3 digit planes) per chunk into one of TWO
 //                          accumulator buffers in TMEM, tcgen05.commit frees the stage / publishes the tile;
-//   warps 4-11 EPILOGUE    two warpgroups taking alternate blocks of 8 channel slots: tcgen05.ld of the finished buffer
+//   warps 5-12 EPILOGUE    two warpgroups taking alternate blocks of 8 channel slots: tcgen05.ld of the finished buffer
 //                          while the next tile's MMAs run; branch-free per-channel arithmetic (8 independent channels in
-//                          flight per thread); the channel rotation exp(-j ph) by the chain's own polynomial sine instead
-//                          of sincospif.  (With one epilogue warp per SM sub-partition and a branch per channel the
-//                          epilogue ran at IPC 0.2 and bounded the kernel: 51 us, ncu.)
+//                          flight per thread, packed FP32 for the (re, im) pair); the channel rotation exp(-j ph) comes
+//                          from a [slot][row] table in shared memory built once per launch with the chain's own
+//                          polynomial sine, times one factor per (tile, slot) that is 1 on the fs_out / 128 raster.
+//                          (History: one epilogue warp per SM sub-partition and a branch per channel ran at IPC 0.2
+//                          and bounded the kernel, 51 us; two polynomial sines per output sample, 41.8 us with the
+//                          epilogue issuing 2/3 of the kernel's 18.6 M warp instructions -- ncu, profiles/r2n.)
 // The three digit planes of G sit side by side in shared memory, so each K step is ONE tcgen05.mma of N = 192 (100 clocks
 // measured, tools/umma_rate.cu) instead of three of N = 64 (3 x 50: small-N MMAs have a ~50-clock floor).
 // All hand-offs are mbarriers (full / empty per stage, acc_full / acc_empty per accumulator buffer).
-constexpr int CH2_THREADS = 384;
-constexpr int CH2_NSTG = 6;                     // 6 x 16 KB ring + 72 KB of G = 168 KB of shared memory: one CTA per SM
+constexpr int CH2_THREADS = 416;                // 4 producer warps, 1 MMA-issuer warp, 8 epilogue warps
+constexpr int CH2_NSTG = 6;                     // 6 x 16 KB ring + 72 KB of G + 32 KB rotation table = 200 KB of shared memory: one CTA per SM
 constexpr int CH2_TMEM_COLS = 512;              // 2 accumulator buffers, 192 of 256 columns used in each
 constexpr int CH2_LAG = 2;                      // chunks of cp.async in flight behind the producers' issue point
 
@@ -223,25 +226,46 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;                                              // n_kchunks x 3 x 8 KB, resident
     uint8_t* sA = sB + (size_t)p.n_kchunks * CH_PLANES * CH_BSUB_BYTES;   // CH2_NSTG x 16 KB ring
-    __shared__ __align__(8) uint64_t bar_full[CH2_NSTG], bar_empty[CH2_NSTG], bar_acc_full[2], bar_acc_empty[2];
+    float2* sT = (float2*)(sA + CH2_NSTG * CH_A_BYTES);              // [slot][row] rotation table of this launch, 32 KB
+    __shared__ __align__(8) uint64_t bar_full[CH2_NSTG], bar_empty[CH2_NSTG], bar_acc_full[2], bar_acc_empty[2], bar_g;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_off[CH_PLANES * CH_NG];
+    __shared__ int2 s_off2[CH_PLANES][CH_SLOTS];                    // (re, im) column offsets of each slot, per digit plane
     __shared__ uint4 s_meta[CH_SLOTS];
+    __shared__ float2* s_outp[CH_SLOTS];                            // output row of each slot's channel (nullptr: empty slot)
+    __shared__ float2 s_F[8][CH_SLOTS];                             // per epilogue warp: this tile's phase factor of each slot
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform
     const int group = blockIdx.y;
-    {
-        const uint4* src = (const uint4*)(p.bimg + (size_t)group * p.n_kchunks * CH_PLANES * CH_BSUB_BYTES);
-        const int n16 = p.n_kchunks * CH_PLANES * CH_BSUB_BYTES / 16;
-        for (int i = tid; i < n16; i += CH2_THREADS) ((uint4*)sB)[i] = __ldg(src + i);
+    // G (72 KB) arrives by bulk copies issued after the barrier initialisation below; only the MMA issuer waits for it
+    for (int i = tid; i < CH_PLANES * CH_NG; i += CH2_THREADS) ((int*)s_off2)[i] = p.offs[(size_t)group * CH_PLANES * CH_NG + i];
+    if (tid < CH_SLOTS) {
+        const uint4 m = p.meta[(size_t)group * CH_SLOTS + tid];
+        s_meta[tid] = m;
+        s_outp[tid] = m.z != 0xffffffffu ? p.out + (size_t)m.z * p.n_out : nullptr;
     }
-    for (int i = tid; i < CH_PLANES * CH_NG; i += CH2_THREADS) s_off[i] = p.offs[(size_t)group * CH_PLANES * CH_NG + i];
-    if (tid < CH_SLOTS) s_meta[tid] = p.meta[(size_t)group * CH_SLOTS + tid];
+    // Rotation table: the channel rotation of output i = 128 tile + row is exp(-j 2 pi ph / 2^32), ph = inc n_newest0 +
+    // inc D i (exact mod 2^32).  T[slot][row] holds the row part (tile 0) by the chain's polynomial sine
+    // (dsp/simd/chebyshev_sine.h, 1.5e-7: sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)); the tile part
+    // exp(-j 2 pi 128 tile inc D / 2^32) is one factor per (tile, slot), and is exactly 1 when 128 inc D = 0 mod 2^32
+    // (centres on the fs_out / 128 raster: the FM band's 200 kHz raster at 1.024 MS/s is).
+    for (int i = tid; i < CH_SLOTS * CH_ROWS; i += CH2_THREADS) {
+        const uint4 m = p.meta[(size_t)group * CH_SLOTS + (i >> 7)];
+        const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)(i & (CH_ROWS - 1));
+        const float tt = (float)(int)ph * 2.3283064365386963e-10f;
+        sT[i] = make_float2(fm::chebyshev_sine(0.25f - fabsf(tt)), fm::chebyshev_sine(tt));      // (cos, sin)
+    }
     if (tid == 0) {
-        for (int i = 0; i < CH2_NSTG; i++) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }   // full: one arrival per producer warp
+        for (int i = 0; i < CH2_NSTG; i++) { mbar_init(&bar_full[i], 4); mbar_init(&bar_empty[i], 1); }   // full: one arrival per producer warp
         for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }  // acc_empty: one arrival per epilogue warp
+        mbar_init(&bar_g, 1);
         tc::mbar_init_fence();
+        const uint32_t g_bytes = (uint32_t)(p.n_kchunks * CH_PLANES * CH_BSUB_BYTES);
+        const int8_t* src = p.bimg + (size_t)group * g_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar_g)), "r"(g_bytes) : "memory");
+        for (uint32_t o = 0; o < g_bytes; o += CH_BSUB_BYTES)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(sB + o)), "l"(src + o), "r"((uint32_t)CH_BSUB_BYTES), "r"(smem_u32(&bar_g)) : "memory");
     }
     if (warp == 0) tc::tmem_alloc(&s_tmem, CH2_TMEM_COLS);
     fence_async_smem();
@@ -252,8 +276,8 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     const int n_my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_chunks = n_my_tiles * p.n_kchunks;
 
-    if (warp < 2) {
-        // ---------------- producers: rows 64 warp + lane, + 32 of every tile ----------------
+    if (warp < 4) {
+        // ---------------- producers: row 32 warp + lane of every tile ----------------
         auto arrive_full = [&](int c) {              // this warp's copies of chunk c have landed
             fence_async_smem();
             __syncwarp();
@@ -263,22 +287,28 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
             const int stage = c % CH2_NSTG, use = c / CH2_NSTG;
             const int tile = (int)blockIdx.x + (c / p.n_kchunks) * (int)gridDim.x, kc = c % p.n_kchunks;
             if (use > 0) mbar_wait(&bar_empty[stage], (uint32_t)((use - 1) & 1));
+            {
+                // one instruction copies two whole window rows (16 lanes x 8 bytes each): the rows start 2 D bytes apart, so
+                // a warp reads 2 D + 128 contiguous bytes (6 sectors) and writes two full 128-byte swizzle rows (2 wavefronts);
+                // with one row per lane (stride 2 D) the same instruction touched 32 sectors and wrote with 4-way bank conflicts
+                const int h = lane >> 4, j = lane & 15;
+                const uint8_t* src = p.iq + (size_t)(tile * CH_ROWS + 32 * warp + h) * p.row_bytes + kc * CH_KCHUNK + 8 * j;
+                const uint32_t dst = smem_u32(sA + stage * CH_A_BYTES + 4 * warp * 1024) + (uint32_t)((j & 1) << 3);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int r = 64 * warp + 32 * h + lane;
-                const uint8_t* src = p.iq + (size_t)(tile * CH_ROWS + r) * p.row_bytes + kc * CH_KCHUNK;
-                const uint32_t dst = smem_u32(sA + stage * CH_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128);
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + (uint32_t)((((j >> 1) ^ (r & 7)) << 4) + ((j & 1) << 3))), "l"(src + 8 * j));
+                for (int i = 0; i < 16; i++) {
+                    const int r7 = ((2 * i) & 7) + h;                            // (row & 7); row = 32 warp + 2 i + h
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+                                 :: "r"(dst + (uint32_t)(((2 * i) >> 3) * 1024 + r7 * 128 + (((j >> 1) ^ r7) << 4))), "l"(src + (size_t)(2 * i) * p.row_bytes));
+                }
             }
             tc::cp_async_commit();
             if (c >= CH2_LAG) { tc::cp_async_wait<CH2_LAG>(); arrive_full(c - CH2_LAG); }
         }
         for (int c = max(0, n_chunks - CH2_LAG); c < n_chunks; c++) { tc::cp_async_wait<0>(); arrive_full(c); }
-    } else if (warp == 2) {
+    } else if (warp == 4) {
         // ---------------- MMA issuer ----------------
         const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+        mbar_wait(&bar_g, 0u);                                       // G has landed
         for (int t = 0; t < n_my_tiles; t++) {
             const int buf = t & 1;
             if (t >= 2) mbar_wait(&bar_acc_empty[buf], (uint32_t)(((t >> 1) - 1) & 1));      // the epilogue has drained this buffer
@@ -302,21 +332,49 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
-        // ---------------- epilogue: TMEM lane = output time; warpgroup eg takes the blocks q = eg, eg + 2, .. of 8 channel slots ----------------
-        const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2, row = ew * 32 + lane;
+    } else {
+        // ---------------- epilogue (warps 5-12): TMEM lane = output time, a warp reads the lane quarter warp % 4; the two warps
+        // of a quarter (eg = 0, 1) take the blocks q = eg, eg + 2, .. of 8 channel slots ----------------
+        const int ew = warp & 3, eg = (warp - 5) >> 2, row = ew * 32 + lane;
         int n_valid = 0;
         for (int s = 0; s < CH_SLOTS; s++) if (s_meta[s].z != 0xffffffffu) n_valid = s + 1;
         const int n_q = (n_valid + 7) / 8;
         const int q_last = (n_q - 1 - eg >= 0) ? eg + 2 * ((n_q - 1 - eg) / 2) : -1;     // this warpgroup's last block (-1: none)
+        const uint32_t tile_step = s_meta[lane].y << 7;                                  // lane = slot: phase step per tile
+        const bool need_F = __any_sync(0xffffffffu, tile_step != 0u && s_meta[lane].z != 0xffffffffu);
+        float2* my_F = s_F[warp - 5];
+        const uint32_t my_T = smem_u32(sT + row);                    // explicit ld.shared / st.global below: both pointers come
+        auto ld_T = [&](int slot) {                                  // out of shared memory and would otherwise be generic
+            float2 v;
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(my_T + (uint32_t)(slot * CH_ROWS * (int)sizeof(float2))));
+            return v;
+        };
+        const float2 w0 = make_float2(p.w0, p.w0), w1 = make_float2(p.w1, p.w1), w2 = make_float2(p.w2, p.w2);
         auto release = [&](int buf) {                    // this warp has finished reading accumulator buffer buf
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_acc_empty[buf])) : "memory");
         };
+        // one slot: digit planes -> complex sample (exact integer offsets first, then the same FMA order as the FP32
+        // kernel's reference sum), rotated by (cs, sn)
+        auto finish = [&](int slot, uint32_t ar0, uint32_t ai0, uint32_t ar1, uint32_t ai1, uint32_t ar2, uint32_t ai2, float2 rot, int i_out) {
+            const int2 o0 = s_off2[0][slot], o1 = s_off2[1][slot], o2 = s_off2[2][slot];
+            const float2 v0 = make_float2((float)((int)ar0 - o0.x), (float)((int)ai0 - o0.y));
+            const float2 v1 = make_float2((float)((int)ar1 - o1.x), (float)((int)ai1 - o1.y));
+            const float2 v2 = make_float2((float)((int)ar2 - o2.x), (float)((int)ai2 - o2.y));
+            const float2 y = __ffma2_rn(v0, w0, __ffma2_rn(v1, w1, __fmul2_rn(v2, w2)));
+            float2* dst = s_outp[slot];
+            if (dst) asm volatile("st.global.v2.f32 [%0], {%1, %2};" :: "l"(dst + i_out), "f"(fmaf(y.x, rot.x, y.y * rot.y)), "f"(fmaf(y.y, rot.x, -y.x * rot.y)) : "memory");
+        };
         for (int t = 0; t < n_my_tiles; t++) {
             const int buf = t & 1;
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            if (need_F) {                                // lane = slot: exp(-j 2 pi tile_step tile / 2^32)
+                const float tt = (float)(int)(tile_step * (uint32_t)tile) * 2.3283064365386963e-10f;
+                __syncwarp();
+                my_F[lane] = make_float2(fm::chebyshev_sine(0.25f - fabsf(tt)), fm::chebyshev_sine(tt));
+                __syncwarp();
+            }
             mbar_wait(&bar_acc_full[buf], (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             if (q_last < 0) release(buf);
@@ -327,26 +385,21 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
                 tmem_ld16(lane_addr + 0 * CH_NG + q * 16, a0);
                 tmem_ld16(lane_addr + 1 * CH_NG + q * 16, a1);
                 tmem_ld16(lane_addr + 2 * CH_NG + q * 16, a2);
+                float2 rot[8];                               // the 8 rotations of this block, loaded under the TMEM loads' latency
+#pragma unroll
+                for (int s = 0; s < 8; s++) rot[s] = ld_T(q * 8 + s);
+                if (need_F) {
+#pragma unroll
+                    for (int s = 0; s < 8; s++) {
+                        const float2 T = rot[s], F = my_F[q * 8 + s];          // (cos, sin) of the row and tile parts
+                        rot[s] = make_float2(fmaf(T.x, F.x, -T.y * F.y), fmaf(T.y, F.x, T.x * F.y));
+                    }
+                }
                 tmem_ld_wait();
                 if (q == q_last) release(buf);               // hand the buffer back before the arithmetic
 #pragma unroll
-                for (int s = 0; s < 8; s++) {                // branch-free: 8 independent channels; an empty slot only skips its store
-                    const int slot = q * 8 + s;
-                    const uint4 m = s_meta[slot];
-                    const int c0 = 2 * slot, c1 = 2 * slot + 1;
-                    const float r0 = (float)((int)a0[2 * s] - s_off[c0]), r1 = (float)((int)a1[2 * s] - s_off[CH_NG + c0]),
-                                r2 = (float)((int)a2[2 * s] - s_off[2 * CH_NG + c0]);
-                    const float q0 = (float)((int)a0[2 * s + 1] - s_off[c1]), q1 = (float)((int)a1[2 * s + 1] - s_off[CH_NG + c1]),
-                                q2 = (float)((int)a2[2 * s + 1] - s_off[2 * CH_NG + c1]);
-                    const float re = fmaf(r0, p.w0, fmaf(r1, p.w1, r2 * p.w2));
-                    const float im = fmaf(q0, p.w0, fmaf(q1, p.w1, q2 * p.w2));
-                    const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)i_out;            // exact mod 2^32
-                    // exp(-j 2 pi t), t = ph / 2^32 in [-1/2, 1/2): the chain's polynomial sine (dsp/simd/chebyshev_sine.h,
-                    // 1.5e-7 max error) -- sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)
-                    const float tt = (float)(int)ph * 2.3283064365386963e-10f;
-                    const float sn = fm::chebyshev_sine(tt), cs = fm::chebyshev_sine(0.25f - fabsf(tt));
-                    if (m.z != 0xffffffffu) p.out[(size_t)m.z * p.n_out + i_out] = make_float2(fmaf(re, cs, im * sn), fmaf(im, cs, -re * sn));
-                }
+                for (int s = 0; s < 8; s++)                  // branch-free: 8 independent channels; an empty slot only skips its store
+                    finish(q * 8 + s, a0[2 * s], a0[2 * s + 1], a1[2 * s], a1[2 * s + 1], a2[2 * s], a2[2 * s + 1], rot[s], i_out);
             }
         }
     }
@@ -493,7 +546,7 @@ int chan_upload_taps(fmgpu_chan* h) {
 }
 
 size_t chan_mma_smem(const fmgpu_chan* h) { return (size_t)h->n_kchunks * CH_PLANES * CH_BSUB_BYTES + 2 * CH_A_BYTES + 1024; }
-size_t chan_mma2_smem(const fmgpu_chan* h) { return (size_t)h->n_kchunks * CH_PLANES * CH_BSUB_BYTES + CH2_NSTG * CH_A_BYTES + 1024; }
+size_t chan_mma2_smem(const fmgpu_chan* h) { return (size_t)h->n_kchunks * CH_PLANES * CH_BSUB_BYTES + CH2_NSTG * CH_A_BYTES + CH_SLOTS * CH_ROWS * sizeof(float2) + 1024; }
 
 // staged buffer already holds history ++ block; writes slot, then rolls the history
 int chan_run(fmgpu_chan* h, int slot) {
