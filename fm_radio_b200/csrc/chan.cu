@@ -197,28 +197,30 @@ chan_mma_i8(const __grid_constant__ ChanMmaParams p)
 // The kernel above is synchronous: every thread copies its row of a K chunk through registers, the CTA meets at
 // a barrier, one thread issues the MMAs, and the epilogue (32 x sincospif per thread) runs with the tensor pipe
 // idle -- ncu: tensor pipe 4 % active, 61 us per launch for 100 stations x 65536 outputs, top stall
-// long_scoreboard.  This one is the classic three-role pipeline, one CTA of 416 threads per SM:
+// long_scoreboard.  This one is the classic three-role pipeline, one CTA of 672 threads per SM:
 //   warps 0-3  PRODUCERS   im2col of the raw capture into a ring of CH2_NSTG K-chunk stages with cp.async (8-byte
 //                          copies: window rows are 2 D = 40 bytes apart, so they are 8- but not 16-byte aligned,
 //                          which also rules out TMA), two chunks in flight ahead of the one being released;
 //   warp  4    MMA ISSUER  one elected lane: 4 tcgen05.mma (K steps; N = 192 = 3 digit planes) per chunk into one of TWO
 //                          accumulator buffers in TMEM, tcgen05.commit frees the stage / publishes the tile;
-//   warps 5-12 EPILOGUE    two warpgroups taking alternate blocks of 8 channel slots: tcgen05.ld of the finished buffer
+//   warps 5-20 EPILOGUE    four warps per TMEM lane quarter, one block of 8 channel slots each: tcgen05.ld of the finished buffer
 //                          while the next tile's MMAs run; branch-free per-channel arithmetic (8 independent channels in
 //                          flight per thread, packed FP32 for the (re, im) pair); the channel rotation exp(-j ph) comes
 //                          from a [slot][row] table in shared memory built once per launch with the chain's own
-//                          polynomial sine, times one factor per (tile, slot) that is 1 on the fs_out / 128 raster.
+//                          polynomial sine, times one factor per (tile, slot) that is +-1 on the fs_out / 256 raster.
 //                          (History: one epilogue warp per SM sub-partition and a branch per channel ran at IPC 0.2
 //                          and bounded the kernel, 51 us; two polynomial sines per output sample, 41.8 us with the
 //                          epilogue issuing 2/3 of the kernel's 18.6 M warp instructions -- ncu, profiles/r2n.)
 // The three digit planes of G sit side by side in shared memory, so each K step is ONE tcgen05.mma of N = 192 (100 clocks
 // measured, tools/umma_rate.cu) instead of three of N = 64 (3 x 50: small-N MMAs have a ~50-clock floor).
 // All hand-offs are mbarriers (full / empty per stage, acc_full / acc_empty per accumulator buffer).
-constexpr int CH2_THREADS = 416;                // 4 producer warps, 1 MMA-issuer warp, 8 epilogue warps
+constexpr int CH2_EPI_WARPS = 16;               // 4 per TMEM lane quarter: warp (quarter, eg) owns the block eg of 8 channel slots
+constexpr int CH2_THREADS = 32 * (5 + CH2_EPI_WARPS);   // 4 producer warps, 1 MMA-issuer warp, 16 epilogue warps = 672 threads
 constexpr int CH2_NSTG = 6;                     // 6 x 16 KB ring + 72 KB of G + 32 KB rotation table = 200 KB of shared memory: one CTA per SM
 constexpr int CH2_TMEM_COLS = 512;              // 2 accumulator buffers, 192 of 256 columns used in each
 constexpr int CH2_LAG = 2;                      // chunks of cp.async in flight behind the producers' issue point
 
+template <bool NEED_F>                          // NEED_F: some channel's phase advances per 128-output tile by something other than 0 or 1/2 turn
 __global__ void __launch_bounds__(CH2_THREADS, 1)
 chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
 {
@@ -232,7 +234,7 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     __shared__ int2 s_off2[CH_PLANES][CH_SLOTS];                    // (re, im) column offsets of each slot, per digit plane
     __shared__ uint4 s_meta[CH_SLOTS];
     __shared__ float2* s_outp[CH_SLOTS];                            // output row of each slot's channel (nullptr: empty slot)
-    __shared__ float2 s_F[8][CH_SLOTS];                             // per epilogue warp: this tile's phase factor of each slot
+    __shared__ float2 s_F[CH2_EPI_WARPS][8];                             // per epilogue warp: this tile's phase factor of each slot
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform
@@ -247,8 +249,8 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     // Rotation table: the channel rotation of output i = 128 tile + row is exp(-j 2 pi ph / 2^32), ph = inc n_newest0 +
     // inc D i (exact mod 2^32).  T[slot][row] holds the row part (tile 0) by the chain's polynomial sine
     // (dsp/simd/chebyshev_sine.h, 1.5e-7: sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)); the tile part
-    // exp(-j 2 pi 128 tile inc D / 2^32) is one factor per (tile, slot), and is exactly 1 when 128 inc D = 0 mod 2^32
-    // (centres on the fs_out / 128 raster: the FM band's 200 kHz raster at 1.024 MS/s is).
+    // exp(-j 2 pi 128 tile inc D / 2^32) is one factor per (tile, slot), and is exactly +-1 when 128 inc D = 0 mod 2^31
+    // (centres on the fs_out / 256 = 4 kHz raster: the FM band's 200 kHz raster and its half points at 1.024 MS/s are).
     for (int i = tid; i < CH_SLOTS * CH_ROWS; i += CH2_THREADS) {
         const uint4 m = p.meta[(size_t)group * CH_SLOTS + (i >> 7)];
         const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)(i & (CH_ROWS - 1));
@@ -257,7 +259,7 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     }
     if (tid == 0) {
         for (int i = 0; i < CH2_NSTG; i++) { mbar_init(&bar_full[i], 4); mbar_init(&bar_empty[i], 1); }   // full: one arrival per producer warp
-        for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }  // acc_empty: one arrival per epilogue warp
+        for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], CH2_EPI_WARPS); }  // acc_empty: one arrival per epilogue warp
         mbar_init(&bar_g, 1);
         tc::mbar_init_fence();
         const uint32_t g_bytes = (uint32_t)(p.n_kchunks * CH_PLANES * CH_BSUB_BYTES);
@@ -333,22 +335,21 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
             }
         }
     } else {
-        // ---------------- epilogue (warps 5-12): TMEM lane = output time, a warp reads the lane quarter warp % 4; the two warps
-        // of a quarter (eg = 0, 1) take the blocks q = eg, eg + 2, .. of 8 channel slots ----------------
+        // ---------------- epilogue (warps 5-20): TMEM lane = output time, a warp reads the lane quarter warp % 4; the four
+        // warps of a quarter (eg = 0..3) each own one block of 8 channel slots, so the rotation table entries of a thread
+        // (its row x its 8 slots) are loaded ONCE and stay in registers ----------------
         const int ew = warp & 3, eg = (warp - 5) >> 2, row = ew * 32 + lane;
-        int n_valid = 0;
-        for (int s = 0; s < CH_SLOTS; s++) if (s_meta[s].z != 0xffffffffu) n_valid = s + 1;
-        const int n_q = (n_valid + 7) / 8;
-        const int q_last = (n_q - 1 - eg >= 0) ? eg + 2 * ((n_q - 1 - eg) / 2) : -1;     // this warpgroup's last block (-1: none)
-        const uint32_t tile_step = s_meta[lane].y << 7;                                  // lane = slot: phase step per tile
-        const bool need_F = __any_sync(0xffffffffu, tile_step != 0u && s_meta[lane].z != 0xffffffffu);
+        static_assert(CH2_EPI_WARPS / 4 * 8 == CH_SLOTS, "one block of 8 slots per epilogue warp");
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 8; s++) any |= s_meta[eg * 8 + s].z != 0xffffffffu;
+        float2 T[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) T[s] = sT[(eg * 8 + s) * CH_ROWS + row];
+        const uint32_t tile_step = s_meta[eg * 8 + (lane & 7)].y << 7;                 // lane & 7 = slot of the block: phase step per tile
+        // half-turn steps (centres on the raster's half points: the 100-station plan is) only flip the sign on odd tiles
+        const uint32_t half_mask = __ballot_sync(0xffffffffu, tile_step == 0x80000000u) & 0xffu;
         float2* my_F = s_F[warp - 5];
-        const uint32_t my_T = smem_u32(sT + row);                    // explicit ld.shared / st.global below: both pointers come
-        auto ld_T = [&](int slot) {                                  // out of shared memory and would otherwise be generic
-            float2 v;
-            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(my_T + (uint32_t)(slot * CH_ROWS * (int)sizeof(float2))));
-            return v;
-        };
         const float2 w0 = make_float2(p.w0, p.w0), w1 = make_float2(p.w1, p.w1), w2 = make_float2(p.w2, p.w2);
         auto release = [&](int buf) {                    // this warp has finished reading accumulator buffer buf
             tc_fence_before();
@@ -356,7 +357,7 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_acc_empty[buf])) : "memory");
         };
         // one slot: digit planes -> complex sample (exact integer offsets first, then the same FMA order as the FP32
-        // kernel's reference sum), rotated by (cs, sn)
+        // kernel's reference sum), rotated by (cs, sn); the store is explicit st.global (the pointer comes out of shared memory)
         auto finish = [&](int slot, uint32_t ar0, uint32_t ai0, uint32_t ar1, uint32_t ai1, uint32_t ar2, uint32_t ai2, float2 rot, int i_out) {
             const int2 o0 = s_off2[0][slot], o1 = s_off2[1][slot], o2 = s_off2[2][slot];
             const float2 v0 = make_float2((float)((int)ar0 - o0.x), (float)((int)ai0 - o0.y));
@@ -369,37 +370,41 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
         for (int t = 0; t < n_my_tiles; t++) {
             const int buf = t & 1;
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            if (need_F) {                                // lane = slot: exp(-j 2 pi tile_step tile / 2^32)
+            if (NEED_F) {                                // lanes 0-7: exp(-j 2 pi tile_step tile / 2^32) of the block's slots
                 const float tt = (float)(int)(tile_step * (uint32_t)tile) * 2.3283064365386963e-10f;
                 __syncwarp();
-                my_F[lane] = make_float2(fm::chebyshev_sine(0.25f - fabsf(tt)), fm::chebyshev_sine(tt));
+                if (lane < 8) my_F[lane] = make_float2(fm::chebyshev_sine(0.25f - fabsf(tt)), fm::chebyshev_sine(tt));
                 __syncwarp();
             }
             mbar_wait(&bar_acc_full[buf], (uint32_t)((t >> 1) & 1));
             tc_fence_after();
-            if (q_last < 0) release(buf);
+            if (!any) { release(buf); continue; }
             const int i_out = tile * CH_ROWS + row;
             const uint32_t lane_addr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256);
-            for (int q = eg; q < n_q; q += 2) {
-                uint32_t a0[16], a1[16], a2[16];
-                tmem_ld16(lane_addr + 0 * CH_NG + q * 16, a0);
-                tmem_ld16(lane_addr + 1 * CH_NG + q * 16, a1);
-                tmem_ld16(lane_addr + 2 * CH_NG + q * 16, a2);
-                float2 rot[8];                               // the 8 rotations of this block, loaded under the TMEM loads' latency
+            // two halves of 4 slots (8 columns per digit plane): 24 accumulator registers live instead of 48
 #pragma unroll
-                for (int s = 0; s < 8; s++) rot[s] = ld_T(q * 8 + s);
-                if (need_F) {
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t a0[8], a1[8], a2[8];
+                tc::tmem_ld8(lane_addr + 0 * CH_NG + eg * 16 + hf * 8, a0);
+                tc::tmem_ld8(lane_addr + 1 * CH_NG + eg * 16 + hf * 8, a1);
+                tc::tmem_ld8(lane_addr + 2 * CH_NG + eg * 16 + hf * 8, a2);
+                float2 rot[4];
 #pragma unroll
-                    for (int s = 0; s < 8; s++) {
-                        const float2 T = rot[s], F = my_F[q * 8 + s];          // (cos, sin) of the row and tile parts
-                        rot[s] = make_float2(fmaf(T.x, F.x, -T.y * F.y), fmaf(T.y, F.x, T.x * F.y));
+                for (int s4 = 0; s4 < 4; s4++) {
+                    const int s = hf * 4 + s4;
+                    if (NEED_F) {
+                        const float2 F = my_F[s];            // (cos, sin) of the tile part
+                        rot[s4] = make_float2(fmaf(T[s].x, F.x, -T[s].y * F.y), fmaf(T[s].y, F.x, T[s].x * F.y));
+                    } else {
+                        const uint32_t sg = (((tile & 1) ? half_mask : 0u) << (31 - s)) & 0x80000000u;
+                        rot[s4] = make_float2(__uint_as_float(__float_as_uint(T[s].x) ^ sg), __uint_as_float(__float_as_uint(T[s].y) ^ sg));
                     }
                 }
                 tmem_ld_wait();
-                if (q == q_last) release(buf);               // hand the buffer back before the arithmetic
+                if (hf == 1) release(buf);                   // hand the buffer back before the arithmetic
 #pragma unroll
-                for (int s = 0; s < 8; s++)                  // branch-free: 8 independent channels; an empty slot only skips its store
-                    finish(q * 8 + s, a0[2 * s], a0[2 * s + 1], a1[2 * s], a1[2 * s + 1], a2[2 * s], a2[2 * s + 1], rot[s], i_out);
+                for (int s4 = 0; s4 < 4; s4++)               // branch-free: independent channels; an empty slot only skips its store
+                    finish(eg * 8 + hf * 4 + s4, a0[2 * s4], a0[2 * s4 + 1], a1[2 * s4], a1[2 * s4 + 1], a2[2 * s4], a2[2 * s4 + 1], rot[s4], i_out);
             }
         }
     }
@@ -475,6 +480,7 @@ struct fmgpu_chan {
     std::vector<cudaEvent_t> ev_done;
     float2* d_g = nullptr; uint2* d_meta32 = nullptr;
     int8_t* d_bimg = nullptr; int* d_offs = nullptr; uint4* d_meta = nullptr;
+    bool need_tile_factor = false;           // some channel's rotation does not repeat every CH_ROWS outputs
     float w0 = 0, w1 = 0, w2 = 0;
     float2* h_out = nullptr;                 // pinned mirror for the host entry point
 };
@@ -519,6 +525,7 @@ int chan_upload_taps(fmgpu_chan* h) {
     for (int c = 0; c < C; c++) {
         const int grp = c / h->per_group, slot = c % h->per_group;
         meta[(size_t)grp * CH_SLOTS + slot] = make_uint4(h->inc[c], (uint32_t)((uint64_t)h->inc[c] * (uint64_t)h->D), (uint32_t)c, 0);
+        if (((uint32_t)((uint64_t)h->inc[c] * (uint64_t)h->D * (uint64_t)CH_ROWS) & 0x7fffffffu) != 0u) h->need_tile_factor = true;   // centre off the fs_out / 256 raster
         for (int K = 0; K < KB; K++) {
             const int k = K >> 1, comp = K & 1;
             // column 2 slot (re): gr * xr - gi * xi; column 2 slot + 1 (im): gi * xr + gr * xi
@@ -570,7 +577,8 @@ int chan_run(fmgpu_chan* h, int slot) {
             chan_mma_i8<<<dim3(per_group, h->n_groups), 128, chan_mma_smem(h), h->st>>>(p);
         } else {
             const int per_group = std::max(1, std::min(p.n_tiles, n_sm / h->n_groups));
-            chan_mma_i8_pipelined<<<dim3(per_group, h->n_groups), CH2_THREADS, chan_mma2_smem(h), h->st>>>(p);
+            if (h->need_tile_factor) chan_mma_i8_pipelined<true><<<dim3(per_group, h->n_groups), CH2_THREADS, chan_mma2_smem(h), h->st>>>(p);
+            else                     chan_mma_i8_pipelined<false><<<dim3(per_group, h->n_groups), CH2_THREADS, chan_mma2_smem(h), h->st>>>(p);
         }
     } else {
         ChanFp32Params p{};
@@ -670,7 +678,10 @@ int fmgpu_chan_create(const fmgpu_chan_config* cfg, const double* centre_hz, fmg
         A(cudaMalloc((void**)&h->d_meta, (size_t)h->n_groups * CH_SLOTS * sizeof(uint4)));
         A(cudaFuncSetAttribute(chan_mma_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma_smem(h)));
         if (chan_mma2_smem(h) <= 227 * 1024)
-            A(cudaFuncSetAttribute(chan_mma_i8_pipelined, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma2_smem(h)));
+        {
+            A(cudaFuncSetAttribute(chan_mma_i8_pipelined<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma2_smem(h)));
+            A(cudaFuncSetAttribute(chan_mma_i8_pipelined<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chan_mma2_smem(h)));
+        }
     }
     {
         const size_t smem = (size_t)(CF_TILE * D + NN - D) * sizeof(float2);
