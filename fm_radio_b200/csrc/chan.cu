@@ -280,33 +280,48 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
 
     if (warp < 4) {
         // ---------------- producers: row 32 warp + lane of every tile ----------------
-        auto arrive_full = [&](int c) {              // this warp's copies of chunk c have landed
+        auto arrive_full = [&](int stg) {            // this warp's copies into ring stage stg have landed
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_full[c % CH2_NSTG])) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_full[stg])) : "memory");
         };
-        for (int c = 0; c < n_chunks; c++) {
-            const int stage = c % CH2_NSTG, use = c / CH2_NSTG;
-            const int tile = (int)blockIdx.x + (c / p.n_kchunks) * (int)gridDim.x, kc = c % p.n_kchunks;
-            if (use > 0) mbar_wait(&bar_empty[stage], (uint32_t)((use - 1) & 1));
-            {
-                // one instruction copies two whole window rows (16 lanes x 8 bytes each): the rows start 2 D bytes apart, so
-                // a warp reads 2 D + 128 contiguous bytes (6 sectors) and writes two full 128-byte swizzle rows (2 wavefronts);
-                // with one row per lane (stride 2 D) the same instruction touched 32 sectors and wrote with 4-way bank conflicts
-                const int h = lane >> 4, j = lane & 15;
-                const uint8_t* src = p.iq + (size_t)(tile * CH_ROWS + 32 * warp + h) * p.row_bytes + kc * CH_KCHUNK + 8 * j;
-                const uint32_t dst = smem_u32(sA + stage * CH_A_BYTES + 4 * warp * 1024) + (uint32_t)((j & 1) << 3);
+        // One instruction copies two whole window rows (16 lanes x 8 bytes each): the rows start 2 D bytes apart, so a warp
+        // reads 2 D + 128 contiguous bytes (6 sectors) and writes two full 128-byte swizzle rows (2 wavefronts); with one
+        // row per lane (stride 2 D) the same instruction touched 32 sectors and wrote with 4-way bank conflicts.
+        // Everything that does not change from chunk to chunk is computed here (the loop used to spend 138 of its 154
+        // instructions per chunk on divisions and address arithmetic, and the producers bounded the kernel -- ncu source view).
+        const int h = lane >> 4, j = lane & 15;
+        uint32_t dsto[4];                                // swizzled offset of row (2 i + h) & 7 within its 8-row group, i = 0..3
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int r7 = ((2 * i) & 7) + h;                            // (row & 7); row = 32 warp + 2 i + h
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
-                                 :: "r"(dst + (uint32_t)(((2 * i) >> 3) * 1024 + r7 * 128 + (((j >> 1) ^ r7) << 4))), "l"(src + (size_t)(2 * i) * p.row_bytes));
+        for (int i = 0; i < 4; i++) { const int r7 = 2 * i + h; dsto[i] = (uint32_t)(r7 * 128 + (((j >> 1) ^ r7) << 4) + ((j & 1) << 3)); }
+        const uint32_t dst0 = smem_u32(sA + 4 * warp * 1024);
+        const size_t rb2 = 2 * (size_t)p.row_bytes, tile_stride = (size_t)gridDim.x * CH_ROWS * p.row_bytes;
+        const uint8_t* tile_src = p.iq + (size_t)((int)blockIdx.x * CH_ROWS + 32 * warp + h) * p.row_bytes + 8 * j;
+        int stage = 0, lag_stage = 0, c = 0;
+        uint32_t empty_parity = 1u;                      // parity of the "previous use released" phase; first pass over the ring: no wait
+        bool first_pass = true;
+        for (int t = 0; t < n_my_tiles; t++, tile_src += tile_stride) {
+            for (int kc = 0; kc < p.n_kchunks; kc++, c++) {
+                if (!first_pass) mbar_wait(&bar_empty[stage], empty_parity);
+                const uint8_t* src = tile_src + kc * CH_KCHUNK;
+                const uint32_t dst = dst0 + (uint32_t)(stage * CH_A_BYTES);
+#pragma unroll
+                for (int i = 0; i < 16; i++, src += rb2)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + (uint32_t)((i >> 2) * 1024) + dsto[i & 3]), "l"(src));
+                tc::cp_async_commit();
+                if (++stage == CH2_NSTG) { stage = 0; empty_parity ^= 1u; first_pass = false; }
+                if (c >= CH2_LAG) {
+                    tc::cp_async_wait<CH2_LAG>();
+                    arrive_full(lag_stage);
+                    if (++lag_stage == CH2_NSTG) lag_stage = 0;
                 }
             }
-            tc::cp_async_commit();
-            if (c >= CH2_LAG) { tc::cp_async_wait<CH2_LAG>(); arrive_full(c - CH2_LAG); }
         }
-        for (int c = max(0, n_chunks - CH2_LAG); c < n_chunks; c++) { tc::cp_async_wait<0>(); arrive_full(c); }
+        for (int k = max(0, n_chunks - CH2_LAG); k < n_chunks; k++) {
+            tc::cp_async_wait<0>();
+            arrive_full(lag_stage);
+            if (++lag_stage == CH2_NSTG) lag_stage = 0;
+        }
     } else if (warp == 4) {
         // ---------------- MMA issuer ----------------
         const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
