@@ -239,24 +239,7 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform
     const int group = blockIdx.y;
-    // G (72 KB) arrives by bulk copies issued after the barrier initialisation below; only the MMA issuer waits for it
-    for (int i = tid; i < CH_PLANES * CH_NG; i += CH2_THREADS) ((int*)s_off2)[i] = p.offs[(size_t)group * CH_PLANES * CH_NG + i];
-    if (tid < CH_SLOTS) {
-        const uint4 m = p.meta[(size_t)group * CH_SLOTS + tid];
-        s_meta[tid] = m;
-        s_outp[tid] = m.z != 0xffffffffu ? p.out + (size_t)m.z * p.n_out : nullptr;
-    }
-    // Rotation table: the channel rotation of output i = 128 tile + row is exp(-j 2 pi ph / 2^32), ph = inc n_newest0 +
-    // inc D i (exact mod 2^32).  T[slot][row] holds the row part (tile 0) by the chain's polynomial sine
-    // (dsp/simd/chebyshev_sine.h, 1.5e-7: sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)); the tile part
-    // exp(-j 2 pi 128 tile inc D / 2^32) is one factor per (tile, slot), and is exactly +-1 when 128 inc D = 0 mod 2^31
-    // (centres on the fs_out / 256 = 4 kHz raster: the FM band's 200 kHz raster and its half points at 1.024 MS/s are).
-    for (int i = tid; i < CH_SLOTS * CH_ROWS; i += CH2_THREADS) {
-        const uint4 m = p.meta[(size_t)group * CH_SLOTS + (i >> 7)];
-        const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)(i & (CH_ROWS - 1));
-        const float tt = (float)(int)ph * 2.3283064365386963e-10f;
-        sT[i] = make_float2(fm::chebyshev_sine(0.25f - fabsf(tt)), fm::chebyshev_sine(tt));      // (cos, sin)
-    }
+    // G (72 KB) arrives by bulk copies issued right after the barrier initialisation; only the MMA issuer waits for it
     if (tid == 0) {
         for (int i = 0; i < CH2_NSTG; i++) { mbar_init(&bar_full[i], 4); mbar_init(&bar_empty[i], 1); }   // full: one arrival per producer warp
         for (int i = 0; i < 2; i++) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], CH2_EPI_WARPS); }  // acc_empty: one arrival per epilogue warp
@@ -268,6 +251,12 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
         for (uint32_t o = 0; o < g_bytes; o += CH_BSUB_BYTES)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(smem_u32(sB + o)), "l"(src + o), "r"((uint32_t)CH_BSUB_BYTES), "r"(smem_u32(&bar_g)) : "memory");
+    }
+    for (int i = tid; i < CH_PLANES * CH_NG; i += CH2_THREADS) ((int*)s_off2)[i] = p.offs[(size_t)group * CH_PLANES * CH_NG + i];
+    if (tid < CH_SLOTS) {
+        const uint4 m = p.meta[(size_t)group * CH_SLOTS + tid];
+        s_meta[tid] = m;
+        s_outp[tid] = m.z != 0xffffffffu ? p.out + (size_t)m.z * p.n_out : nullptr;
     }
     if (warp == 0) tc::tmem_alloc(&s_tmem, CH2_TMEM_COLS);
     fence_async_smem();
@@ -355,6 +344,19 @@ chan_mma_i8_pipelined(const __grid_constant__ ChanMmaParams p)
         // (its row x its 8 slots) are loaded ONCE and stay in registers ----------------
         const int ew = warp & 3, eg = (warp - 5) >> 2, row = ew * 32 + lane;
         static_assert(CH2_EPI_WARPS / 4 * 8 == CH_SLOTS, "one block of 8 slots per epilogue warp");
+        // Rotation table, built by the epilogue warps while the producers and the MMA issuer already run: the channel
+        // rotation of output i = 128 tile + row is exp(-j 2 pi ph / 2^32), ph = inc n_newest0 + inc D i (exact mod 2^32).
+        // T[slot][row] holds the row part (tile 0) by the chain's polynomial sine (dsp/simd/chebyshev_sine.h, 1.5e-7:
+        // sin(2 pi t) = S(t), cos(2 pi t) = S(1/4 - |t|)); the tile part exp(-j 2 pi 128 tile inc D / 2^32) is one factor
+        // per (tile, slot), and is exactly +-1 when 128 inc D = 0 mod 2^31 (centres on the fs_out / 256 = 4 kHz raster:
+        // the FM band's 200 kHz raster and its half points at 1.024 MS/s are).
+        for (int i = tid - 160; i < CH_SLOTS * CH_ROWS; i += 32 * CH2_EPI_WARPS) {
+            const uint4 m = s_meta[i >> 7];
+            const uint32_t ph = m.x * p.n_newest0 + m.y * (uint32_t)(i & (CH_ROWS - 1));
+            const float tt = (float)(int)ph * 2.3283064365386963e-10f;
+            sT[i] = make_float2(fm::chebyshev_sine(0.25f - fabsf(tt)), fm::chebyshev_sine(tt));      // (cos, sin)
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * CH2_EPI_WARPS) : "memory");
         bool any = false;
 #pragma unroll
         for (int s = 0; s < 8; s++) any |= s_meta[eg * 8 + s].z != 0xffffffffu;
