@@ -190,7 +190,8 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
         }
     };
 
-    auto epilogue = [&](const TileRef& r, int buf, int par) {
+    // after_sync runs right after the epilogue's CTA barrier, before the stores (NACC == 1: the next-but-one tile's copies)
+    auto epilogue = [&](const TileRef& r, int buf, int par, auto&& after_sync) {
         const int s = r.s, row0 = r.row0;
         const int n_valid = min(K1T_ROWS, p.n_rows - row0);
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * 128 + 16 * half);
@@ -216,6 +217,7 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
         // previous row / of the row before the tile
         if (half == 0) s_mid[par][row] = th[3].y; else s_last[par][row] = th[3].y;
         __syncthreads();
+        after_sync();
         const float th_before = half ? s_mid[par][row] : (row == 0 ? s_thprev[buf] : s_last[par][row - 1]);
         if (row >= n_valid) return;
         if (half == 1 && row0 + row == p.n_rows - 1) p.theta_out[s] = th[3].y;     // the block's last angle -> next block
@@ -228,14 +230,20 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
         dst[1] = make_float4(d2.x, d2.y, d3.x, d3.y);
     };
 
+    // NACC == 2: tile it + NS - 1 is staged in iteration it, into the slot of tile it - 1.
+    // NACC == 1: the slot of tile `it` is dead as soon as its MMAs have completed and every warp has left pre_epilogue, i.e.
+    // right after the epilogue's CTA barrier -- tile it + NS is staged THERE, so its bytes have the rest of this epilogue plus
+    // a whole iteration to arrive (staged at the top of the next iteration they had half of that, and ncu's source view
+    // showed 18 % of the kernel's warp time waiting for them).
+    constexpr int PRE = NACC == 2 ? K1T_NS - 1 : K1T_NS;                          // tiles staged ahead of the loop
     TileRef cur = tile_ref((int)blockIdx.x), pre = cur, prev = cur;
 #pragma unroll
-    for (int k = 0; k < K1T_NS - 1; k++) { stage(pre, k); advance(pre); }
+    for (int k = 0; k < PRE; k++) { stage(pre, k); advance(pre); }
     const bool mma_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;                // warp-uniform
     int it = 0;
     for (; cur.tile < p.n_tiles; it++) {
         const int buf = NACC == 2 ? (it & 1) : 0, slot = it % K1T_NS;
-        tc::cp_async_wait<K1T_NS - 2>();             // all but the newest NS - 2 groups have landed: tile `it` is in place
+        tc::cp_async_wait<PRE - 1>();                // all but the newest PRE - 1 groups have landed: tile `it` is in place
         tc::fence_async_smem();
         __syncthreads();                             // ... for every thread's copies; everyone has left iteration it - 1
         if (mma_warp && tc::elect_one()) {
@@ -260,13 +268,11 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
             }
             stage(pre, (it + K1T_NS - 1) % K1T_NS);  // tile it + NS - 1 into the slot of tile it - 1
             advance(pre);
-            if (it >= 1) epilogue(prev, buf ^ 1, it & 1);
+            if (it >= 1) epilogue(prev, buf ^ 1, it & 1, [] {});
         } else {
-            stage(pre, (it + K1T_NS - 1) % K1T_NS);  // into the slot of tile it - 1 (its MMAs were awaited one iteration ago)
-            advance(pre);
             tc::mbar_wait(&bar_acc[0], (uint32_t)(it & 1));
             tc::fence_after();
-            epilogue(cur, 0, it & 1);
+            epilogue(cur, 0, it & 1, [&] { stage(pre, slot); advance(pre); });   // tile it + NS into this tile's slot
         }
         prev = cur;
         advance(cur);
@@ -274,7 +280,7 @@ k1_toeplitz_i8(const uint8_t* __restrict__ iq, const uint8_t* __restrict__ hist_
     if (NACC == 2 && it >= 1) {
         tc::mbar_wait(&bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
         tc::fence_after();
-        epilogue(prev, (it - 1) & 1, it & 1);
+        epilogue(prev, (it - 1) & 1, it & 1, [] {});
     }
     tc::cp_async_wait<0>();
     tc::fence_before();
