@@ -375,6 +375,8 @@ def run_cuda_arm(args):
             "metric": "IQ MS/s demodulated stereo+RDS", "value": value, "unit": "MS/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "dtype_note": "f32 throughout, as the reference; the first FIR (K1) sums u8 samples x 24-bit fixed-point taps exactly in int32 "
+                          "(tcgen05 kind::i8, three signed digit planes) and recombines in f32 -- |tap error| <= 2^-26, not a reduced precision",
             "config": {"workload": f"{S} streams x {B}-sample u8 IQ blocks per GPU (BASELINE config 3; N GPUs = config 5 sharded by stream)",
                        "streams_per_gpu": S, "block_size": B, "pipeline_depth": demod.depth,
                        "audio_out": (f"32 kHz f32 frames + {args.audio_pcm_rate} Hz f32 and int16 PCM (K7)" if args.audio_pcm_rate
@@ -551,8 +553,11 @@ def run_wideband_arm(args):
                     "d2h_bytes_per_step": n_st * (pcm_n * 4 + sym_cap * 4 + 4), "steps": e2e_steps,
                     "api": "pinned host block -> rank 0 -> broadcast -> fmgpu_chan_feed_device; fmgpu_fetch_outputs (PCM + symbols) per rank"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"kernel": "chan_mma_i8", "bound": "tensor", "achieved": macs / (chan_ms * 1e-3) / 1e12, "peak": int8_peak,
-                         "unit": "TOP/s", "frac": macs / (chan_ms * 1e-3) / 1e12 / int8_peak, "traffic": None,
+            "roofline": {"kernel": "chan_mma_i8_pipelined", "bound": "tensor", "achieved": macs / (chan_ms * 1e-3) / 1e12, "peak": int8_peak,
+                         "unit": "TOP/s", "frac": macs / (chan_ms * 1e-3) / 1e12 / int8_peak,
+                         "traffic": (ncu_traffic().get("chan_mma_i8_pipelined", {}).get("dram_bytes") if (world == 1 and n_st == 100) else None),
+                         "traffic_source": "profiles/r2_ncu_traffic.json (ncu --set full of tools/chan_profile.py, 100 stations x 65536 outputs; "
+                                           "read from the capture, not measured by this run)",
                          "ms_per_launch": chan_ms, "ops_per_launch": macs,
                          "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (dense int8 = 2 x dense bf16 on sm_100)",
                          "note": "algorithmic ops (192 complex taps); the kernel executes 3 digit planes of them and the step is "

@@ -79,9 +79,13 @@ def traffic_json(path, out_path):
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    out = {"_source": path}
+    try:
+        out = json.load(open(out_path))                  # several captures (chain, channelizer) share one file
+    except Exception:
+        out = {}
+    out["_source"] = ", ".join(sorted(set(filter(None, [out.get("_source"), path]))))
     for r in data:
-        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("fm::", "").split("<")[0]
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("fm::", "").replace("<unnamed>::", "").split("<")[0]
         b = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             b += float(r[col[key]]) * scale.get(units[col[key]], 1.0)
