@@ -254,6 +254,10 @@ cudaError_t launch_kdbg_audio_iq(const float2* fm_out_iq, const float* pll_dt, c
 cudaError_t launch_kdbg(float2* pilot, const float* pll_state, const float* pll_dt, float2* pll_out,
                         int n, int n_streams, cudaStream_t st);
 // stand-alone polyphase decimator (dsp/polyphase_filter.h:41-64) for the dsp API surface
+cudaError_t launch_iir_seq(const float* x, float* y, int n, int K, const float* b, const float* a, float* state, int is_complex, cudaStream_t st);
+cudaError_t launch_hilbert_pack(const float* ext, const float* fir, float2* y, int n, int mid, cudaStream_t st);
+cudaError_t launch_agc_power_seq(const float2* x, int n, float* sum, cudaStream_t st);
+cudaError_t launch_agc_scale(const float2* x, float2* y, int n, float g, cudaStream_t st);
 cudaError_t launch_polyphase_ds(const float* ext, const float* taps, float* y, int M, int NN, int n_out,
                                 int is_complex, cudaStream_t st);
 

@@ -1360,6 +1360,102 @@ int fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* y
     return FMGPU_OK;
 }
 
+// ---- FIR_Filter / Hilbert_FIR_Filter / IIR_Filter / AGC_Filter stand-alone (dsp/fir_filter.h, hilbert_fir_filter.h, iir_filter.h, agc.h) ----
+struct fmgpu_dsp_filter {
+    int kind, K, is_complex;
+    std::vector<float> b, a;       // host taps (get_b / get_a)
+    std::vector<float> state;      // FIR kinds: the last K inputs; IIR: xn[K] ++ yn[K]
+    float* d_x = nullptr; float* d_y = nullptr; float* d_tmp = nullptr; float* d_coef = nullptr; float* d_state = nullptr;
+    size_t cap = 0;
+};
+
+int fmgpu_dsp_filter_create(int kind, int K, int is_complex, fmgpu_dsp_filter** out) {
+    if (!out || K < 1 || kind < FMGPU_FILTER_FIR || kind > FMGPU_FILTER_IIR) return fail(FMGPU_ERR_ARG, "filter_create: bad argument");
+    if (kind == FMGPU_FILTER_IIR && K < 2) return fail(FMGPU_ERR_ARG, "filter_create: IIR_Filter needs K >= 2 (the reference indexes yn[K-2])");
+    if (kind == FMGPU_FILTER_HILBERT && is_complex) return fail(FMGPU_ERR_ARG, "filter_create: Hilbert_FIR_Filter takes a real input");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(FMGPU_ERR_CUDA, "filter_create: no CUDA device (there is no CPU fallback)");
+    auto* f = new fmgpu_dsp_filter();
+    f->kind = kind; f->K = K; f->is_complex = is_complex ? 1 : 0;
+    const int C = f->is_complex ? 2 : 1;
+    f->b.assign(K, 0.0f);
+    if (kind == FMGPU_FILTER_IIR) f->a.assign(K, 0.0f);
+    if (kind == FMGPU_FILTER_HILBERT) fmgpu_create_fir_hilbert(f->b.data(), K);          // the constructor designs the taps (:21-22)
+    f->state.assign((size_t)(kind == FMGPU_FILTER_IIR ? 2 : 1) * K * C, 0.0f);
+    cudaError_t e = cudaMalloc((void**)&f->d_coef, 2 * (size_t)K * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_state, f->state.size() * sizeof(float));
+    if (e != cudaSuccess) { fmgpu_dsp_filter_destroy(f); return fail(FMGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = f;
+    return FMGPU_OK;
+}
+
+void fmgpu_dsp_filter_destroy(fmgpu_dsp_filter* f) {
+    if (!f) return;
+    for (float* p : { f->d_x, f->d_y, f->d_tmp, f->d_coef, f->d_state }) if (p) cudaFree(p);
+    delete f;
+}
+
+float* fmgpu_dsp_filter_get_b(fmgpu_dsp_filter* f) { return f ? f->b.data() : nullptr; }
+float* fmgpu_dsp_filter_get_a(fmgpu_dsp_filter* f) { return (f && !f->a.empty()) ? f->a.data() : nullptr; }
+int fmgpu_dsp_filter_get_K(const fmgpu_dsp_filter* f) { return f ? f->K : 0; }
+
+int fmgpu_dsp_filter_process(fmgpu_dsp_filter* f, const float* x_host, float* y_host, int n) {
+    if (!f || !x_host || !y_host || n < 0) return fail(FMGPU_ERR_ARG, "filter_process: bad argument");
+    if (n == 0) return FMGPU_OK;
+    const int C = f->is_complex ? 2 : 1, K = f->K;
+    const size_t need = ((size_t)K + n) * 2;                       // floats per buffer, enough for every kind
+    if (f->cap < need) {
+        for (float** p : { &f->d_x, &f->d_y, &f->d_tmp }) { if (*p) cudaFree(*p); *p = nullptr; CU(cudaMalloc((void**)p, need * sizeof(float))); }
+        f->cap = need;
+    }
+    CU(cudaMemcpy(f->d_coef, f->b.data(), K * sizeof(float), cudaMemcpyHostToDevice));
+    if (f->kind == FMGPU_FILTER_IIR) {
+        CU(cudaMemcpy(f->d_coef + K, f->a.data(), K * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(f->d_state, f->state.data(), f->state.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(f->d_x, x_host, (size_t)n * C * sizeof(float), cudaMemcpyHostToDevice));
+        CU(fm::launch_iir_seq(f->d_x, f->d_y, n, K, f->d_coef, f->d_coef + K, f->d_state, f->is_complex, 0));
+        CU(cudaMemcpy(y_host, f->d_y, (size_t)n * C * sizeof(float), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(f->state.data(), f->d_state, f->state.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        return FMGPU_OK;
+    }
+    // FIR kinds: ext = (last K inputs) ++ x, y[i] = sum_k b[k] ext[i + 1 + k]  (the polyphase kernel with M = 1, NN = K)
+    CU(cudaMemcpy(f->d_x, f->state.data(), (size_t)K * C * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(f->d_x + (size_t)K * C, x_host, (size_t)n * C * sizeof(float), cudaMemcpyHostToDevice));
+    if (f->kind == FMGPU_FILTER_FIR) {
+        CU(fm::launch_polyphase_ds(f->d_x, f->d_coef, f->d_y, 1, K, n, f->is_complex, 0));
+        CU(cudaMemcpy(y_host, f->d_y, (size_t)n * C * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        CU(fm::launch_polyphase_ds(f->d_x, f->d_coef, f->d_tmp, 1, K, n, 0, 0));
+        CU(fm::launch_hilbert_pack(f->d_x, f->d_tmp, (float2*)f->d_y, n, (K - 1) / 2, 0));
+        CU(cudaMemcpy(y_host, f->d_y, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    CU(cudaMemcpy(f->state.data(), f->d_x + (size_t)n * C, (size_t)K * C * sizeof(float), cudaMemcpyDeviceToHost));
+    return FMGPU_OK;
+}
+
+void fmgpu_agc_init(fmgpu_agc* g) { if (g) { g->target_power = 1.0f; g->current_gain = 0.1f; g->beta = 0.2f; } }
+
+int fmgpu_agc_process(fmgpu_agc* g, const float* x_host, float* y_host, int n) {
+    if (!g || !x_host || !y_host || n <= 0) return fail(FMGPU_ERR_ARG, "agc_process: bad argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(FMGPU_ERR_CUDA, "agc_process: no CUDA device (there is no CPU fallback)");
+    float2* d_x = nullptr; float* d_sum = nullptr;
+    CU(cudaMalloc((void**)&d_x, (size_t)n * sizeof(float2)));
+    cudaError_t e = cudaMalloc((void**)&d_sum, sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_x); return fail(FMGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    auto done = [&](cudaError_t err) { cudaFree(d_x); cudaFree(d_sum); return err == cudaSuccess ? FMGPU_OK : fail(FMGPU_ERR_CUDA, cudaGetErrorString(err)); };
+    if ((e = cudaMemcpy(d_x, x_host, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return done(e);
+    if ((e = fm::launch_agc_power_seq(d_x, n, d_sum, 0)) != cudaSuccess) return done(e);
+    float sum = 0.0f;
+    if ((e = cudaMemcpy(&sum, d_sum, sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) return done(e);
+    const float avg_power = sum / (float)n;                                              // agc.h:28
+    const float target_gain = std::sqrt(g->target_power / avg_power);                   // :15 (unguarded: 0 power -> inf, as the reference)
+    g->current_gain = g->current_gain + g->beta * (target_gain - g->current_gain);      // :16
+    if ((e = fm::launch_agc_scale(d_x, d_x, n, g->current_gain, 0)) != cudaSuccess) return done(e);
+    e = cudaMemcpy(y_host, d_x, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost);
+    return done(e);
+}
+
 // ---- PolyphaseUpsampler<T> (dsp/polyphase_filter.h:90-185) ----
 int fmgpu_polyphase_us_create(const float* b, int L, int K, int is_complex, fmgpu_polyphase** out) {
     if (!out || !b || L < 1 || K < 1) return fail(FMGPU_ERR_ARG, "polyphase_us_create: bad argument");

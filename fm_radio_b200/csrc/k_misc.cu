@@ -115,4 +115,71 @@ cudaError_t launch_polyphase_ds(const float* ext, const float* taps, float* y, i
     return cudaGetLastError();
 }
 
+// ---- stand-alone src/dsp filter classes (FIR_Filter is polyphase_ds_kernel with M = 1) ----
+// Hilbert_FIR_Filter<float>::process (dsp/hilbert_fir_filter.h:26-46): y[i] = { x delayed by (K-1)/2, FIR(x) };
+// ext = (K history samples) ++ x, so the delayed sample of output i is ext[i + 1 + (K-1)/2].
+__global__ void hilbert_pack_kernel(const float* __restrict__ ext, const float* __restrict__ fir, float2* __restrict__ y, int n, int mid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = make_float2(ext[i + 1 + mid], fir[i]);
+}
+
+// IIR_Filter<T>::process (dsp/iir_filter.h:40-69), direct form I, strictly sequential: one thread walks the block in the
+// reference's operation order -- y = 0; y += (xn[i] b[i] + yn[i] a[i]) for i = 0 .. K-1 -- with explicit roundings (no
+// contraction), so the result is bit-identical to the scalar program.  state = xn[K] ++ yn[K] (C floats per entry).
+template <int C>
+__global__ void iir_seq_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int K,
+                               const float* __restrict__ b, const float* __restrict__ a, float* __restrict__ state)
+{
+    extern __shared__ float s_iir[];                 // b[K], a[K], xn[K*C], yn[K*C]
+    float* sb = s_iir; float* sa = sb + K; float* xn = sa + K; float* yn = xn + K * C;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = 0; i < K; i++) { sb[i] = b[i]; sa[i] = a[i]; }
+    for (int i = 0; i < K * C; i++) { xn[i] = state[i]; yn[i] = state[K * C + i]; }
+    for (int t = 0; t < n; t++) {
+        for (int i = 0; i < (K - 1) * C; i++) xn[i] = xn[i + C];
+        for (int c = 0; c < C; c++) xn[(K - 1) * C + c] = x[(size_t)t * C + c];
+        float acc[C];
+        for (int c = 0; c < C; c++) acc[c] = 0.0f;
+        for (int i = 0; i < K; i++)
+            for (int c = 0; c < C; c++)
+                acc[c] = __fadd_rn(acc[c], __fadd_rn(__fmul_rn(xn[i * C + c], sb[i]), __fmul_rn(yn[i * C + c], sa[i])));
+        for (int c = 0; c < C; c++) y[(size_t)t * C + c] = acc[c];
+        for (int i = 0; i < (K - 2) * C; i++) yn[i] = yn[i + C];
+        if (K >= 2) for (int c = 0; c < C; c++) yn[(K - 2) * C + c] = acc[c];
+    }
+    for (int i = 0; i < K * C; i++) { state[i] = xn[i]; state[K * C + i] = yn[i]; }
+}
+
+cudaError_t launch_iir_seq(const float* x, float* y, int n, int K, const float* b, const float* a, float* state, int is_complex, cudaStream_t st)
+{
+    const size_t smem = (size_t)(2 * K + 2 * K * (is_complex ? 2 : 1)) * sizeof(float);
+    if (is_complex) iir_seq_kernel<2><<<1, 32, smem, st>>>(x, y, n, K, b, a, state);
+    else            iir_seq_kernel<1><<<1, 32, smem, st>>>(x, y, n, K, b, a, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hilbert_pack(const float* ext, const float* fir, float2* y, int n, int mid, cudaStream_t st)
+{
+    hilbert_pack_kernel<<<(n + 127) / 128, 128, 0, st>>>(ext, fir, y, n, mid);
+    return cudaGetLastError();
+}
+
+// AGC_Filter<cf32>::calculate_average_power (dsp/agc.h:21-30): the reference adds I*I + Q*Q sample by sample into one
+// float; one thread does exactly that (explicit roundings), so the gain matches the scalar program bit for bit.
+__global__ void agc_power_seq_kernel(const float2* __restrict__ x, int n, float* __restrict__ sum)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float acc = 0.0f;
+    for (int i = 0; i < n; i++) { const float2 v = x[i]; acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))); }
+    *sum = acc;
+}
+__global__ void agc_scale_kernel(const float2* __restrict__ x, float2* __restrict__ y, int n, float g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float2 v = x[i]; y[i] = make_float2(__fmul_rn(g, v.x), __fmul_rn(g, v.y)); }
+}
+cudaError_t launch_agc_power_seq(const float2* x, int n, float* sum, cudaStream_t st) { agc_power_seq_kernel<<<1, 32, 0, st>>>(x, n, sum); return cudaGetLastError(); }
+cudaError_t launch_agc_scale(const float2* x, float2* y, int n, float g, cudaStream_t st) { agc_scale_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, y, n, g); return cudaGetLastError(); }
+
 } // namespace fm

@@ -299,6 +299,28 @@ int  fmgpu_polyphase_ds_process(fmgpu_polyphase* f, const float* x_host, float* 
 int  fmgpu_polyphase_us_create(const float* b, int L, int K, int is_complex, fmgpu_polyphase** out);
 int  fmgpu_polyphase_us_process(fmgpu_polyphase* f, const float* x_host, float* y_host, int n_in);
 
+/* ---- the other src/dsp filter classes, stand-alone (host buffers in / out, the work on the device) ----------------
+ * FIR_Filter<T>(K)            dsp/fir_filter.h:9-88     y[i] = sum_k b[k] x[i - (K-1) + k]; state: the last K inputs
+ * Hilbert_FIR_Filter<float>(K) dsp/hilbert_fir_filter.h:13-47  taps by create_fir_hilbert; y[i] = { x[i - (K-1)/2], FIR(x)[i] } (cf32 out)
+ * IIR_Filter<T>(K)            dsp/iir_filter.h:5-89     direct form I, y = sum_i (xn[i] b[i] + yn[i] a[i]) in the reference's
+ *                                                       operation order (bit-identical to the scalar program); K >= 2
+ * AGC_Filter<cf32>            dsp/agc.h:6-31            block-wise gain: target_power, current_gain, beta are plain fields
+ * kind: FMGPU_FILTER_*; is_complex selects T = std::complex<float> (interleaved re, im) over float.  get_b / get_a return
+ * host arrays of K floats the caller fills, like get_b() / get_a() (a is NULL for the FIR kinds). */
+#define FMGPU_FILTER_FIR     0
+#define FMGPU_FILTER_HILBERT 1
+#define FMGPU_FILTER_IIR     2
+typedef struct fmgpu_dsp_filter fmgpu_dsp_filter;
+int  fmgpu_dsp_filter_create(int kind, int K, int is_complex, fmgpu_dsp_filter** out);
+void fmgpu_dsp_filter_destroy(fmgpu_dsp_filter* f);
+float* fmgpu_dsp_filter_get_b(fmgpu_dsp_filter* f);
+float* fmgpu_dsp_filter_get_a(fmgpu_dsp_filter* f);
+int  fmgpu_dsp_filter_get_K(const fmgpu_dsp_filter* f);
+int  fmgpu_dsp_filter_process(fmgpu_dsp_filter* f, const float* x_host, float* y_host, int n);   /* Hilbert: y_host holds n cf32 */
+typedef struct fmgpu_agc { float target_power, current_gain, beta; } fmgpu_agc;          /* defaults 1.0, 0.1, 0.2 (agc.h:9-11) */
+void fmgpu_agc_init(fmgpu_agc* g);
+int  fmgpu_agc_process(fmgpu_agc* g, const float* x_cf32_host, float* y_cf32_host, int n);
+
 /* ---- audio output helpers, stand-alone (host buffers; the in-chain version is FMGPU_CTL_AUDIO_PCM_RATE_HZ) ----
  * fmgpu_resample_linear = Resample(buf_in, buf_out) of audio/resampled_pcm_player.cpp:37-54 on stereo
  * Frame<float> arrays (2 floats per frame): linear interpolation at read positions j += (float)n_in/(float)n_out.
