@@ -138,6 +138,8 @@ EXPORTED_SYMBOLS = [
     "fmgpu_rds_device_fetch", "fmgpu_rds_device_counts", "fmgpu_rds_device_get_groups",
     "fmgpu_rds_device_get_bytes", "fmgpu_rds_device_get_db", "fmgpu_get_partition",
     "fmgpu_rds_get_db_ext", "fmgpu_rds_device_get_db_ext",
+    "fmgpu_dsp_filter_create", "fmgpu_dsp_filter_destroy", "fmgpu_dsp_filter_get_b", "fmgpu_dsp_filter_get_a", "fmgpu_dsp_filter_get_K",
+    "fmgpu_dsp_filter_process", "fmgpu_agc_init", "fmgpu_agc_process",
     "fmgpu_enqueue_cf32_device", "fmgpu_stream_wait_input_free",
     "fmgpu_chan_create", "fmgpu_chan_destroy", "fmgpu_chan_get_b", "fmgpu_chan_get_config", "fmgpu_chan_get_freqs",
     "fmgpu_chan_process_u8", "fmgpu_chan_enqueue_u8_device", "fmgpu_chan_feed_device",
@@ -239,6 +241,18 @@ def lib():
     L.fmgpu_rds_get_db.argtypes = [vp, C.POINTER(C.c_uint16), vp, vp, C.POINTER(C.c_uint8)]
     L.fmgpu_rds_get_db.restype = None
     L.fmgpu_rds_get_db_ext.argtypes = [vp, vp]
+    L.fmgpu_dsp_filter_create.argtypes = [ci, ci, ci, C.POINTER(vp)]
+    L.fmgpu_dsp_filter_destroy.argtypes = [vp]
+    L.fmgpu_dsp_filter_destroy.restype = None
+    L.fmgpu_dsp_filter_get_b.argtypes = [vp]
+    L.fmgpu_dsp_filter_get_b.restype = C.POINTER(C.c_float)
+    L.fmgpu_dsp_filter_get_a.argtypes = [vp]
+    L.fmgpu_dsp_filter_get_a.restype = C.POINTER(C.c_float)
+    L.fmgpu_dsp_filter_get_K.argtypes = [vp]
+    L.fmgpu_dsp_filter_process.argtypes = [vp, vp, vp, ci]
+    L.fmgpu_agc_init.argtypes = [vp]
+    L.fmgpu_agc_init.restype = None
+    L.fmgpu_agc_process.argtypes = [vp, vp, vp, ci]
     L.fmgpu_rds_get_db_ext.restype = None
     L.fmgpu_rds_device_get_db_ext.argtypes = [vp, ci, vp]
     L.fmgpu_get_partition.argtypes = [vp, C.POINTER(ci * 2)]
@@ -633,6 +647,88 @@ class RDSDecoder:
         e = RdsDbExt()
         self.L.fmgpu_rds_get_db_ext(self.h, C.byref(e))
         return e.as_dict()
+
+
+class _DspFilter:
+    """Common part of FIR_Filter / Hilbert_FIR_Filter / IIR_Filter (include/fmgpu.h fmgpu_dsp_filter_*)."""
+    KIND = 0
+
+    def __init__(self, K: int, is_complex: bool = False):
+        self.L = lib()
+        self.K, self.is_complex = K, bool(is_complex)
+        h = C.c_void_p()
+        _check(self.L.fmgpu_dsp_filter_create(self.KIND, K, int(self.is_complex), C.byref(h)), "fmgpu_dsp_filter_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fmgpu_dsp_filter_destroy(self.h)
+            self.h = None
+
+    def get_b(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.L.fmgpu_dsp_filter_get_b(self.h), shape=(self.K,))
+
+    def get_K(self) -> int:
+        return self.L.fmgpu_dsp_filter_get_K(self.h)
+
+    def _process(self, x, out_complex: bool) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64 if self.is_complex else np.float32)
+        y = np.zeros(x.size, np.complex64 if out_complex else np.float32)
+        _check(self.L.fmgpu_dsp_filter_process(self.h, x.ctypes.data, y.ctypes.data, x.size), "fmgpu_dsp_filter_process")
+        return y
+
+
+class FIRFilter(_DspFilter):
+    """dsp/fir_filter.h:9-88 FIR_Filter<T>(K): get_b(), get_K(), process(x) -> y."""
+    KIND = 0
+
+    def process(self, x) -> np.ndarray:
+        return self._process(x, self.is_complex)
+
+
+class HilbertFIRFilter(_DspFilter):
+    """dsp/hilbert_fir_filter.h:13-47 Hilbert_FIR_Filter<float>(K): process(x real) -> complex { delayed x, Hilbert(x) }."""
+    KIND = 1
+
+    def __init__(self, K: int):
+        super().__init__(K, False)
+
+    def process(self, x) -> np.ndarray:
+        return self._process(x, True)
+
+
+class IIRFilter(_DspFilter):
+    """dsp/iir_filter.h:5-89 IIR_Filter<T>(K): get_b(), get_a(), process(x) -> y (direct form I, the reference's operation order)."""
+    KIND = 2
+
+    def get_a(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.L.fmgpu_dsp_filter_get_a(self.h), shape=(self.K,))
+
+    def process(self, x) -> np.ndarray:
+        return self._process(x, self.is_complex)
+
+
+class _Agc(C.Structure):
+    _fields_ = [("target_power", C.c_float), ("current_gain", C.c_float), ("beta", C.c_float)]
+
+
+class AGCFilter:
+    """dsp/agc.h:6-31 AGC_Filter<std::complex<float>>: public fields target_power / current_gain / beta, process(x) -> y."""
+
+    def __init__(self):
+        self.L = lib()
+        self._g = _Agc()
+        self.L.fmgpu_agc_init(C.byref(self._g))
+
+    target_power = property(lambda self: self._g.target_power, lambda self, v: setattr(self._g, "target_power", v))
+    current_gain = property(lambda self: self._g.current_gain, lambda self, v: setattr(self._g, "current_gain", v))
+    beta = property(lambda self: self._g.beta, lambda self, v: setattr(self._g, "beta", v))
+
+    def process(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        y = np.zeros(x.size, np.complex64)
+        _check(self.L.fmgpu_agc_process(C.byref(self._g), x.ctypes.data, y.ctypes.data, x.size), "fmgpu_agc_process")
+        return y
 
 
 class PolyphaseDownsampler:

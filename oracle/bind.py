@@ -92,6 +92,12 @@ def lib(kind: str = "ref"):
         L.polyphase_ds_cf32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.polyphase_us_f32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.resample_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        for name in ("fir_f32", "fir_cf32"):
+            getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.hilbert_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        for name in ("iir_f32", "iir_cf32"):
+            getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.agc_cf32.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.frames_to_s16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.fft_mag_process.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         if kind == "port":

@@ -207,6 +207,50 @@ void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* 
     for (int c = 0; c < n_calls; c++) polyds_process(&f, x + (size_t)c*N_out*M*2, y + (size_t)c*N_out*2, N_out);
     polyds_free(&f);
 }
+/* dsp/fir_filter.h:9-88  FIR_Filter<T>(K): y[i] = sum_k b[k] X[i - (K-1) + k] over X = (last K inputs) ++ x, i.e. the
+ * decimator above with M = 1 (its head / tail split, :30-57, is again filtering over the concatenation). */
+void fmo_fir_f32(int K, const float* b, const float* x, float* y, int N, int n_calls) { fmo_polyphase_ds_f32(1, K, b, x, y, N, n_calls); }
+void fmo_fir_cf32(int K, const float* b, const float* x, float* y, int N, int n_calls) { fmo_polyphase_ds_cf32(1, K, b, x, y, N, n_calls); }
+/* dsp/hilbert_fir_filter.h:13-47  Hilbert_FIR_Filter<float>(K): taps by create_fir_hilbert (:21-22);
+ * y[i] = { X[i - (K-1) + (K-1)/2], FIR(X)[i] }  (real part = input delayed by (K-1)/2, :34-35, :43-44). */
+void fmo_hilbert_f32(int K, const float* x, float* y, int N, int n_calls) {
+    polyds f; polyds_init(&f, 1, K, 0); fmo_create_fir_hilbert(f.b, K);
+    float* im = (float*)malloc(sizeof(float)*(size_t)N);
+    float* hist = (float*)calloc((size_t)K, sizeof(float));
+    const int M = (K-1)/2;
+    for (int c = 0; c < n_calls; c++) {
+        const float* xc = x + (size_t)c*N;
+        polyds_process(&f, xc, im, N);
+        for (int i = 0; i < N; i++) {
+            const int j = i - (K-1) + M;                 /* index into this call's x; negative = history */
+            y[2*((size_t)c*N + i)] = j >= 0 ? xc[j] : hist[K + j];
+            y[2*((size_t)c*N + i) + 1] = im[i];
+        }
+        memcpy(hist, f.hist, sizeof(float)*(size_t)K);
+    }
+    free(im); free(hist); polyds_free(&f);
+}
+/* dsp/iir_filter.h:5-89  IIR_Filter<T>(K), direct form I, one sample at a time (:40-46):
+ *   push_x; y = sum_{i<K} (xn[i] b[i] + yn[i] a[i]) in that order; push_y (yn[K-1] stays 0). */
+static void iir_generic(int K, int C, const float* b, const float* a, const float* x, float* y, int N, int n_calls) {
+    float* xn = (float*)calloc((size_t)K*C, sizeof(float));
+    float* yn = (float*)calloc((size_t)K*C, sizeof(float));
+    for (size_t t = 0; t < (size_t)N*n_calls; t++) {
+        for (int i = 0; i < (K-1)*C; i++) xn[i] = xn[i+C];
+        for (int c = 0; c < C; c++) xn[(K-1)*C + c] = x[t*C + c];
+        for (int c = 0; c < C; c++) {
+            float acc = 0.0f;
+            for (int i = 0; i < K; i++) acc += (xn[i*C + c]*b[i] + yn[i*C + c]*a[i]);
+            y[t*C + c] = acc;
+        }
+        for (int i = 0; i < (K-2)*C; i++) yn[i] = yn[i+C];
+        for (int c = 0; c < C; c++) yn[(K-2)*C + c] = y[t*C + c];
+    }
+    free(xn); free(yn);
+}
+void fmo_iir_f32(int K, const float* b, const float* a, const float* x, float* y, int N, int n_calls) { iir_generic(K, 1, b, a, x, y, N, n_calls); }
+void fmo_iir_cf32(int K, const float* b, const float* a, const float* x, float* y, int N, int n_calls) { iir_generic(K, 2, b, a, x, y, N, n_calls); }
+
 /* audio/resampled_pcm_player.cpp:37-54  Resample(buf_in, buf_out) on stereo Frame<float> arrays:
  * the read position j walks in float (j += step), j0 = (int)j, k = j - j0, the last frame is held;
  * out = f0*(1-k) + f1*k with one rounding per Frame operator (audio/frame.h:10-16, 42-49). */
@@ -357,6 +401,12 @@ static void agc_process(agc_t* g, c32* x, int N) {
     const float target_gain = sqrtf(g->target_power/avg_power);
     g->current_gain = g->current_gain + g->beta*(target_gain - g->current_gain);
     for (int i = 0; i < N; i++) { x[i].re = g->current_gain*x[i].re; x[i].im = g->current_gain*x[i].im; }
+}
+
+void fmo_agc_cf32(float target_power, float beta, float gain0, const float* x, float* y, int N, int n_calls, float* gains_out) {
+    agc_t g = { target_power, gain0, beta };
+    memcpy(y, x, sizeof(float)*2*(size_t)N*n_calls);
+    for (int c = 0; c < n_calls; c++) { agc_process(&g, (c32*)y + (size_t)c*N, N); if (gains_out) gains_out[c] = g.current_gain; }
 }
 
 /* fm_demod/pll_mixer.cpp:12-21 */

@@ -76,6 +76,13 @@ void fmo_polyphase_ds_f32(int M, int K, const float* b, const float* x, float* y
 void fmo_polyphase_ds_cf32(int M, int K, const float* b, const float* x, float* y, int N_out, int n_calls);
 void fmo_polyphase_us_f32(int L, int K, const float* b, const float* x, float* y, int N_in, int n_calls);
 void fmo_resample_linear(const float* in, int n_in, float* out, int n_out);
+/* stand-alone src/dsp filter classes, n_calls consecutive blocks of N samples through one object (state carried) */
+void fmo_fir_f32(int K, const float* b, const float* x, float* y, int N, int n_calls);
+void fmo_fir_cf32(int K, const float* b, const float* x, float* y, int N, int n_calls);
+void fmo_hilbert_f32(int K, const float* x, float* y_cf32, int N, int n_calls);
+void fmo_iir_f32(int K, const float* b, const float* a, const float* x, float* y, int N, int n_calls);
+void fmo_iir_cf32(int K, const float* b, const float* a, const float* x, float* y, int N, int n_calls);
+void fmo_agc_cf32(float target_power, float beta, float gain0, const float* x, float* y, int N, int n_calls, float* gains_out);
 void fmo_frames_to_s16(const float* frames, size_t n_frames, int16_t* out);
 void fmo_fft_f64(const float* x_cf32, double* y_c64, int n, int fftshift);
 void fmo_fft_mag_process(int mode, float beta, const float* x_cf32, float* y, int n);

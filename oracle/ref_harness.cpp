@@ -25,6 +25,10 @@
 #include "fm_demod/bpsk_synchroniser.h"
 #undef private
 #include "dsp/filter_designer.h"
+#include "dsp/fir_filter.h"
+#include "dsp/hilbert_fir_filter.h"
+#include "dsp/iir_filter.h"
+#include "dsp/agc.h"
 #include "audio/frame.h"
 #include "dsp/calculate_fft_mag.h"
 #include "dsp/fftshift.h"
@@ -307,6 +311,41 @@ void fmref_polyphase_us_f32(int L, int K, const float* b, const float* x, float*
 }
 
 // audio/resampled_pcm_player.cpp:37-54: the reference's own Resample(), compiled from its source file.
+// dsp/fir_filter.h, hilbert_fir_filter.h, iir_filter.h, agc.h stand-alone: n_calls consecutive blocks through ONE object.
+void fmref_fir_f32(int K, const float* b, const float* x, float* y, int N, int n_calls) {
+    FIR_Filter<float> f(K);
+    std::memcpy(f.get_b(), b, sizeof(float)*K);
+    for (int c = 0; c < n_calls; c++) f.process(x + (size_t)c*N, y + (size_t)c*N, N);
+}
+void fmref_fir_cf32(int K, const float* b, const float* x, float* y, int N, int n_calls) {
+    FIR_Filter<std::complex<float>> f(K);
+    std::memcpy(f.get_b(), b, sizeof(float)*K);
+    auto* xc = (const std::complex<float>*)x; auto* yc = (std::complex<float>*)y;
+    for (int c = 0; c < n_calls; c++) f.process(xc + (size_t)c*N, yc + (size_t)c*N, N);
+}
+void fmref_hilbert_f32(int K, const float* x, float* y, int N, int n_calls) {
+    Hilbert_FIR_Filter<float> f(K);
+    auto* yc = (std::complex<float>*)y;
+    for (int c = 0; c < n_calls; c++) f.process(x + (size_t)c*N, yc + (size_t)c*N, N);
+}
+void fmref_iir_f32(int K, const float* b, const float* a, const float* x, float* y, int N, int n_calls) {
+    IIR_Filter<float> f(K);
+    std::memcpy(f.get_b(), b, sizeof(float)*K); std::memcpy(f.get_a(), a, sizeof(float)*K);
+    for (int c = 0; c < n_calls; c++) f.process(x + (size_t)c*N, y + (size_t)c*N, N);
+}
+void fmref_iir_cf32(int K, const float* b, const float* a, const float* x, float* y, int N, int n_calls) {
+    IIR_Filter<std::complex<float>> f(K);
+    std::memcpy(f.get_b(), b, sizeof(float)*K); std::memcpy(f.get_a(), a, sizeof(float)*K);
+    auto* xc = (const std::complex<float>*)x; auto* yc = (std::complex<float>*)y;
+    for (int c = 0; c < n_calls; c++) f.process(xc + (size_t)c*N, yc + (size_t)c*N, N);
+}
+void fmref_agc_cf32(float target_power, float beta, float gain0, const float* x, float* y, int N, int n_calls, float* gains_out) {
+    AGC_Filter<std::complex<float>> g;
+    g.target_power = target_power; g.beta = beta; g.current_gain = gain0;
+    auto* xc = (const std::complex<float>*)x; auto* yc = (std::complex<float>*)y;
+    for (int c = 0; c < n_calls; c++) { g.process(xc + (size_t)c*N, yc + (size_t)c*N, N); if (gains_out) gains_out[c] = g.current_gain; }
+}
+
 void fmref_resample_linear(const float* in, int n_in, float* out, int n_out) {
     Resample(tcb::span<const Frame<float>>((const Frame<float>*)in, (size_t)n_in),
              tcb::span<Frame<float>>((Frame<float>*)out, (size_t)n_out));

@@ -333,3 +333,66 @@ def test_device_rds_database_flags_clock_and_programme_type_name():
             chk.process_u8(caps[1, 2 * H.B * k:2 * H.B * (k + 1)])
         assert g.rds_db_ext(1) == chk.db_ext() and g.rds_db(1) == chk.db()
     g.close()
+
+
+def test_dsp_filter_classes_match_checker_and_reference():
+    """The stand-alone src/dsp classes behind the C-ABI (fmgpu_dsp_filter_*, fmgpu_agc_*): FIR_Filter, Hilbert_FIR_Filter,
+    IIR_Filter, AGC_Filter, several consecutive blocks through one object (state carried), including blocks shorter than
+    the filter's history.  IIR and AGC run the reference's operation order: bit-identical to the restatement; the FIR
+    sums differ from it by FMA contraction only."""
+    rng = np.random.default_rng(7)
+    libs = [bind.lib(k) for k in H.cpu_checker_kinds()]          # port first, then the compiled reference where present
+    for (K, N, calls) in ((65, 100, 3), (65, 20, 6), (33, 32, 4), (8, 1, 9), (3, 257, 2), (128, 4096, 2)):
+        b = rng.standard_normal(K).astype(np.float32)
+        for cplx in (False, True):
+            C, dt = (2, np.complex64) if cplx else (1, np.float32)
+            x = rng.standard_normal(C * N * calls).astype(np.float32)
+            xs = x.view(dt)
+            f = fm.FIRFilter(K, cplx)
+            assert f.get_K() == K
+            f.get_b()[:] = b
+            got = np.concatenate([f.process(xs[c * N:(c + 1) * N]) for c in range(calls)])
+            for L in libs:
+                ref = np.zeros_like(x)
+                (L.fir_cf32 if cplx else L.fir_f32)(K, b.ctypes.data, x.ctypes.data, ref.ctypes.data, N, calls)
+                assert np.abs(got - ref.view(dt)).max() <= 1e-5 * np.sqrt(K), (K, N, cplx)
+            bi = (rng.standard_normal(K) / K).astype(np.float32)
+            ai = (rng.standard_normal(K) * 0.4 / K).astype(np.float32)
+            g = fm.IIRFilter(K, cplx)
+            g.get_b()[:] = bi
+            g.get_a()[:] = ai
+            got = np.concatenate([g.process(xs[c * N:(c + 1) * N]) for c in range(calls)])
+            for n_lib, L in enumerate(libs):
+                ref = np.zeros_like(x)
+                (L.iir_cf32 if cplx else L.iir_f32)(K, bi.ctypes.data, ai.ctypes.data, x.ctypes.data, ref.ctypes.data, N, calls)
+                if n_lib == 0:
+                    assert np.array_equal(got, ref.view(dt)), (K, N, cplx)
+                else:
+                    assert np.abs(got - ref.view(dt)).max() <= 1e-5, (K, N, cplx)
+        if K % 2 == 1:
+            x = rng.standard_normal(N * calls).astype(np.float32)
+            hf = fm.HilbertFIRFilter(K)
+            assert np.array_equal(hf.get_b(), fm.create_fir_hilbert(K))
+            got = np.concatenate([hf.process(x[c * N:(c + 1) * N]) for c in range(calls)])
+            for L in libs:
+                ref = np.zeros(2 * N * calls, np.float32)
+                L.hilbert_f32(K, x.ctypes.data, ref.ctypes.data, N, calls)
+                assert np.array_equal(got.real, ref[0::2]) and np.abs(got.imag - ref[1::2]).max() <= 1e-5 * np.sqrt(K), (K, N)
+        x = (rng.standard_normal(2 * N * calls) * 3.0).astype(np.float32)
+        a = fm.AGCFilter()
+        assert (a.target_power, a.current_gain, a.beta) == (1.0, np.float32(0.1), np.float32(0.2))
+        a.target_power = 0.5
+        got, gains = [], []
+        for c in range(calls):
+            got.append(a.process(x.view(np.complex64)[c * N:(c + 1) * N]))
+            gains.append(a.current_gain)
+        got = np.concatenate(got)
+        for n_lib, L in enumerate(libs):
+            ref, gref = np.zeros_like(x), np.zeros(calls, np.float32)
+            L.agc_cf32(0.5, 0.2, 0.1, x.ctypes.data, ref.ctypes.data, N, calls, gref.ctypes.data)
+            if n_lib == 0:
+                assert np.array_equal(np.float32(gains), gref) and np.array_equal(got, ref.view(np.complex64)), (K, N)
+            else:
+                assert np.allclose(np.float32(gains), gref, rtol=2e-6) and np.allclose(got, ref.view(np.complex64), rtol=2e-6, atol=1e-7)
+    with pytest.raises(fm.FMGPUError):
+        fm.IIRFilter(1)

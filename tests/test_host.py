@@ -17,7 +17,7 @@ from tests import helpers as H
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(H.ROOT, "include", "fmgpu.h")).read()
-    declared = set(re.findall(r"\b(fmgpu_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(fmgpu_[A-Za-z0-9_]+)\s*\(", hdr))
     assert declared == set(api.EXPORTED_SYMBOLS), declared ^ set(api.EXPORTED_SYMBOLS)
     L = C.CDLL(api.LIB_PATH)
     for name in sorted(declared):

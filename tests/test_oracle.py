@@ -143,3 +143,45 @@ def test_port_polyphase_matches_reference():
         Lr.polyphase_us_f32(L, K, b.ctypes.data, x.ctypes.data, ya.ctypes.data, n_in, calls)
         Lp.polyphase_us_f32(L, K, b.ctypes.data, x.ctypes.data, yb.ctypes.data, n_in, calls)
         assert np.abs(ya - yb).max() < 1e-4
+
+
+def _dsp_cases():
+    # (K, N per call, calls): blocks shorter than the history (N < K - 1), equal to it, and long ones
+    return ((65, 100, 3), (65, 20, 6), (33, 32, 4), (8, 1, 9), (3, 257, 2))
+
+
+@pytest.mark.skipif(not bind.available("ref"), reason="oracle/_ref not built")
+def test_port_dsp_filter_classes_match_reference():
+    """FIR_Filter / Hilbert_FIR_Filter / IIR_Filter / AGC_Filter (dsp/fir_filter.h, hilbert_fir_filter.h, iir_filter.h,
+    agc.h), several consecutive blocks through one object: the restatement against the reference's own classes."""
+    Lr, Lp = bind.lib("ref"), bind.lib("port")
+    rng = np.random.default_rng(7)
+    for (K, N, calls) in _dsp_cases():
+        b = rng.standard_normal(K).astype(np.float32)
+        for cplx in (False, True):
+            C = 2 if cplx else 1
+            x = rng.standard_normal(C * N * calls).astype(np.float32)
+            ya, yb = np.zeros_like(x), np.zeros_like(x)
+            (Lr.fir_cf32 if cplx else Lr.fir_f32)(K, b.ctypes.data, x.ctypes.data, ya.ctypes.data, N, calls)
+            (Lp.fir_cf32 if cplx else Lp.fir_f32)(K, b.ctypes.data, x.ctypes.data, yb.ctypes.data, N, calls)
+            assert np.abs(ya - yb).max() < 1e-4, (K, N, cplx)
+            # a stable IIR of order K - 1: poles well inside the unit circle
+            bi = (rng.standard_normal(K) / K).astype(np.float32)
+            ai = (rng.standard_normal(K) * 0.4 / K).astype(np.float32)
+            ya, yb = np.zeros_like(x), np.zeros_like(x)
+            (Lr.iir_cf32 if cplx else Lr.iir_f32)(K, bi.ctypes.data, ai.ctypes.data, x.ctypes.data, ya.ctypes.data, N, calls)
+            (Lp.iir_cf32 if cplx else Lp.iir_f32)(K, bi.ctypes.data, ai.ctypes.data, x.ctypes.data, yb.ctypes.data, N, calls)
+            assert np.abs(ya - yb).max() < 1e-5, (K, N, cplx)
+        if K % 2 == 1:
+            x = rng.standard_normal(N * calls).astype(np.float32)
+            ya, yb = np.zeros(2 * N * calls, np.float32), np.zeros(2 * N * calls, np.float32)
+            Lr.hilbert_f32(K, x.ctypes.data, ya.ctypes.data, N, calls)
+            Lp.hilbert_f32(K, x.ctypes.data, yb.ctypes.data, N, calls)
+            assert np.array_equal(ya[0::2], yb[0::2])            # the delayed input: a copy
+            assert np.abs(ya - yb).max() < 1e-4, (K, N)
+        x = (rng.standard_normal(2 * N * calls) * 3.0).astype(np.float32)
+        ya, yb = np.zeros_like(x), np.zeros_like(x)
+        ga, gb = np.zeros(calls, np.float32), np.zeros(calls, np.float32)
+        Lr.agc_cf32(0.5, 0.2, 0.1, x.ctypes.data, ya.ctypes.data, N, calls, ga.ctypes.data)
+        Lp.agc_cf32(0.5, 0.2, 0.1, x.ctypes.data, yb.ctypes.data, N, calls, gb.ctypes.data)
+        assert np.allclose(ga, gb, rtol=2e-6) and np.allclose(ya, yb, rtol=2e-6, atol=1e-7)
