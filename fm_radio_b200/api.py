@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfmgpu.so")
+LIB_PATH = os.environ.get("FMGPU_LIB") or os.path.join(HERE, "libfmgpu.so")     # FMGPU_LIB: an A/B build (fm_radio_b200/build.py)
 
 
 class FMGPUError(RuntimeError):

@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libfmgpu.so")
+LIB = os.environ.get("FMGPU_BUILD_OUT") or os.path.join(HERE, "libfmgpu.so")        # FMGPU_BUILD_OUT + FMGPU_NVCC_EXTRA: A/B builds
 CU_SOURCES = ["fmgpu.cu", "k1_fir4_discrim.cu", "k1_toeplitz_i8.cu", "k2_mpx.cu", "k3_pll.cu", "k4_mix_fir.cu", "k5_bpsk.cu", "k6_rds.cu", "k7_audio_pcm.cu", "k_fft.cu", "k_misc.cu", "chan.cu"]
 CPP_SOURCES = ["filter_designer.cpp", "rds_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -40,14 +40,15 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    extra = os.environ.get("FMGPU_NVCC_EXTRA", "").split()
+    objdir = os.path.join(HERE, "build" + ("_" + "".join(c for c in "_".join(extra) if c.isalnum() or c == "_") if extra else ""))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     log = []
     for src in CU_SOURCES + CPP_SOURCES:
         obj = os.path.join(objdir, src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:

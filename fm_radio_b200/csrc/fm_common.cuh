@@ -149,7 +149,8 @@ struct K3Params {
     int n;                      // B/8
     int n_streams;
     int keep;
-    int exact;                  // 1: the exact body only (9 / 7-op chain); 0: the fast pass with exact redo (k3_pll.cu)
+    int exact;                  // 0: fast pass, helper-warp version when the grid fits rec_sms; 1: the exact body only; 2 / 3: force the one-warp / helper-warp fast pass
+    int rec_sms;                // SMs of the partition the kernel runs on (0: unknown)
 };
 
 struct K4Params {

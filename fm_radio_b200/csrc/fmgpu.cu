@@ -96,7 +96,7 @@ struct fmgpu_demod {
     int k1t_off[3] = { 0, 0, 0 }; float k1t_w[3] = { 0, 0, 0 };
     int last_input_kind = 0;       // 0 none yet, 1 u8, 2 cf32
     int k1t_shape = 1;             // 3 CTAs/SM (measured 0.0574 vs 0.0627 ms for the 2-CTA shape, tools/k1t_probe.cu)
-    bool k5_literal = false, k3_exact = false, k4_v1 = false;
+    bool k5_literal = false, k3_exact = false, k4_v1 = false, k3_single = false, k3_duo = false;
     // CUDA-graph replay of small blocks (enqueue_chain)
     cudaStream_t stG = nullptr;
     bool use_graph = false, last_was_graph = false;
@@ -301,6 +301,8 @@ int alloc_all(fmgpu_demod* h) {
     if (const char* e = std::getenv("FMGPU_GRAPH")) h->use_graph = std::atoi(e) != 0;
     h->k5_literal = std::getenv("FMGPU_K5_LITERAL") != nullptr;
     h->k3_exact = std::getenv("FMGPU_K3_EXACT") != nullptr;
+    h->k3_single = std::getenv("FMGPU_K3_SINGLE") != nullptr;
+    h->k3_duo = std::getenv("FMGPU_K3_DUO") != nullptr;
     h->k4_v1 = std::getenv("FMGPU_K4_V1") != nullptr;
     if (const char* e = std::getenv("FMGPU_K1T_SHAPE")) h->k1t_shape = std::atoi(e);
     {
@@ -546,7 +548,7 @@ int enqueue_chain_on(fmgpu_demod* h, const void* iq_dev, bool u8, bool wait_H, c
         p.int_KTs = 0.1f * Ts; p.Kp = 0.01f;
         p.f_center = -19000.0f; p.f_gain = -100.0f; p.mixer_KTs = Ts;
         p.agc_target = 1.0f; p.agc_beta = 0.2f;
-        p.n = h->n8; p.n_streams = h->S; p.keep = keep; p.exact = h->k3_exact ? 1 : 0;
+        p.n = h->n8; p.n_streams = h->S; p.keep = keep; p.exact = h->k3_exact ? 1 : (h->k3_single ? 2 : (h->k3_duo ? 3 : 0)); p.rec_sms = h->sms_rec > 0 ? h->sms_rec : h->n_sm_fir;
         if (prof) CU(cudaEventRecord(prof[3], stB));
         CU(fm::launch_k3(sl.theta, sl.power, h->pll_state, sl.pll_dt, h->dbg.pll_raw, h->dbg.pll_pi, p, stB));
         if (prof) CU(cudaEventRecord(prof[4], stB));
@@ -1219,6 +1221,8 @@ long long fmgpu_launch_count(fmgpu_demod* h) { return h ? h->launches : 0; }
 //   "k1_fp32"     1: the u8 FIR + discriminator on the FP32 FMA pipe (k1_fir4_discrim_u8) instead of the tensor cores
 //   "k5_literal"  1: the BPSK synchroniser's per-sample loop instead of the symbol-wise loop (identical bits)
 //   "k3_exact"    1: the pilot PLL's exact body only, without the fast pass (k3_pll.cu)
+//   "k3_single"   1: always the fast pass in one warp;  "k3_duo" 1: always recurrence warp + helper warp (bit-identical; by default
+//                 the helper-warp version runs when its grid fits the recurrence partition one CTA per SM, k3_pll.cu)
 //   "graph"       1 / 0: force the CUDA-graph replay of the per-block chain on / off (default: on for small launch-bound blocks)
 //   "k4_v1"       1: the mixdown + FIR kernel reads its FIR taps from shared memory (first version) instead of the constant bank
 int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
@@ -1229,6 +1233,8 @@ int fmgpu_set_option(fmgpu_demod* h, const char* name, int value) {
         h->use_k1t = value == 0;
     } else if (n == "k5_literal") h->k5_literal = value != 0;
     else if (n == "k3_exact") h->k3_exact = value != 0;
+    else if (n == "k3_single") h->k3_single = value != 0;
+    else if (n == "k3_duo") h->k3_duo = value != 0;
     else if (n == "k4_v1") h->k4_v1 = value != 0;
     else if (n == "graph") h->use_graph = value != 0;
     else return fail(FMGPU_ERR_ARG, "set_option: unknown option");

@@ -396,3 +396,27 @@ def test_dsp_filter_classes_match_checker_and_reference():
                 assert np.allclose(np.float32(gains), gref, rtol=2e-6) and np.allclose(got, ref.view(np.complex64), rtol=2e-6, atol=1e-7)
     with pytest.raises(fm.FMGPUError):
         fm.IIRFilter(1)
+
+
+@pytest.mark.parametrize("S,bs,keep", [(3, 65536, True), (37, 8192, False), (2, 1024, True)])
+def test_k3_helper_warp_version_equals_single_warp_fast_pass(S, bs, keep):
+    """k3_pll_duo (recurrence warp + helper warp that prepares the detector increments one group ahead) against the
+    single-warp fast pass: the recurrence warp's arithmetic is the same, so every output is bit-identical -- from the
+    first block (acquisition: every group redone by the exact body) through lock; ragged stream counts leave dead lanes
+    in the last CTA, and a silent block in the middle poisons the loop (the CTA's fallback path) the same way in both."""
+    nblk = {65536: 56, 8192: 40, 1024: 64}[bs]
+    caps = np.stack([synth.synth_u8_numpy(bs * nblk, synth.StreamParams.for_stream(200 + (s % 5))) for s in range(S)])
+    if bs == 8192:
+        caps[1, 2 * bs * 20:2 * bs * 21] = 127                     # stream 1: one silent block -> non-finite AGC gain from then on
+    a = fm.FMDemod(bs, S, keep_intermediates=keep)
+    b = fm.FMDemod(bs, S, keep_intermediates=keep)
+    a.set_option("k3_duo", 1)                                      # by default launch_k3 picks by grid size
+    b.set_option("k3_single", 1)
+    bufs = [Buf.PLL_DT, Buf.AUDIO_OUT, Buf.RDS_PRED_SYM] + ([Buf.PLL_RAW_PHASE_ERROR, Buf.PLL_LPF_PHASE_ERROR] if keep else [])
+    for k in range(nblk):
+        blk = np.ascontiguousarray(caps[:, 2 * bs * k:2 * bs * (k + 1)])
+        a.process_u8(blk); b.process_u8(blk)
+        for s in (0, S // 2, S - 1):
+            for buf in bufs:
+                assert np.array_equal(a.get(buf, s), b.get(buf, s), equal_nan=True), (k, s, buf)
+    a.close(); b.close()
