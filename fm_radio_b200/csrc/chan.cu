@@ -210,7 +210,7 @@ chan_mma_i8(const __grid_constant__ ChanMmaParams p)
 //                          polynomial sine, times one factor per (tile, slot) that is +-1 on the fs_out / 256 raster.
 //                          (History: one epilogue warp per SM sub-partition and a branch per channel ran at IPC 0.2
 //                          and bounded the kernel, 51 us; two polynomial sines per output sample, 41.8 us with the
-//                          epilogue issuing 2/3 of the kernel's 18.6 M warp instructions -- ncu, profiles/r2z_ncu_summary.md.)
+//                          epilogue issuing 2/3 of the kernel's 18.6 M warp instructions -- ncu, profiles/r2z2_ncu_summary.md.)
 // The three digit planes of G sit side by side in shared memory, so each K step is ONE tcgen05.mma of N = 192 (100 clocks
 // measured, tools/umma_rate.cu) instead of three of N = 64 (3 x 50: small-N MMAs have a ~50-clock floor).
 // All hand-offs are mbarriers (full / empty per stage, acc_full / acc_empty per accumulator buffer).
