@@ -8,7 +8,7 @@
  *
  * PARITY PIN: the reference has no golden vectors of its own, so this
  * restatement is pinned against the unmodified reference compiled in place (oracle/_ref/libfmref.so,
- * see oracle/ref_harness.cpp) by tests/test_oracle_vs_reference.py, and against the golden fixtures
+ * see oracle/ref_harness.cpp) by tests/test_oracle.py, and against the golden fixtures
  * under tests/golden/ that were generated from that library by tests/golden/make_golden.py.
  *
  * The exported functions mirror the harness (prefix fmo_ instead of fmref_) so one Python binding
