@@ -581,7 +581,7 @@ def main():
                          "20.48 MS/s capture, channels sharded over the GPUs, NCCL broadcast of the capture (configs 4 / 5)")
     ap.add_argument("--stations", type=int, default=100)
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
-    ap.add_argument("--depth", type=int, default=4, help="pipeline depth (blocks in flight)")
+    ap.add_argument("--depth", type=int, default=3, help="pipeline depth = ring slots = blocks in flight (3: the chain's latency is 2.7 steps; deeper rings let the first stages run ahead and lengthen the drain of short runs)")
     ap.add_argument("--input-blocks", type=int, default=24, help="distinct, CONTINUOUS input blocks per stream kept in HBM (24 = 1.5 s of signal, 3.2 GB)")
     ap.add_argument("--audio-pcm-rate", type=int, default=48000, help="audio output stage K7: resample GetAudioOut to this rate + int16 PCM (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -237,14 +237,10 @@ bool create_partitioned_streams(fmgpu_demod* h, int prio_hi) {
     if (p_cuGreenCtxCreate(&g_rec, d_rec, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     if (p_cuGreenCtxCreate(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(g_rec); return false; }
     CUstream a = nullptr, a2 = nullptr, pp = nullptr, b = nullptr, c = nullptr, d = nullptr, e2 = nullptr;
-    // FIR-partition stream priorities (experiment, FMGPU_FIR_PRIO=1): later stages first, so that a block that is further
-    // along drains before a younger one starts -- shortens the chain's latency under load (the fill + drain of short runs)
-    const bool graded = std::getenv("FMGPU_FIR_PRIO") != nullptr;
-    const int pr_k1 = 0, pr_k2 = graded ? std::max(prio_hi, -1) : 0, pr_k4 = graded ? std::max(prio_hi, -2) : 0;
-    const bool ok = p_cuGreenCtxStreamCreate(&a, g_rest, CU_STREAM_NON_BLOCKING, pr_k1) == CUDA_SUCCESS
-                 && p_cuGreenCtxStreamCreate(&a2, g_rest, CU_STREAM_NON_BLOCKING, pr_k2) == CUDA_SUCCESS
-                 && p_cuGreenCtxStreamCreate(&pp, std::getenv("FMGPU_K7_ON_REC") ? g_rec : g_rest, CU_STREAM_NON_BLOCKING, pr_k4) == CUDA_SUCCESS
-                 && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, pr_k4) == CUDA_SUCCESS
+    const bool ok = p_cuGreenCtxStreamCreate(&a, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&a2, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&pp, std::getenv("FMGPU_K7_ON_REC") ? g_rec : g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
+                 && p_cuGreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&b, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&d, g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
                  && p_cuGreenCtxStreamCreate(&e2, std::getenv("FMGPU_K6_ON_FIR") ? g_rest : g_rec, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
